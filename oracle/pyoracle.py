@@ -82,6 +82,7 @@ def lib():
         L.rdsp_oracle_chan_set_mode.argtypes = [C.c_void_p, C.POINTER(Params)]
         L.rdsp_oracle_chan_process.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p,
                                                C.c_size_t, C.c_void_p, C.c_size_t]
+        L.rdsp_oracle_chan_spec256_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rdsp_oracle_chan_read_spectrum.argtypes = [C.c_void_p, C.c_void_p]
         L.rdsp_oracle_chan_read_audio_spectrum.argtypes = [C.c_void_p, C.c_void_p]
         L.rdsp_oracle_chan_read_panadapter.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
@@ -164,6 +165,17 @@ class OracleChan:
         lib().rdsp_oracle_chan_process(self._h, nb, _ptr(iq), 2 * BLK, _ptr(out), 2 * BLK,
                                        _ptr(f32) if want_f32 else None, 2 * BLK)
         return (out, f32) if want_f32 else out
+
+    def spec256_raw(self, I: np.ndarray, Q: np.ndarray):
+        """K9 alone (no biquads) on int16 [n_blocks,128] I/Q -> list of (block_index, output[256])."""
+        I = np.ascontiguousarray(I, np.int16); Q = np.ascontiguousarray(Q, np.int16)
+        res = []
+        for k in range(I.shape[0]):
+            lib().rdsp_oracle_chan_spec256_raw(self._h, _ptr(I[k]), _ptr(Q[k]))
+            out, ready = self.read_spectrum()
+            if ready:
+                res.append((k, out))
+        return res
 
     def read_spectrum(self):
         out = np.zeros(256, np.uint16)

@@ -80,7 +80,8 @@ static int16_t q15_round(double v)
  *     A = (cI + cQ)/sqrt2 (applied to I),  B = (cQ - cI)/sqrt2 (applied to Q)
  *     = real / imaginary part of c * e^{-j45deg}; USB = A(I) - B(Q), LSB = A(I) + B(Q).
  *   AM: A = B = real low-pass (lo = -hi), envelope of (A(I), B(Q)).
- *   Band-pass bank: real taps 2*cI. */
+ *   Band-pass bank: real taps 2*cI.
+ *   Every designed pair is first scaled to unity gain at the centre of its pass-band. */
 static const double k_hil_band[RDSP_DEMOD_COUNT][2] = {
     { 100.0, 3600.0 },   /* LSB    */
     { 100.0, 3600.0 },   /* USB    */
@@ -96,6 +97,22 @@ static const double k_bp_band[RDSP_FILTER_COUNT][2] = {
     { 150.0, 3900.0 },   /* audioAM   "3.9 kHz" */
 };
 
+/* scale a designed pair to unity gain at the centre of its pass-band (a 129-tap window cannot reach
+ * unity for the narrow CW filters: its main lobe is wider than the band) */
+static void normalise_centre_gain(double *cI, double *cQ, int n, double lo, double hi, double fs)
+{
+    const double w = 3.1415926535897932384626433832795 * (hi / fs + lo / fs);
+    const double fCenter = 0.5 * (double)(n - 1);
+    double gr = 0.0, gi = 0.0;
+    for (int k = 0; k < n; k++) {
+        const double ang = w * ((double)k - fCenter);
+        gr += cI[k] * cos(ang) + cQ[k] * sin(ang);
+        gi += cQ[k] * cos(ang) - cI[k] * sin(ang);
+    }
+    const double g = sqrt(gr * gr + gi * gi);
+    for (int k = 0; k < n; k++) { cI[k] = cI[k] / g; cQ[k] = cQ[k] / g; }
+}
+
 static int16_t g_hil_i[RDSP_DEMOD_COUNT][NTAPS], g_hil_q[RDSP_DEMOD_COUNT][NTAPS], g_bp[RDSP_FILTER_COUNT][NTAPS];
 static int g_taps_ready = 0;
 
@@ -106,6 +123,7 @@ static void build_taps(void)
     const double rs2 = 0.70710678118654752440;
     for (int m = 0; m < RDSP_DEMOD_COUNT; m++) {
         rdsp_oracle_calc_cplx_fir(cI, cQ, NTAPS, k_hil_band[m][0], k_hil_band[m][1], RDSP_SAMPLE_RATE_HZ);
+        normalise_centre_gain(cI, cQ, NTAPS, k_hil_band[m][0], k_hil_band[m][1], RDSP_SAMPLE_RATE_HZ);
         for (int k = 0; k < NTAPS; k++) {
             if (m == RDSP_DEMOD_AM) {
                 g_hil_i[m][k] = q15_round(cI[k]);
@@ -118,6 +136,7 @@ static void build_taps(void)
     }
     for (int f = 0; f < RDSP_FILTER_COUNT; f++) {
         rdsp_oracle_calc_cplx_fir(cI, cQ, NTAPS, k_bp_band[f][0], k_bp_band[f][1], RDSP_SAMPLE_RATE_HZ);
+        normalise_centre_gain(cI, cQ, NTAPS, k_bp_band[f][0], k_bp_band[f][1], RDSP_SAMPLE_RATE_HZ);
         for (int k = 0; k < NTAPS; k++) g_bp[f][k] = q15_round(2.0 * cI[k]);
     }
     g_taps_ready = 1;
@@ -458,17 +477,13 @@ static void stage_conv(rdsp_oracle_chan_t *c, const int16_t *sp_L, const int16_t
     memcpy(out_R, float_buffer_R, sizeof(float_buffer_R));
 }
 
-/* a11 + K9: HP biquads (RadioDSP_SDR_RX.ino:75-78) + AudioAnalyzeFFT256IQ::update, analyze_fft256iq.cpp:65-118 */
-static void stage_spec256(rdsp_oracle_chan_t *c, const int16_t *iq)
+/* K9: AudioAnalyzeFFT256IQ::update, analyze_fft256iq.cpp:65-118, on one block per port */
+static void spec256_update(rdsp_oracle_chan_t *c, const int16_t *bi, const int16_t *bqv)
 {
-    int16_t bi[BLK], bqv[BLK];
     int16_t buffer[512] __attribute__((aligned(4)));
-    for (int n = 0; n < BLK; n++) { bi[n] = iq[2 * n]; bqv[n] = iq[2 * n + 1]; }
-    oracle_biquad_update(&c->bq_i, bi);
-    oracle_biquad_update(&c->bq_q, bqv);
     if (!c->have_prev) {                                             /* :73-77 */
-        memcpy(c->prev_i, bi, sizeof(bi));
-        memcpy(c->prev_q, bqv, sizeof(bqv));
+        memcpy(c->prev_i, bi, BLK * sizeof(int16_t));
+        memcpy(c->prev_q, bqv, BLK * sizeof(int16_t));
         c->have_prev = 1;
         return;
     }
@@ -492,8 +507,24 @@ static void stage_spec256(rdsp_oracle_chan_t *c, const int16_t *iq)
         for (int i = 0; i < 256; i++) c->output[255 - (i ^ 128)] = (uint16_t)oracle_sqrt_uint32_approx(c->sum[i]);
         c->outputflag = 1;
     }
-    memcpy(c->prev_i, bi, sizeof(bi));                               /* :114-117 */
-    memcpy(c->prev_q, bqv, sizeof(bqv));
+    memcpy(c->prev_i, bi, BLK * sizeof(int16_t));                    /* :114-117 */
+    memcpy(c->prev_q, bqv, BLK * sizeof(int16_t));
+}
+
+/* test hook: K9 alone on already separated I / Q blocks (no biquads), to pin it against the compiled reference */
+void rdsp_oracle_chan_spec256_raw(rdsp_oracle_chan_t *c, const int16_t *i_blk, const int16_t *q_blk)
+{
+    spec256_update(c, i_blk, q_blk);
+}
+
+/* a11 + K9: HP biquads (RadioDSP_SDR_RX.ino:75-78,155-156) feeding the IQ spectrum */
+static void stage_spec256(rdsp_oracle_chan_t *c, const int16_t *iq)
+{
+    int16_t bi[BLK], bqv[BLK];
+    for (int n = 0; n < BLK; n++) { bi[n] = iq[2 * n]; bqv[n] = iq[2 * n + 1]; }
+    oracle_biquad_update(&c->bq_i, bi);
+    oracle_biquad_update(&c->bq_q, bqv);
+    spec256_update(c, bi, bqv);
 }
 
 /* one AudioStream tick of the graph wired at RadioDSP_SDR_RX.ino:71-89 */

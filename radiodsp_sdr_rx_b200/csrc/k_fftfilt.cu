@@ -1,0 +1,150 @@
+// k_fftfilt.cu — K5 (+K8) + K7: FFT-256 overlap-save band-pass ("PBT") filter of the complex signal
+// L + jR, optional spectral-subtraction NR, f32 -> q15.
+//
+// Replaces doConvolutionalProcessing(), RDSP_convolutional.h:228-353 up to the DNR call:
+//   q15 -> f32 (:241-242), frame = [previous block | current block] (:256-285), forward FFT (:291),
+//   product with the pre-computed mask (:301), inverse FFT (:309), keep samples 128..255 (:314-318),
+//   f32 -> q15 with truncation + saturation (:346-347).
+// With nr_kind == SPECTRAL the product is replaced by the spectral subtraction of the backup sketch
+// (backup/RDSP_convolutional_spec.h:181-238, loop bounds restated as FFT_length): magnitudes, noise floor
+// from the mean of bins 30..180, one-pole tracker, subtract / floor, keep the phase.
+//
+// Mapping: one warp per channel, 8 points per lane, the whole forward FFT -> product -> inverse FFT chain
+// stays in registers (fft_f32_lanes.cuh) with warp-private shared memory exchanges.  The previous input
+// block is carried in registers across the blocks of one call and stored in HBM as the exact q15 values.
+// Channels whose NLMS DNR follows hand their f32 L signal to k_nlms through a scratch row.
+#include "rdsp_common.cuh"
+#include "fft_f32_lanes.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int WARPS = 8;
+
+__global__ void __launch_bounds__(WARPS * 32) k_fftfilt(FftFiltArgs a)
+{
+    __shared__ float2 s_tw[256];
+    __shared__ __align__(16) float2 s_buf[WARPS][FFT256_BUF];
+
+    for (int i = threadIdx.x; i < 256; i += WARPS * 32) s_tw[i] = a.tw256[i];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ch = blockIdx.x * WARPS + warp;
+    if (ch >= a.C) return;
+    float2 *buf = s_buf[warp];
+
+    const RdspChanParams p = a.par[ch];
+    const int kind = a.nr_stage ? p.nr_kind : 0;       // 0 off, 1 LMS (follows in k_nlms), 2 spectral
+    const bool spectral = (kind == 2);
+    const bool to_dnr = (kind == 1);
+
+    float2 mk[8];
+    if (!spectral) {
+        const float2 *mrow = a.masks + (size_t)p.mask_id * 256;
+#pragma unroll
+        for (int j = 0; j < 8; j++) mk[j] = mrow[lane + 32 * j];
+    }
+
+    // previous block: q15 words (L | R << 16) for samples lane + 32 j
+    uint32_t pw[4];
+    {
+        const uint32_t *lrow = reinterpret_cast<const uint32_t *>(a.last + (size_t)ch * 2 * RDSP_BLK);
+#pragma unroll
+        for (int j = 0; j < 4; j++) pw[j] = lrow[lane + 32 * j];
+    }
+    float nfloor = a.nfloor[ch];
+
+    for (int t = 0; t < a.T; t++) {
+        const size_t cb = (size_t)t * a.C + ch;
+        uint32_t cw[4];
+        if (a.in_mono) {
+            const uint16_t *src = reinterpret_cast<const uint16_t *>(a.in_mono + cb * RDSP_BLK);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const uint32_t s = src[lane + 32 * j]; cw[j] = s | (s << 16); }
+        } else {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(a.in_stereo + cb * 2 * RDSP_BLK);
+#pragma unroll
+            for (int j = 0; j < 4; j++) cw[j] = src[lane + 32 * j];
+        }
+        float2 v[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            v[j] = make_float2((float)lo16(pw[j]) / 32768.0f, (float)hi16(pw[j]) / 32768.0f);
+            v[4 + j] = make_float2((float)lo16(cw[j]) / 32768.0f, (float)hi16(cw[j]) / 32768.0f);
+            pw[j] = cw[j];
+        }
+
+        fft256_warp(lane, v, buf, s_tw);                   // v[j] = X[lane + 32 j]
+
+        if (!spectral) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = c_mul(v[j], mk[j]);
+        } else {
+            float mag[8], part = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                mag[j] = sqrtf(__fadd_rn(__fmul_rn(v[j].x, v[j].x), __fmul_rn(v[j].y, v[j].y)));
+                const int k = lane + 32 * j;
+                if (k >= 30 && k <= 180) part += mag[j];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            float th = part / 150.0f;
+            th = (float)((double)th * ((double)p.nr_spec_level * 1.5));
+            nfloor = __fadd_rn(nfloor, __fmul_rn(th - nfloor, 0.65f));
+            nfloor = nfloor > 0.0f ? nfloor : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float nm = mag[j] <= nfloor ? (float)((double)mag[j] * 0.2) : mag[j] - nfloor;
+                const float sc = mag[j] > 0.0f ? nm / mag[j] : 0.0f;     // keep the phase, new magnitude
+                v[j] = make_float2(v[j].x * sc, v[j].y * sc);
+            }
+        }
+
+        // inverse = conj, forward, conj, 1/N
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j].y = -v[j].y;
+        fft256_warp(lane, v, buf, s_tw);
+
+        // keep x[128 + lane + 32 h]; re-distribute so that each lane owns 4 consecutive samples
+#pragma unroll
+        for (int h = 0; h < 4; h++)
+            buf[lane + 32 * h] = make_float2(v[4 + h].x * (1.0f / 256.0f), -v[4 + h].y * (1.0f / 256.0f));
+        __syncwarp();
+        float2 o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = buf[4 * lane + i];
+        __syncwarp();
+
+        if (to_dnr) {
+            *reinterpret_cast<float4 *>(a.out_f32_L + cb * RDSP_BLK + 4 * lane) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
+        } else {
+            int4 q;
+            q.x = (int)mk16(f32_to_q15(o[0].x), f32_to_q15(o[0].y));
+            q.y = (int)mk16(f32_to_q15(o[1].x), f32_to_q15(o[1].y));
+            q.z = (int)mk16(f32_to_q15(o[2].x), f32_to_q15(o[2].y));
+            q.w = (int)mk16(f32_to_q15(o[3].x), f32_to_q15(o[3].y));
+            st_stream16(a.out_stereo + cb * 2 * RDSP_BLK + lane * 8, q);
+            if (a.dbg) {
+                float4 *dp = reinterpret_cast<float4 *>(a.dbg + cb * 2 * RDSP_BLK + lane * 8);
+                dp[0] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+                dp[1] = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+            }
+        }
+    }
+
+    {
+        uint32_t *lrow = reinterpret_cast<uint32_t *>(a.last + (size_t)ch * 2 * RDSP_BLK);
+#pragma unroll
+        for (int j = 0; j < 4; j++) lrow[lane + 32 * j] = pw[j];
+    }
+    if (spectral && lane == 0) a.nfloor[ch] = nfloor;
+}
+
+}  // namespace
+
+void launch_fftfilt(const FftFiltArgs &a, cudaStream_t st)
+{
+    k_fftfilt<<<(a.C + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(a);
+}

@@ -1,0 +1,112 @@
+// kernels.h — argument blocks and launchers of the sm_100a kernels (internal to librdsp_gpu.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rdsp_common.cuh"
+
+// K0+K1+K2 -----------------------------------------------------------------------------------
+struct FrontArgs {
+    const int16_t *iq;          // [T][C][128][2]
+    int16_t *out_mono;          // [T][C][128]       or nullptr
+    int16_t *out_stereo;        // [T][C][128][2]    or nullptr (front end is the last stage)
+    float *dbg;                 // [T][C][128][2]    or nullptr
+    int16_t *hist;              // [C][3][128] delay lines: I', Q', demodulated
+    const RdspChanParams *par;  // [C]
+    const int32_t *taps;        // [15][132]: hilbert_i[5], hilbert_q[5], bandpass[5]
+    int C, T;
+};
+void launch_front(const FrontArgs &a, cudaStream_t st);
+
+// K3 / K6: normalised LMS ----------------------------------------------------------------------
+struct NlmsArgs {
+    const int *list;            // channels to run (nullptr: 0..n_list-1)
+    int n_list;
+    int C, T;
+    const int16_t *in_q15;      // [T][C][128]  (notch) or nullptr
+    const float *in_f32;        // [T][C][128]  (DNR)   or nullptr
+    float *out_f32;             // [T][C][128]  error signal (notch)
+    int16_t *out_stereo;        // [T][C][128][2] 1.1*y, L = R (DNR)
+    float *dbg;                 // [T][C][128][2] or nullptr
+    float *coeff;               // [C][96] CMSIS order (index 0 multiplies the oldest sample)
+    float *prev;                // [C][128] previous input block (= de-correlation ring + FIR history)
+    float *energy;              // [C]
+    uint8_t *first;             // [C] 1 until the instance ran once (RDSP_noise_reduction.h:69 statics)
+    const RdspChanParams *par;
+    int mode;                   // 0 = notch (output error), 1 = DNR (output estimate)
+};
+void launch_nlms(const NlmsArgs &a, cudaStream_t st);
+
+// K4: AGC + output gain -------------------------------------------------------------------------
+struct AgcArgs {
+    const int16_t *in_q15;      // [T][C][128]
+    const float *in_f32;        // [T][C][128] used for channels with notch_on (if use_f32)
+    int16_t *out_mono;          // [T][C][128]    or nullptr
+    int16_t *out_stereo;        // [T][C][128][2] or nullptr
+    float *dbg;                 // [T][C][128][2] or nullptr
+    float *env;                 // [C]
+    const RdspChanParams *par;
+    int C, T;
+    int use_f32;                // notch stage present
+    int agc_stage;              // 0: only quantise (notch without AGC stage)
+    float target, max_gain, alpha_a;
+};
+void launch_agc(const AgcArgs &a, cudaStream_t st);
+
+// K5 (+K8) + K7 ---------------------------------------------------------------------------------
+struct FftFiltArgs {
+    const int16_t *in_mono;     // [T][C][128]     (L = R) or nullptr
+    const int16_t *in_stereo;   // [T][C][128][2]  or nullptr
+    int16_t *out_stereo;        // [T][C][128][2]
+    float *out_f32_L;           // [T][C][128] for channels whose DNR follows
+    float *dbg;                 // [T][C][128][2] or nullptr
+    int16_t *last;              // [C][128][2] previous input block (q15, exact)
+    float *nfloor;              // [C] spectral-NR noise floor
+    const float2 *masks;        // [n_masks][256]
+    const float2 *tw256;        // [256] (cos, sin)(2*pi*k/256)
+    const RdspChanParams *par;
+    int C, T;
+    int nr_stage;               // RDSP_STAGE_NR present
+};
+void launch_fftfilt(const FftFiltArgs &a, cudaStream_t st);
+
+// a11 + K9 --------------------------------------------------------------------------------------
+struct Spec256Args {
+    const int16_t *iq;          // [T][C][128][2]
+    int32_t *bq_state;          // [C][2][4]: bprev, aprev, sum, pad  for I and Q
+    int16_t *prev;              // [C][128][2] previous post-biquad block
+    uint32_t *sum;              // [C][256]
+    uint16_t *output;           // [C][256]
+    int C, T;
+    int have_prev;              // 0 on the very first tick
+    int count;                  // averaging counter at the first tick of this call
+    int naverage;
+    unsigned long long div_magic;   // ceil(2^div_shift / naverage), div_shift = 32 + ceil(log2 naverage):
+    int div_shift;                  // (magsq * div_magic) >> div_shift == magsq / naverage for magsq <= 2^31
+    const uint32_t *tw;         // [3072] twiddleCoef_4096_q15 as (cos | sin << 16) words
+    const int16_t *win;         // [256] Hann
+    int32_t b0, b1, b2, a1, a2; // Q30, feedback already negated
+};
+void launch_spec256(const Spec256Args &a, cudaStream_t st);
+
+// K10 -------------------------------------------------------------------------------------------
+struct Spec1024Args {
+    const int16_t *audio;       // [T][C][128][2] (L used)
+    int16_t *ring;              // [C][8][128] last blocks of L, slot = tick mod 8
+    uint16_t *output;           // [C][512]
+    int C, T;
+    unsigned long long tick0;   // global tick index of block 0 of this call
+    int any_fft;                // some tick of this call completes a 1024-sample frame
+    const uint32_t *tw;         // [3072]
+    const int16_t *win;         // [1024] Hann
+};
+void launch_spec1024(const Spec1024Args &a, cudaStream_t st);
+
+// K11 -------------------------------------------------------------------------------------------
+struct PanArgs {
+    const uint16_t *spec;       // [C][256]
+    uint16_t *view;             // [C][256] SpectrumView (state: SpectrumViewOld)
+    float *smeter;              // [C]
+    int ch_first, ch_count;
+};
+void launch_panadapter(const PanArgs &a, cudaStream_t st);
+

@@ -1,0 +1,104 @@
+// rdsp_common.cuh — shared device helpers and the HBM data layout of the batched receive chain.
+//
+// Layout conventions (all per handle, channel-major, see DESIGN.md "Data layout in HBM"):
+//   iq_in      int16 [n_blocks][C][128][2]   (I,Q interleaved = I2S frame order)
+//   audio_out  int16 [n_blocks][C][128][2]   (L,R interleaved)
+//   mono mids  int16 [n_blocks][C][128]
+//   f32 mids   float [n_blocks][C][128]
+//   per-channel state: one contiguous row per channel per stage (coalesced 128-bit accesses).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define RDSP_BLK        128
+#define RDSP_NTAPS      129
+#define RDSP_TAPS_PAD   132          // tap rows padded to a multiple of 4 words (LDS.128)
+#define RDSP_LMS_NTAPS  96
+#define RDSP_N_DEMOD    5
+#define RDSP_N_FILTER   5
+
+// per-channel parameters as the kernels see them (written by rdsp_gpu_set_mode)
+struct __align__(16) RdspChanParams {
+    int32_t mult_i;        // K0 AudioMixer4-style gain, 65536 = unity
+    int32_t mult_q;
+    float   out_gain;      // SDR.setOutputGain
+    float   mu_notch;      // K3 NLMS step size
+    float   mu_dnr;        // K6 NLMS step size
+    float   agc_alpha_d;   // K4 decay coefficient of the selected AGC mode
+    float   nr_spec_level; // K8 iNRLevel
+    int32_t mask_id;       // K5 row of the mask table
+    uint8_t demod;         // RDSP_DEMOD_*
+    uint8_t filter;        // RDSP_FILTER_*
+    uint8_t agc_mode;      // RDSP_AGC_*
+    uint8_t notch_on;
+    uint8_t nr_kind;       // RDSP_NR_* (0 when level == 0)
+    uint8_t pad[11];
+};
+static_assert(sizeof(RdspChanParams) == 48, "RdspChanParams layout");
+
+// ---- saturating / packed-q15 arithmetic (ARMv7E-M DSP instruction semantics) --------------
+__device__ __forceinline__ int32_t sat16(int32_t v) { return max(-32768, min(32767, v)); }
+__device__ __forceinline__ int32_t lo16(uint32_t a) { return (int32_t)(int16_t)(a & 0xFFFFu); }
+__device__ __forceinline__ int32_t hi16(uint32_t a) { return ((int32_t)a) >> 16; }
+__device__ __forceinline__ uint32_t mk16(int32_t lo, int32_t hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+
+__device__ __forceinline__ uint32_t SHADD16(uint32_t a, uint32_t b) { return mk16((lo16(a) + lo16(b)) >> 1, (hi16(a) + hi16(b)) >> 1); }
+__device__ __forceinline__ uint32_t SHSUB16(uint32_t a, uint32_t b) { return mk16((lo16(a) - lo16(b)) >> 1, (hi16(a) - hi16(b)) >> 1); }
+__device__ __forceinline__ uint32_t QADD16(uint32_t a, uint32_t b) { return mk16(sat16(lo16(a) + lo16(b)), sat16(hi16(a) + hi16(b))); }
+__device__ __forceinline__ uint32_t QSUB16(uint32_t a, uint32_t b) { return mk16(sat16(lo16(a) - lo16(b)), sat16(hi16(a) - hi16(b))); }
+__device__ __forceinline__ uint32_t QASX(uint32_t a, uint32_t b) { return mk16(sat16(lo16(a) - hi16(b)), sat16(hi16(a) + lo16(b))); }
+__device__ __forceinline__ uint32_t QSAX(uint32_t a, uint32_t b) { return mk16(sat16(lo16(a) + hi16(b)), sat16(hi16(a) - lo16(b))); }
+__device__ __forceinline__ uint32_t SHASX(uint32_t a, uint32_t b) { return mk16((lo16(a) - hi16(b)) >> 1, (hi16(a) + lo16(b)) >> 1); }
+__device__ __forceinline__ uint32_t SHSAX(uint32_t a, uint32_t b) { return mk16((lo16(a) + hi16(b)) >> 1, (hi16(a) - lo16(b)) >> 1); }
+// (cos + j sin) twiddle word times sample word, both products keep their top 16 bits
+__device__ __forceinline__ uint32_t CMULPACK(uint32_t c, uint32_t r)
+{
+    uint32_t re = (uint32_t)(lo16(c) * lo16(r)) + (uint32_t)(hi16(c) * hi16(r));   // SMUAD
+    uint32_t im = (uint32_t)(lo16(c) * hi16(r)) - (uint32_t)(hi16(c) * lo16(r));   // SMUSDX
+    return (im & 0xFFFF0000u) | (re >> 16);
+}
+
+// sqrt_uint32_approx of the Teensy Audio library: table seed + two Newton steps, 0 -> 0
+__constant__ uint16_t c_sqrt_guess[33] = {
+    55109, 38968, 27555, 19484, 13778, 9742, 6889, 4871, 3445, 2436, 1723, 1218, 862, 609, 431, 305,
+    216, 153, 108, 77, 54, 39, 27, 20, 14, 10, 7, 5, 4, 3, 2, 1, 0 };
+__device__ __forceinline__ uint32_t sqrt_u32_approx(uint32_t in)
+{
+    if (in == 0u) return 0u;
+    uint32_t n = c_sqrt_guess[__clz((int)in)];
+    n = ((in / n) + n) >> 1;
+    n = ((in / n) + n) >> 1;
+    return n;
+}
+
+// arm_float_to_q15: truncate toward zero, saturate
+__device__ __forceinline__ int32_t f32_to_q15(float v)
+{
+    float s = v * 32768.0f;
+    s = fminf(fmaxf(s, -40000.0f), 40000.0f);          // keeps the cast defined; NaN -> -40000 -> sat
+    if (v != v) s = 0.0f;
+    return sat16((int32_t)s);                           // cvt.rzi
+}
+
+// streaming (read-once / write-once) 128-bit global accesses
+__device__ __forceinline__ int4 ld_stream16(const void *p)
+{
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int2 ld_stream8(const void *p)
+{
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream16(void *p, int4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream8(void *p, int2 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.s32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}

@@ -1,0 +1,767 @@
+// rdsp_gpu.cu — the C ABI of include/rdsp_gpu.h: handle, per-channel state in HBM, parameter
+// bookkeeping and the per-tick kernel pipeline.  Host code only; the kernels are in k_*.cu.
+//
+// Pipeline of one rdsp_gpu_process_blocks(T) call (reference graph order, RadioDSP_SDR_RX.ino:71-89):
+//   spectrum path : k_spec256 (HP biquads + 256-pt IQ spectrum)                       on raw IQ
+//   audio path    : k_front (K0-K2) -> k_nlms<notch> (K3, listed channels) -> k_agc (K4)
+//                   -> k_fftfilt (K5/K8/K7) -> k_nlms<dnr> (K6, listed channels) -> k_spec1024 (K10)
+// Intermediates between kernels are int16 mono / f32 rows in handle-owned scratch (L2 resident at
+// the batch sizes of BASELINE.json); per-channel state makes one HBM round trip per call.
+#include "../../include/rdsp_gpu.h"
+#include "host_design.h"
+#include "kernels.h"
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#define RDSP_VERSION "rdsp-b200 0.1 (sm_100a)"
+
+namespace {
+
+std::string g_create_error;
+
+enum KernelKind { KK_FRONT = 0, KK_NOTCH, KK_AGC, KK_FFTFILT, KK_DNR, KK_SPEC256, KK_SPEC1024, KK_PAN, KK_COUNT };
+const char *const kKernelNames[KK_COUNT] = {"k_front", "k_nlms_notch", "k_agc", "k_fftfilt", "k_nlms_dnr",
+                                            "k_spec256", "k_spec1024", "k_panadapter"};
+
+struct ProfRec { int kind; cudaEvent_t e0, e1; };
+
+}  // namespace
+
+struct rdsp_gpu {
+    rdsp_gpu_config_t cfg;
+    int C = 0, maxT = 1;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    std::string err;
+
+    // parameters
+    std::vector<rdsp_chan_params_t> par;       // as set by the caller
+    std::vector<RdspChanParams> dpar;          // as the kernels see them
+    std::vector<int> dnr_old_level, notch_old_level;
+    bool par_dirty = true;
+    RdspChanParams *d_par = nullptr;
+    int *d_list_notch = nullptr, *d_list_dnr = nullptr;
+    int n_notch = 0, n_dnr = 0;
+
+    // coefficient tables
+    int16_t taps[15][RDSP_FIR_TAPS];
+    bool taps_dirty = true;
+    int32_t *d_taps = nullptr;
+    std::map<std::pair<float, float>, int> mask_ids;
+    std::vector<float> masks;                  // [n][512]
+    int masks_uploaded = 0, mask_cap = 0;
+    float2 *d_masks = nullptr;
+    uint32_t *d_tw = nullptr;
+    int16_t *d_win256 = nullptr, *d_win1024 = nullptr;
+    float2 *d_tw256 = nullptr;
+    int32_t bq[5];
+    float agc_alpha_a = 0.f, agc_alpha_d[4] = {0.f, 0.f, 0.f, 0.f};
+
+    // per-channel state
+    int16_t *d_fe_hist = nullptr;
+    float *d_nc_coeff = nullptr, *d_nc_prev = nullptr, *d_nc_energy = nullptr; uint8_t *d_nc_first = nullptr;
+    float *d_dn_coeff = nullptr, *d_dn_prev = nullptr, *d_dn_energy = nullptr; uint8_t *d_dn_first = nullptr;
+    float *d_agc_env = nullptr;
+    int16_t *d_conv_last = nullptr; float *d_nfloor = nullptr;
+    int32_t *d_bq_state = nullptr; int16_t *d_spec_prev = nullptr; uint32_t *d_spec_sum = nullptr; uint16_t *d_spec_out = nullptr;
+    int16_t *d_ring = nullptr; uint16_t *d_spec1024_out = nullptr;
+    uint16_t *d_view = nullptr; float *d_smeter = nullptr;
+
+    // scratch
+    int16_t *d_mid_a = nullptr, *d_mid_b = nullptr;
+    float *d_scr = nullptr, *d_dbg = nullptr;
+    int16_t *d_in_stage = nullptr, *d_out_stage = nullptr;
+
+    // tick bookkeeping (uniform over channels)
+    int spec_have_prev = 0, spec_count = 0;
+    unsigned long long tick = 0;
+    std::vector<uint8_t> spec_ready, spec1024_ready;
+
+    // instrumentation
+    uint64_t launches = 0;
+    bool profiling = false;
+    std::vector<ProfRec> prof_pending;
+    double prof_ms[KK_COUNT] = {0};
+    uint64_t prof_n[KK_COUNT] = {0};
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            h->err = b_;                                                                           \
+            return RDSP_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(T **p, size_t n)
+{
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemset(*p, 0, n * sizeof(T));
+}
+
+bool has(const rdsp_gpu *h, uint32_t st) { return (h->cfg.stage_mask & st) != 0; }
+
+int validate_params(const rdsp_chan_params_t *p, std::string &why)
+{
+    if (p->demod < 0 || p->demod >= RDSP_DEMOD_COUNT) { why = "demod out of range"; return RDSP_ERR_RANGE; }
+    if (p->audio_filter < 0 || p->audio_filter >= RDSP_FILTER_COUNT) { why = "audio_filter out of range"; return RDSP_ERR_RANGE; }
+    if (p->agc_mode < 0 || p->agc_mode >= RDSP_AGC_COUNT) { why = "agc_mode out of range"; return RDSP_ERR_RANGE; }
+    if (p->notch_on < 0 || p->notch_on > 1) { why = "notch_on must be 0 or 1"; return RDSP_ERR_RANGE; }
+    if (p->notch_level < 0 || p->notch_level > 100) { why = "notch_level out of range"; return RDSP_ERR_RANGE; }
+    if (p->nr_kind < RDSP_NR_OFF || p->nr_kind > RDSP_NR_SPECTRAL) { why = "nr_kind out of range"; return RDSP_ERR_RANGE; }
+    if (p->nr_level < 0 || p->nr_level > 100) { why = "nr_level out of range"; return RDSP_ERR_RANGE; }
+    if (!(p->pbt_lo_hz >= -22050.0f && p->pbt_hi_hz <= 22050.0f && p->pbt_hi_hz > p->pbt_lo_hz)) { why = "pbt cut-offs invalid"; return RDSP_ERR_RANGE; }
+    if (!(p->in_gain >= 0.0f && p->in_gain <= 16.0f)) { why = "in_gain out of range"; return RDSP_ERR_RANGE; }
+    if (!(p->out_gain >= 0.0f && p->out_gain <= 16.0f)) { why = "out_gain out of range"; return RDSP_ERR_RANGE; }
+    if (!(p->iq_balance > 0.0f && p->iq_balance <= 4.0f)) { why = "iq_balance out of range"; return RDSP_ERR_RANGE; }
+    return RDSP_OK;
+}
+
+int mask_id_for(rdsp_gpu *h, float lo, float hi)
+{
+    auto key = std::make_pair(lo, hi);
+    auto it = h->mask_ids.find(key);
+    if (it != h->mask_ids.end()) return it->second;
+    const int id = (int)(h->masks.size() / 512);
+    h->masks.resize(h->masks.size() + 512);
+    rdsp_host::design_mask((double)lo, (double)hi, &h->masks[(size_t)id * 512]);
+    h->mask_ids[key] = id;
+    return id;
+}
+
+void derive_params(rdsp_gpu *h, int ch)
+{
+    const rdsp_chan_params_t &p = h->par[ch];
+    RdspChanParams &d = h->dpar[ch];
+    memset(&d, 0, sizeof(d));
+    d.mult_i = (int32_t)((double)p.in_gain * 65536.0);
+    d.mult_q = (int32_t)((double)p.in_gain * (double)p.iq_balance * 65536.0);
+    d.out_gain = p.out_gain;
+    d.mu_notch = rdsp_host::lms_mu(p.notch_level);
+    d.mu_dnr = rdsp_host::lms_mu(p.nr_level);
+    d.agc_alpha_d = h->agc_alpha_d[p.agc_mode];
+    d.nr_spec_level = (float)p.nr_level;
+    d.demod = (uint8_t)p.demod;
+    d.filter = (uint8_t)p.audio_filter;
+    d.agc_mode = (uint8_t)p.agc_mode;
+    d.notch_on = (uint8_t)p.notch_on;
+    d.nr_kind = (uint8_t)(p.nr_level > 0 ? p.nr_kind : RDSP_NR_OFF);
+}
+
+int upload_masks(rdsp_gpu *h)
+{
+    const int n = (int)(h->masks.size() / 512);
+    if (n == h->masks_uploaded) return RDSP_OK;
+    if (n > h->mask_cap) {
+        int cap = h->mask_cap ? h->mask_cap : 16;
+        while (cap < n) cap *= 2;
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->d_masks) CK(cudaFree(h->d_masks));
+        CK(cudaMalloc((void **)&h->d_masks, (size_t)cap * 512 * sizeof(float)));
+        h->mask_cap = cap;
+        h->masks_uploaded = 0;
+    }
+    CK(cudaMemcpyAsync(h->d_masks + (size_t)h->masks_uploaded * 256, &h->masks[(size_t)h->masks_uploaded * 512],
+                       (size_t)(n - h->masks_uploaded) * 512 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    // the host vector may be reallocated by a later set_mode before the copy has run
+    CK(cudaStreamSynchronize(h->stream));
+    h->masks_uploaded = n;
+    return RDSP_OK;
+}
+
+// zero [first, first+count) rows of an array with `row` elements per channel, merging contiguous runs
+template <typename T>
+cudaError_t zero_rows(T *base, size_t row, const std::vector<int> &chs, cudaStream_t st)
+{
+    size_t i = 0;
+    while (i < chs.size()) {
+        size_t j = i + 1;
+        while (j < chs.size() && chs[j] == chs[j - 1] + 1) j++;
+        cudaError_t e = cudaMemsetAsync(base + (size_t)chs[i] * row, 0, (j - i) * row * sizeof(T), st);
+        if (e != cudaSuccess) return e;
+        i = j;
+    }
+    return cudaSuccess;
+}
+
+// bring the device view of parameters, work lists, taps and masks up to date (start of a process call)
+int sync_tables(rdsp_gpu *h)
+{
+    if (h->taps_dirty) {
+        std::vector<int32_t> t(15 * RDSP_TAPS_PAD, 0);
+        for (int r = 0; r < 15; r++)
+            for (int k = 0; k < RDSP_FIR_TAPS; k++) t[(size_t)r * RDSP_TAPS_PAD + k] = h->taps[r][k];
+        CK(cudaMemcpyAsync(h->d_taps, t.data(), t.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->taps_dirty = false;
+    }
+    if (!h->par_dirty) return RDSP_OK;
+
+    const bool notch_stage = has(h, RDSP_STAGE_NOTCH), nr_stage = has(h, RDSP_STAGE_NR);
+    std::vector<int> l_notch, l_dnr, re_notch, re_dnr;
+    for (int ch = 0; ch < h->C; ch++) {
+        const rdsp_chan_params_t &p = h->par[ch];
+        // Init_LMS_NR on a level change: clears ring/state/energy, keeps the coefficients
+        // (RDSP_convolutional.h:327-330, RDSP_noise_reduction.h:35-64)
+        if (notch_stage && p.notch_on) {
+            l_notch.push_back(ch);
+            if (p.notch_level != h->notch_old_level[ch]) { re_notch.push_back(ch); h->notch_old_level[ch] = p.notch_level; }
+        }
+        if (nr_stage && p.nr_kind == RDSP_NR_LMS && p.nr_level > 0) {
+            l_dnr.push_back(ch);
+            if (p.nr_level != h->dnr_old_level[ch]) { re_dnr.push_back(ch); h->dnr_old_level[ch] = p.nr_level; }
+        }
+    }
+    if (h->d_nc_prev) {
+        CK(zero_rows(h->d_nc_prev, RDSP_BLK, re_notch, h->stream));
+        CK(zero_rows(h->d_nc_energy, 1, re_notch, h->stream));
+    }
+    if (h->d_dn_prev) {
+        CK(zero_rows(h->d_dn_prev, RDSP_BLK, re_dnr, h->stream));
+        CK(zero_rows(h->d_dn_energy, 1, re_dnr, h->stream));
+    }
+    int rc = upload_masks(h);
+    if (rc != RDSP_OK) return rc;
+    CK(cudaMemcpyAsync(h->d_par, h->dpar.data(), (size_t)h->C * sizeof(RdspChanParams), cudaMemcpyHostToDevice, h->stream));
+    h->n_notch = (int)l_notch.size();
+    h->n_dnr = (int)l_dnr.size();
+    if (h->n_notch) CK(cudaMemcpyAsync(h->d_list_notch, l_notch.data(), l_notch.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (h->n_dnr) CK(cudaMemcpyAsync(h->d_list_dnr, l_dnr.data(), l_dnr.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));      // the host staging vectors go out of scope
+    h->par_dirty = false;
+    return RDSP_OK;
+}
+
+struct Prof {
+    rdsp_gpu *h; int kind; ProfRec r; bool on;
+    Prof(rdsp_gpu *h_, int kind_) : h(h_), kind(kind_), on(h_->profiling) {
+        if (on) {
+            r.kind = kind;
+            cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+            cudaEventRecord(r.e0, h->stream);
+        }
+    }
+    ~Prof() {
+        h->launches++;
+        if (on) { cudaEventRecord(r.e1, h->stream); h->prof_pending.push_back(r); }
+    }
+};
+
+void prof_collect(rdsp_gpu *h)
+{
+    for (auto &r : h->prof_pending) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.e1);
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { h->prof_ms[r.kind] += ms; h->prof_n[r.kind]++; }
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    h->prof_pending.clear();
+}
+
+void free_all(rdsp_gpu *h)
+{
+    void *ptrs[] = {h->d_par, h->d_list_notch, h->d_list_dnr, h->d_taps, h->d_masks, h->d_tw, h->d_win256, h->d_win1024,
+                    h->d_tw256, h->d_fe_hist, h->d_nc_coeff, h->d_nc_prev, h->d_nc_energy, h->d_nc_first, h->d_dn_coeff,
+                    h->d_dn_prev, h->d_dn_energy, h->d_dn_first, h->d_agc_env, h->d_conv_last, h->d_nfloor, h->d_bq_state,
+                    h->d_spec_prev, h->d_spec_sum, h->d_spec_out, h->d_ring, h->d_spec1024_out, h->d_view, h->d_smeter,
+                    h->d_mid_a, h->d_mid_b, h->d_scr, h->d_dbg, h->d_in_stage, h->d_out_stage};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rdsp_gpu_version(void) { return RDSP_VERSION; }
+
+void rdsp_gpu_default_config(rdsp_gpu_config_t *cfg)
+{
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = (uint32_t)sizeof(*cfg);
+    cfg->n_channels = 1;
+    cfg->device = 0;
+    cfg->stage_mask = RDSP_STAGE_ALL;
+    cfg->max_blocks_per_call = 1;
+    cfg->io_location = RDSP_IO_DEVICE;
+    cfg->spec256_naverage = 30;                  // FFT.averageTogether(30), RadioDSP_SDR_RX.ino:145
+    cfg->agc_target = 0.25f;
+    cfg->agc_max_gain = 1000.0f;
+    cfg->agc_attack_ms = 5.0f;
+    cfg->agc_decay_ms[RDSP_AGC_FAST] = 100.0f;
+    cfg->agc_decay_ms[RDSP_AGC_MEDIUM] = 500.0f;
+    cfg->agc_decay_ms[RDSP_AGC_SLOW] = 2000.0f;
+}
+
+void rdsp_gpu_default_params(rdsp_chan_params_t *p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->demod = RDSP_DEMOD_LSB;                   // RadioDSP_SDR_RX.ino:139
+    p->audio_filter = RDSP_FILTER_2700;          // :138
+    p->agc_mode = RDSP_AGC_MEDIUM;               // :121
+    p->notch_on = 0;                             // :125
+    p->notch_level = 20;
+    p->nr_kind = RDSP_NR_OFF;                    // RDSP_general_includes.h:111
+    p->nr_level = 0;
+    p->pbt_lo_hz = 300.0f;                       // RadioDSP_SDR_RX.ino:183
+    p->pbt_hi_hz = 4000.0f;
+    p->in_gain = 1.0f;                           // :133
+    p->out_gain = 0.5f;                          // :134
+    p->iq_balance = 1.020f;                      // :135
+}
+
+const char *rdsp_gpu_last_error(const rdsp_gpu_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
+{
+    if (!cfg || !out) { g_create_error = "NULL argument"; return RDSP_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(rdsp_gpu_config_t)) { g_create_error = "config struct_size mismatch"; return RDSP_ERR_INVALID; }
+    if (cfg->n_channels == 0 || cfg->n_channels > (1u << 24)) { g_create_error = "n_channels out of range"; return RDSP_ERR_RANGE; }
+    if (cfg->max_blocks_per_call == 0 || cfg->max_blocks_per_call > 4096) { g_create_error = "max_blocks_per_call out of range"; return RDSP_ERR_RANGE; }
+    const uint32_t sm = cfg->stage_mask;
+    if ((sm & ~RDSP_STAGE_ALL) || sm == 0) { g_create_error = "stage_mask invalid"; return RDSP_ERR_RANGE; }
+    if ((sm & (RDSP_STAGE_NOTCH | RDSP_STAGE_AGC)) && !(sm & RDSP_STAGE_FRONTEND)) { g_create_error = "NOTCH/AGC need FRONTEND"; return RDSP_ERR_STATE; }
+    if ((sm & RDSP_STAGE_NR) && !(sm & RDSP_STAGE_FFTFILT)) { g_create_error = "NR needs FFTFILT"; return RDSP_ERR_STATE; }
+    if ((sm & RDSP_STAGE_SPEC1024) && !(sm & (RDSP_STAGE_FRONTEND | RDSP_STAGE_FFTFILT))) { g_create_error = "SPEC1024 needs an audio path"; return RDSP_ERR_STATE; }
+    if (cfg->spec256_naverage == 0 || cfg->spec256_naverage > 255) { g_create_error = "spec256_naverage must be 1..255"; return RDSP_ERR_RANGE; }
+    if (cfg->io_location > RDSP_IO_HOST) { g_create_error = "io_location invalid"; return RDSP_ERR_RANGE; }
+    if (!(cfg->agc_target > 0.f) || !(cfg->agc_max_gain > 0.f) || !(cfg->agc_attack_ms > 0.f)) { g_create_error = "AGC constants invalid"; return RDSP_ERR_RANGE; }
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+        return RDSP_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "device ordinal out of range"; return RDSP_ERR_RANGE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10) {
+        g_create_error = "device is not sm_100-class (kernels are built for sm_100a only)";
+        return RDSP_ERR_CUDA;
+    }
+
+    rdsp_gpu *h = new (std::nothrow) rdsp_gpu();
+    if (!h) { g_create_error = "out of host memory"; return RDSP_ERR_NOMEM; }
+    h->cfg = *cfg;
+    h->C = (int)cfg->n_channels;
+    h->maxT = (int)cfg->max_blocks_per_call;
+    const size_t C = (size_t)h->C, T = (size_t)h->maxT;
+
+    auto fail = [&](cudaError_t ce, const char *what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        free_all(h);
+        delete h;
+        return ce == cudaErrorMemoryAllocation ? RDSP_ERR_NOMEM : RDSP_ERR_CUDA;
+    };
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(e_, #call); } while (0)
+
+    CKC(cudaSetDevice(cfg->device));
+    CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+
+    // host-side tables
+    for (int m = 0; m < RDSP_DEMOD_COUNT; m++) rdsp_host::design_hilbert_pair(m, h->taps[m], h->taps[RDSP_DEMOD_COUNT + m]);
+    for (int f = 0; f < RDSP_FILTER_COUNT; f++) rdsp_host::design_bandpass(f, h->taps[2 * RDSP_DEMOD_COUNT + f]);
+    h->agc_alpha_a = rdsp_host::agc_alpha(cfg->agc_attack_ms);
+    for (int m = 1; m < 4; m++) h->agc_alpha_d[m] = cfg->agc_decay_ms[m] > 0.f ? rdsp_host::agc_alpha(cfg->agc_decay_ms[m]) : 0.f;
+    rdsp_host::biquad_highpass_q30(500.0f, 0.5f, h->bq);           // RadioDSP_SDR_RX.ino:155-156
+
+    rdsp_chan_params_t defp;
+    rdsp_gpu_default_params(&defp);
+    h->par.assign(C, defp);
+    h->dpar.resize(C);
+    h->dnr_old_level.assign(C, 15);                                 // oldNRLevel = 15 + Init_LMS_NR(15): RDSP_convolutional.h:80, .ino:172
+    h->notch_old_level.assign(C, -1);
+    const int mid = mask_id_for(h, defp.pbt_lo_hz, defp.pbt_hi_hz);
+    for (size_t ch = 0; ch < C; ch++) { derive_params(h, (int)ch); h->dpar[ch].mask_id = mid; }
+    h->spec_ready.assign(C, 0);
+    h->spec1024_ready.assign(C, 0);
+
+    CKC(dalloc(&h->d_par, C));
+    CKC(dalloc(&h->d_taps, (size_t)15 * RDSP_TAPS_PAD));
+    if (sm & RDSP_STAGE_FRONTEND) {
+        CKC(dalloc(&h->d_fe_hist, C * 3 * RDSP_BLK));
+        CKC(dalloc(&h->d_mid_a, T * C * RDSP_BLK));
+    }
+    if (sm & RDSP_STAGE_NOTCH) {
+        CKC(dalloc(&h->d_list_notch, C));
+        CKC(dalloc(&h->d_nc_coeff, C * RDSP_LMS_NTAPS));
+        CKC(dalloc(&h->d_nc_prev, C * RDSP_BLK));
+        CKC(dalloc(&h->d_nc_energy, C));
+        CKC(cudaMalloc((void **)&h->d_nc_first, C));
+        CKC(cudaMemset(h->d_nc_first, 1, C));
+    }
+    if (sm & (RDSP_STAGE_NOTCH | RDSP_STAGE_AGC)) {
+        CKC(dalloc(&h->d_agc_env, C));
+        CKC(dalloc(&h->d_mid_b, T * C * RDSP_BLK));
+    }
+    if (sm & (RDSP_STAGE_NOTCH | RDSP_STAGE_NR)) CKC(dalloc(&h->d_scr, T * C * RDSP_BLK));
+    if (sm & RDSP_STAGE_FFTFILT) {
+        CKC(dalloc(&h->d_conv_last, C * 2 * RDSP_BLK));
+        CKC(dalloc(&h->d_nfloor, C));
+        CKC(dalloc(&h->d_tw256, (size_t)256));
+        float cs[512];
+        rdsp_host::make_twiddle_256_f32(cs);
+        CKC(cudaMemcpy(h->d_tw256, cs, sizeof(cs), cudaMemcpyHostToDevice));
+    }
+    if (sm & RDSP_STAGE_NR) {
+        CKC(dalloc(&h->d_list_dnr, C));
+        CKC(dalloc(&h->d_dn_coeff, C * RDSP_LMS_NTAPS));
+        CKC(dalloc(&h->d_dn_prev, C * RDSP_BLK));
+        CKC(dalloc(&h->d_dn_energy, C));
+        CKC(cudaMalloc((void **)&h->d_dn_first, C));
+        CKC(cudaMemset(h->d_dn_first, 1, C));
+    }
+    if (sm & (RDSP_STAGE_SPEC256 | RDSP_STAGE_SPEC1024)) {
+        CKC(dalloc(&h->d_tw, (size_t)3072));
+        std::vector<uint32_t> tw(3072);
+        rdsp_host::make_twiddle_4096_q15(tw.data());
+        CKC(cudaMemcpy(h->d_tw, tw.data(), tw.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    if (sm & RDSP_STAGE_SPEC256) {
+        CKC(dalloc(&h->d_bq_state, C * 8));
+        CKC(dalloc(&h->d_spec_prev, C * 2 * RDSP_BLK));
+        CKC(dalloc(&h->d_spec_sum, C * 256));
+        CKC(dalloc(&h->d_spec_out, C * 256));
+        CKC(dalloc(&h->d_win256, (size_t)256));
+        CKC(dalloc(&h->d_view, C * 256));
+        CKC(dalloc(&h->d_smeter, C));
+        int16_t w[256];
+        rdsp_host::make_hann_q15(w, 256);
+        CKC(cudaMemcpy(h->d_win256, w, sizeof(w), cudaMemcpyHostToDevice));
+        std::vector<uint16_t> v0(C * 256, 0);
+        for (size_t ch = 0; ch < C; ch++) v0[ch * 256] = 1;        // SpectrumViewOld[512] = {1}, RDSP_display.h:32
+        CKC(cudaMemcpy(h->d_view, v0.data(), v0.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+    if (sm & RDSP_STAGE_SPEC1024) {
+        CKC(dalloc(&h->d_ring, C * 8 * RDSP_BLK));
+        CKC(dalloc(&h->d_spec1024_out, C * 512));
+        CKC(dalloc(&h->d_win1024, (size_t)1024));
+        int16_t w[1024];
+        rdsp_host::make_hann_q15(w, 1024);
+        CKC(cudaMemcpy(h->d_win1024, w, sizeof(w), cudaMemcpyHostToDevice));
+    }
+    if (cfg->debug_f32) CKC(dalloc(&h->d_dbg, T * C * 2 * RDSP_BLK));
+    if (cfg->io_location == RDSP_IO_HOST) {
+        CKC(dalloc(&h->d_in_stage, T * C * 2 * RDSP_BLK));
+        CKC(dalloc(&h->d_out_stage, T * C * 2 * RDSP_BLK));
+    }
+#undef CKC
+    h->par_dirty = true;
+    h->taps_dirty = true;
+    *out = h;
+    return RDSP_OK;
+}
+
+void rdsp_gpu_destroy(rdsp_gpu_t *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    prof_collect(h);
+    free_all(h);
+    delete h;
+}
+
+int rdsp_gpu_set_mode(rdsp_gpu_t *h, uint32_t ch_first, uint32_t ch_count, const rdsp_chan_params_t *p)
+{
+    if (!h || !p) return RDSP_ERR_INVALID;
+    if (ch_count == 0 || (uint64_t)ch_first + ch_count > (uint64_t)h->C) { h->err = "channel range out of bounds"; return RDSP_ERR_RANGE; }
+    std::string why;
+    int rc = validate_params(p, why);
+    if (rc != RDSP_OK) { h->err = why; return rc; }
+    const int mid = mask_id_for(h, p->pbt_lo_hz, p->pbt_hi_hz);
+    for (uint32_t ch = ch_first; ch < ch_first + ch_count; ch++) {
+        h->par[ch] = *p;
+        derive_params(h, (int)ch);
+        h->dpar[ch].mask_id = mid;
+    }
+    h->par_dirty = true;
+    return RDSP_OK;
+}
+
+int rdsp_gpu_get_mode(rdsp_gpu_t *h, uint32_t ch, rdsp_chan_params_t *p)
+{
+    if (!h || !p) return RDSP_ERR_INVALID;
+    if (ch >= (uint32_t)h->C) { h->err = "channel out of bounds"; return RDSP_ERR_RANGE; }
+    *p = h->par[ch];
+    return RDSP_OK;
+}
+
+int rdsp_gpu_set_stream(rdsp_gpu_t *h, void *cuda_stream)
+{
+    if (!h) return RDSP_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return RDSP_OK;
+}
+
+int rdsp_gpu_synchronize(rdsp_gpu_t *h)
+{
+    if (!h) return RDSP_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    return RDSP_OK;
+}
+
+int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_in, int16_t *audio_out)
+{
+    if (!h || !iq_in) return RDSP_ERR_INVALID;
+    const bool fe = has(h, RDSP_STAGE_FRONTEND), notch = has(h, RDSP_STAGE_NOTCH), agc = has(h, RDSP_STAGE_AGC);
+    const bool ff = has(h, RDSP_STAGE_FFTFILT), nr = has(h, RDSP_STAGE_NR);
+    const bool audio_path = fe || ff;
+    if (audio_path && !audio_out) { h->err = "audio_out is NULL"; return RDSP_ERR_INVALID; }
+    if (n_blocks == 0) return RDSP_OK;
+    if (n_blocks > (uint32_t)h->maxT) { h->err = "n_blocks exceeds max_blocks_per_call"; return RDSP_ERR_RANGE; }
+    if (((uintptr_t)iq_in & 15) || ((uintptr_t)audio_out & 15)) { h->err = "buffers must be 16-byte aligned"; return RDSP_ERR_INVALID; }
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = sync_tables(h);
+    if (rc != RDSP_OK) return rc;
+
+    const int C = h->C, T = (int)n_blocks;
+    const size_t io_bytes = (size_t)T * C * 2 * RDSP_BLK * sizeof(int16_t);
+    const int16_t *iq = iq_in;
+    int16_t *audio = audio_out;
+    if (h->cfg.io_location == RDSP_IO_HOST) {
+        CK(cudaMemcpyAsync(h->d_in_stage, iq_in, io_bytes, cudaMemcpyHostToDevice, h->stream));
+        iq = h->d_in_stage;
+        audio = h->d_out_stage;
+    }
+    cudaStream_t st = h->stream;
+
+    if (has(h, RDSP_STAGE_SPEC256)) {
+        Spec256Args a{};
+        a.iq = iq; a.bq_state = h->d_bq_state; a.prev = h->d_spec_prev; a.sum = h->d_spec_sum; a.output = h->d_spec_out;
+        a.C = C; a.T = T; a.have_prev = h->spec_have_prev; a.count = h->spec_count; a.naverage = (int)h->cfg.spec256_naverage;
+        int lg = 0; while ((1u << lg) < h->cfg.spec256_naverage) lg++;
+        a.div_shift = 32 + lg;
+        a.div_magic = ((1ull << a.div_shift) + h->cfg.spec256_naverage - 1) / h->cfg.spec256_naverage;
+        a.tw = h->d_tw; a.win = h->d_win256;
+        a.b0 = h->bq[0]; a.b1 = h->bq[1]; a.b2 = h->bq[2]; a.a1 = h->bq[3]; a.a2 = h->bq[4];
+        { Prof pr(h, KK_SPEC256); launch_spec256(a, st); }
+        // host mirror of the uniform counters (analyze_fft256iq.cpp:73-77,99-113)
+        int updates = T - (h->spec_have_prev ? 0 : 1);
+        h->spec_have_prev = 1;
+        const int total = h->spec_count + updates;
+        if (total / (int)h->cfg.spec256_naverage > 0) std::fill(h->spec_ready.begin(), h->spec_ready.end(), (uint8_t)1);
+        h->spec_count = total % (int)h->cfg.spec256_naverage;
+    }
+
+    const int16_t *mono = nullptr;
+    if (fe) {
+        const bool last = !(notch || agc || ff);
+        FrontArgs a{};
+        a.iq = iq; a.out_mono = last ? nullptr : h->d_mid_a; a.out_stereo = last ? audio : nullptr;
+        a.dbg = last ? h->d_dbg : nullptr; a.hist = h->d_fe_hist; a.par = h->d_par; a.taps = h->d_taps; a.C = C; a.T = T;
+        { Prof pr(h, KK_FRONT); launch_front(a, st); }
+        mono = h->d_mid_a;
+        if (notch && h->n_notch > 0) {
+            NlmsArgs n{};
+            n.list = h->d_list_notch; n.n_list = h->n_notch; n.C = C; n.T = T;
+            n.in_q15 = h->d_mid_a; n.out_f32 = h->d_scr;
+            n.coeff = h->d_nc_coeff; n.prev = h->d_nc_prev; n.energy = h->d_nc_energy; n.first = h->d_nc_first;
+            n.par = h->d_par; n.mode = 0;
+            { Prof pr(h, KK_NOTCH); launch_nlms(n, st); }
+        }
+        if (notch || agc) {
+            AgcArgs g{};
+            g.in_q15 = h->d_mid_a; g.in_f32 = h->d_scr; g.out_mono = ff ? h->d_mid_b : nullptr; g.out_stereo = ff ? nullptr : audio;
+            g.dbg = ff ? nullptr : h->d_dbg; g.env = h->d_agc_env; g.par = h->d_par; g.C = C; g.T = T;
+            g.use_f32 = notch ? 1 : 0; g.agc_stage = agc ? 1 : 0;
+            g.target = h->cfg.agc_target; g.max_gain = h->cfg.agc_max_gain; g.alpha_a = h->agc_alpha_a;
+            { Prof pr(h, KK_AGC); launch_agc(g, st); }
+            mono = h->d_mid_b;
+        }
+    }
+    if (ff) {
+        FftFiltArgs f{};
+        f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq; f.out_stereo = audio; f.out_f32_L = h->d_scr;
+        f.dbg = h->d_dbg; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256;
+        f.par = h->d_par; f.C = C; f.T = T; f.nr_stage = nr ? 1 : 0;
+        { Prof pr(h, KK_FFTFILT); launch_fftfilt(f, st); }
+        if (nr && h->n_dnr > 0) {
+            NlmsArgs n{};
+            n.list = h->d_list_dnr; n.n_list = h->n_dnr; n.C = C; n.T = T;
+            n.in_f32 = h->d_scr; n.out_stereo = audio; n.dbg = h->d_dbg;
+            n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
+            n.par = h->d_par; n.mode = 1;
+            { Prof pr(h, KK_DNR); launch_nlms(n, st); }
+        }
+    }
+    if (has(h, RDSP_STAGE_SPEC1024)) {
+        Spec1024Args s{};
+        s.audio = audio; s.ring = h->d_ring; s.output = h->d_spec1024_out; s.C = C; s.T = T; s.tick0 = h->tick;
+        s.tw = h->d_tw; s.win = h->d_win1024;
+        int n_fft = 0;
+        for (int t = 0; t < T; t++) {
+            const unsigned long long tk = h->tick + t;
+            if (tk >= 7 && ((tk - 7) & 3) == 0) n_fft++;
+        }
+        s.any_fft = n_fft > 0;
+        { Prof pr(h, KK_SPEC1024); launch_spec1024(s, st); }
+        if (n_fft) std::fill(h->spec1024_ready.begin(), h->spec1024_ready.end(), (uint8_t)1);
+    }
+    h->tick += T;
+    CK(cudaGetLastError());
+
+    if (h->cfg.io_location == RDSP_IO_HOST && audio_path)
+        CK(cudaMemcpyAsync(audio_out, h->d_out_stage, io_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (!h->cfg.async) CK(cudaStreamSynchronize(h->stream));
+    return RDSP_OK;
+}
+
+int rdsp_gpu_process_block(rdsp_gpu_t *h, const int16_t *iq_in, int16_t *audio_out)
+{
+    return rdsp_gpu_process_blocks(h, 1, iq_in, audio_out);
+}
+
+static int read_rows(rdsp_gpu_t *h, const uint16_t *dsrc, size_t row, std::vector<uint8_t> &flags,
+                     uint32_t ch_first, uint32_t ch_count, uint16_t *out, uint8_t *ready)
+{
+    if (!out) return RDSP_ERR_INVALID;
+    if (ch_count == 0 || (uint64_t)ch_first + ch_count > (uint64_t)h->C) { h->err = "channel range out of bounds"; return RDSP_ERR_RANGE; }
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out, dsrc + (size_t)ch_first * row, (size_t)ch_count * row * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < ch_count; i++) {
+        if (ready) ready[i] = flags[ch_first + i];
+        flags[ch_first + i] = 0;                 // available() clears the flag, analyze_fft256iq.h:61-67
+    }
+    return RDSP_OK;
+}
+
+int rdsp_gpu_read_spectrum(rdsp_gpu_t *h, uint32_t ch_first, uint32_t ch_count, uint16_t *out, uint8_t *ready)
+{
+    if (!h) return RDSP_ERR_INVALID;
+    if (!has(h, RDSP_STAGE_SPEC256)) { h->err = "handle has no SPEC256 stage"; return RDSP_ERR_STATE; }
+    return read_rows(h, h->d_spec_out, 256, h->spec_ready, ch_first, ch_count, out, ready);
+}
+
+int rdsp_gpu_read_audio_spectrum(rdsp_gpu_t *h, uint32_t ch_first, uint32_t ch_count, uint16_t *out, uint8_t *ready)
+{
+    if (!h) return RDSP_ERR_INVALID;
+    if (!has(h, RDSP_STAGE_SPEC1024)) { h->err = "handle has no SPEC1024 stage"; return RDSP_ERR_STATE; }
+    return read_rows(h, h->d_spec1024_out, 512, h->spec1024_ready, ch_first, ch_count, out, ready);
+}
+
+int rdsp_gpu_read_panadapter(rdsp_gpu_t *h, uint32_t ch_first, uint32_t ch_count, uint16_t *trace, float *smeter)
+{
+    if (!h || !trace || !smeter) return RDSP_ERR_INVALID;
+    if (!has(h, RDSP_STAGE_SPEC256)) { h->err = "handle has no SPEC256 stage"; return RDSP_ERR_STATE; }
+    if (ch_count == 0 || (uint64_t)ch_first + ch_count > (uint64_t)h->C) { h->err = "channel range out of bounds"; return RDSP_ERR_RANGE; }
+    CK(cudaSetDevice(h->cfg.device));
+    PanArgs a{};
+    a.spec = h->d_spec_out; a.view = h->d_view; a.smeter = h->d_smeter; a.ch_first = (int)ch_first; a.ch_count = (int)ch_count;
+    { Prof pr(h, KK_PAN); launch_panadapter(a, h->stream); }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(trace, h->d_view + (size_t)ch_first * 256, (size_t)ch_count * 256 * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(smeter, h->d_smeter + ch_first, (size_t)ch_count * sizeof(float), cudaMemcpyDeviceToHost));
+    return RDSP_OK;
+}
+
+static int16_t *taps_row(rdsp_gpu_t *h, int kind, int index)
+{
+    if (kind == RDSP_TAPS_HILBERT_I && index >= 0 && index < RDSP_DEMOD_COUNT) return h->taps[index];
+    if (kind == RDSP_TAPS_HILBERT_Q && index >= 0 && index < RDSP_DEMOD_COUNT) return h->taps[RDSP_DEMOD_COUNT + index];
+    if (kind == RDSP_TAPS_BANDPASS && index >= 0 && index < RDSP_FILTER_COUNT) return h->taps[2 * RDSP_DEMOD_COUNT + index];
+    return nullptr;
+}
+
+int rdsp_gpu_set_taps(rdsp_gpu_t *h, int kind, int index, const int16_t *taps, uint32_t n_taps)
+{
+    if (!h || !taps) return RDSP_ERR_INVALID;
+    int16_t *row = taps_row(h, kind, index);
+    if (!row || n_taps != RDSP_FIR_TAPS) { h->err = "tap table kind/index/length invalid"; return RDSP_ERR_RANGE; }
+    memcpy(row, taps, RDSP_FIR_TAPS * sizeof(int16_t));
+    h->taps_dirty = true;
+    return RDSP_OK;
+}
+
+int rdsp_gpu_get_taps(rdsp_gpu_t *h, int kind, int index, int16_t *taps, uint32_t n_taps)
+{
+    if (!h || !taps) return RDSP_ERR_INVALID;
+    int16_t *row = taps_row(h, kind, index);
+    if (!row || n_taps != RDSP_FIR_TAPS) { h->err = "tap table kind/index/length invalid"; return RDSP_ERR_RANGE; }
+    memcpy(taps, row, RDSP_FIR_TAPS * sizeof(int16_t));
+    return RDSP_OK;
+}
+
+int rdsp_gpu_set_mask(rdsp_gpu_t *h, uint32_t ch_first, uint32_t ch_count, const float *mask512)
+{
+    if (!h || !mask512) return RDSP_ERR_INVALID;
+    if (ch_count == 0 || (uint64_t)ch_first + ch_count > (uint64_t)h->C) { h->err = "channel range out of bounds"; return RDSP_ERR_RANGE; }
+    const int id = (int)(h->masks.size() / 512);
+    h->masks.insert(h->masks.end(), mask512, mask512 + 512);
+    for (uint32_t ch = ch_first; ch < ch_first + ch_count; ch++) h->dpar[ch].mask_id = id;
+    h->par_dirty = true;
+    return RDSP_OK;
+}
+
+int rdsp_gpu_get_mask(rdsp_gpu_t *h, uint32_t ch, float *mask512)
+{
+    if (!h || !mask512) return RDSP_ERR_INVALID;
+    if (ch >= (uint32_t)h->C) { h->err = "channel out of bounds"; return RDSP_ERR_RANGE; }
+    memcpy(mask512, &h->masks[(size_t)h->dpar[ch].mask_id * 512], 512 * sizeof(float));
+    return RDSP_OK;
+}
+
+int rdsp_gpu_read_debug_f32(rdsp_gpu_t *h, uint32_t n_blocks, uint32_t ch_first, uint32_t ch_count, float *out)
+{
+    if (!h || !out) return RDSP_ERR_INVALID;
+    if (!h->d_dbg) { h->err = "handle was created without debug_f32"; return RDSP_ERR_STATE; }
+    if (n_blocks == 0 || n_blocks > (uint32_t)h->maxT) { h->err = "n_blocks out of range"; return RDSP_ERR_RANGE; }
+    if (ch_count == 0 || (uint64_t)ch_first + ch_count > (uint64_t)h->C) { h->err = "channel range out of bounds"; return RDSP_ERR_RANGE; }
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    const size_t row = 2 * RDSP_BLK;
+    CK(cudaMemcpy2D(out, (size_t)ch_count * row * sizeof(float), h->d_dbg + (size_t)ch_first * row,
+                    (size_t)h->C * row * sizeof(float), (size_t)ch_count * row * sizeof(float), n_blocks, cudaMemcpyDeviceToHost));
+    return RDSP_OK;
+}
+
+uint64_t rdsp_gpu_kernel_launches(const rdsp_gpu_t *h) { return h ? h->launches : 0; }
+
+int rdsp_gpu_profile(rdsp_gpu_t *h, int enable)
+{
+    if (!h) return RDSP_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    prof_collect(h);
+    if (enable && !h->profiling) {
+        for (int i = 0; i < KK_COUNT; i++) { h->prof_ms[i] = 0.0; h->prof_n[i] = 0; }
+    }
+    h->profiling = enable != 0;
+    return RDSP_OK;
+}
+
+int rdsp_gpu_profile_read(rdsp_gpu_t *h, int max, const char **names, double *ms, uint64_t *launches)
+{
+    if (!h) return RDSP_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    prof_collect(h);
+    for (int i = 0; i < KK_COUNT && i < max; i++) {
+        if (names) names[i] = kKernelNames[i];
+        if (ms) ms[i] = h->prof_ms[i];
+        if (launches) launches[i] = h->prof_n[i];
+    }
+    return KK_COUNT;
+}
+
+}  // extern "C"
