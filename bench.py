@@ -90,6 +90,7 @@ def algorithmic_bytes(workload: str, T: int) -> dict:
         k["k_agc"] = 256 + 256 + st(16)
         k["k_fftfilt"] = 256 + 512 + st(512)
         k["k_nlms_dnr"] = 0.8 * (512 + 512 + st(1288))
+        k["k_biquad"] = 512 + 512 + st(32)
         k["k_spec256"] = 512 + st(1540) + 512.0 / 30
         k["k_spec1024"] = 256 + 256 + 1792.0 / 4 + 1024.0 / 4
     # whole fused-ideal step (no intermediates), SURVEY.md 8d totals
@@ -100,7 +101,7 @@ def algorithmic_bytes(workload: str, T: int) -> dict:
 
 # lane-operations (FP32 FMA / INT32 IMAD class) per channel-block, for the pipe fraction
 PIPE_OPS = {"k_front": 3 * 129 * 128, "k_nlms_notch": 128 * (96 * 2 + 8), "k_nlms_dnr": 128 * (96 * 2 + 8),
-            "k_fftfilt": 2 * 256 * 8 * 2.5 + 256 * 4, "k_agc": 128 * 8, "k_spec256": 4 * 64 * 40 + 256 * 8 + 128 * 2 * 12,
+            "k_fftfilt": 2 * 256 * 8 * 2.5 + 256 * 4, "k_agc": 128 * 8, "k_biquad": 128 * 2 * 12, "k_spec256": 4 * 64 * 40 + 256 * 8,
             "k_spec1024": (5 * 256 * 40 + 1024 * 4) / 4.0}
 
 
@@ -293,7 +294,11 @@ def run_b200(args):
             b.set_mode(c, 1, rd.default_params(**channel_params(wl, ch0 + c)))
         return b
 
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the C ABI takes NULL to mean "the handle's own stream", and CUDA events must be
+    # recorded on the stream the kernels are launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     bank = new_bank(rd.IO_DEVICE)
     bank.set_stream(stream.cuda_stream)
 

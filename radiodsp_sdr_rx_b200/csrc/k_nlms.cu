@@ -20,6 +20,10 @@
 namespace {
 
 constexpr int NWARPS = 2;
+constexpr int XS = 257;
+
+__device__ __forceinline__ void st4(float *p, float4 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
+__device__ __forceinline__ float4 ld4(const float *p) { return make_float4(p[0], p[1], p[2], p[3]); }
 constexpr float LMS_EPS = 0.000000119209289f;
 
 template <int G>
@@ -27,7 +31,9 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
 {
     constexpr int W = RDSP_LMS_NTAPS / G;        // taps per lane
     constexpr int CPW = 32 / G;                  // channels per warp
-    __shared__ __align__(16) float s_x[NWARPS * CPW][256];   // [0,128) previous block / outputs, [128,256) current
+    // [0,128) previous block / outputs, [128,256) current.  Row stride 257: the 32/G channels of a warp and the G
+    // lanes of a channel (offsets -W*g, W a multiple of 4) then hit 32 different banks on every access.
+    __shared__ float s_x[NWARPS * CPW][XS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane % G;                      // lane within the channel group
@@ -36,7 +42,6 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
     const bool active = li < a.n_list;
     const int ch = active ? (a.list ? a.list[li] : li) : 0;
     float *xb = s_x[slot];
-    float4 *xb4 = reinterpret_cast<float4 *>(xb);
 
     float c[W], xw[W];
     float energy = 0.0f, mu = 0.0f;
@@ -48,13 +53,13 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
 #pragma unroll
         for (int i = 0; i < W; i++) c[i] = cf[95 - W * g - i];        // register i <-> delay W*g + i
         const float4 *pv = reinterpret_cast<const float4 *>(a.prev + (size_t)ch * RDSP_BLK);
-        for (int i = g; i < 32; i += G) xb4[i] = pv[i];
+        for (int i = g; i < 32; i += G) st4(xb + 4 * i, pv[i]);
         energy = a.energy[ch];
         first = a.first[ch] != 0;
     } else {
 #pragma unroll
         for (int i = 0; i < W; i++) c[i] = 0.0f;
-        for (int i = g; i < 32; i += G) xb4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = g; i < 32; i += G) st4(xb + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
     }
 
     for (int t = 0; t < a.T; t++) {
@@ -63,19 +68,19 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
         if (active) {
             if (a.in_f32) {
                 const float4 *src = reinterpret_cast<const float4 *>(a.in_f32 + cb * RDSP_BLK);
-                for (int i = g; i < 32; i += G) xb4[32 + i] = src[i];
+                for (int i = g; i < 32; i += G) st4(xb + 128 + 4 * i, src[i]);
             } else {
                 const int4 *src = reinterpret_cast<const int4 *>(a.in_q15 + cb * RDSP_BLK);
                 for (int i = g; i < 16; i += G) {
                     const int4 v = src[i];
-                    xb4[32 + 2 * i] = make_float4((float)lo16(v.x) / 32768.0f, (float)hi16(v.x) / 32768.0f,
-                                                  (float)lo16(v.y) / 32768.0f, (float)hi16(v.y) / 32768.0f);
-                    xb4[32 + 2 * i + 1] = make_float4((float)lo16(v.z) / 32768.0f, (float)hi16(v.z) / 32768.0f,
-                                                      (float)lo16(v.w) / 32768.0f, (float)hi16(v.w) / 32768.0f);
+                    st4(xb + 128 + 8 * i, make_float4((float)lo16(v.x) / 32768.0f, (float)hi16(v.x) / 32768.0f,
+                                                      (float)lo16(v.y) / 32768.0f, (float)hi16(v.y) / 32768.0f));
+                    st4(xb + 128 + 8 * i + 4, make_float4((float)lo16(v.z) / 32768.0f, (float)hi16(v.z) / 32768.0f,
+                                                          (float)lo16(v.w) / 32768.0f, (float)hi16(v.w) / 32768.0f));
                 }
             }
         } else {
-            for (int i = g; i < 32; i += G) xb4[32 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = g; i < 32; i += G) st4(xb + 128 + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
         }
         __syncwarp();
 
@@ -119,12 +124,12 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
         if (active) {
             if (a.mode == 0) {
                 float4 *dst = reinterpret_cast<float4 *>(a.out_f32 + cb * RDSP_BLK);
-                for (int i = g; i < 32; i += G) dst[i] = xb4[i];
+                for (int i = g; i < 32; i += G) dst[i] = ld4(xb + 4 * i);
             } else {
                 int4 *dst = reinterpret_cast<int4 *>(a.out_stereo + cb * 2 * RDSP_BLK);
                 float4 *dbg = a.dbg ? reinterpret_cast<float4 *>(a.dbg + cb * 2 * RDSP_BLK) : nullptr;
                 for (int i = g; i < 32; i += G) {
-                    const float4 y = xb4[i];
+                    const float4 y = ld4(xb + 4 * i);
                     const float f0 = (float)((double)y.x * 1.1), f1 = (float)((double)y.y * 1.1);
                     const float f2 = (float)((double)y.z * 1.1), f3 = (float)((double)y.w * 1.1);
                     const int32_t q0 = f32_to_q15(f0), q1 = f32_to_q15(f1), q2 = f32_to_q15(f2), q3 = f32_to_q15(f3);
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
             }
         }
         __syncwarp();
-        for (int i = g; i < 32; i += G) xb4[i] = xb4[32 + i];       // current block becomes the previous one
+        for (int i = g; i < 32; i += G) st4(xb + 4 * i, ld4(xb + 128 + 4 * i));   // current block becomes the previous one
         __syncwarp();
     }
 
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
 #pragma unroll
         for (int i = 0; i < W; i++) cf[95 - W * g - i] = c[i];
         float4 *pv = reinterpret_cast<float4 *>(a.prev + (size_t)ch * RDSP_BLK);
-        for (int i = g; i < 32; i += G) pv[i] = xb4[i];
+        for (int i = g; i < 32; i += G) pv[i] = ld4(xb + 4 * i);
         if (g == 0) {
             a.energy[ch] = energy;
             a.first[ch] = 0;

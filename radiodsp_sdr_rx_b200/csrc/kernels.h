@@ -38,15 +38,16 @@ void launch_nlms(const NlmsArgs &a, cudaStream_t st);
 
 // K4: AGC + output gain -------------------------------------------------------------------------
 struct AgcArgs {
-    const int16_t *in_q15;      // [T][C][128]
-    const float *in_f32;        // [T][C][128] used for channels with notch_on (if use_f32)
+    const int *list;            // channels to run (nullptr: 0..n_list-1)
+    int n_list;
+    const int16_t *in_q15;      // [T][C][128] q15 rows (channels that bypass the notch) ...
+    const float *in_f32;        // ... or [T][C][128] f32 rows (channels whose notch ran); exactly one is set
     int16_t *out_mono;          // [T][C][128]    or nullptr
     int16_t *out_stereo;        // [T][C][128][2] or nullptr
     float *dbg;                 // [T][C][128][2] or nullptr
     float *env;                 // [C]
     const RdspChanParams *par;
     int C, T;
-    int use_f32;                // notch stage present
     int agc_stage;              // 0: only quantise (notch without AGC stage)
     float target, max_gain, alpha_a;
 };
@@ -69,10 +70,19 @@ struct FftFiltArgs {
 };
 void launch_fftfilt(const FftFiltArgs &a, cudaStream_t st);
 
-// a11 + K9 --------------------------------------------------------------------------------------
+// a11 -------------------------------------------------------------------------------------------
+struct BiquadArgs {
+    const int16_t *iq;          // [T][C][128][2] raw IQ
+    int16_t *out;               // [T][C][128][2] high-passed IQ
+    int32_t *state;             // [C][2][4]: bprev, aprev, sum, pad  for I and Q
+    int C, T;
+    int32_t b0, b1, b2, a1, a2; // Q30, feedback already negated
+};
+void launch_biquad(const BiquadArgs &a, cudaStream_t st);
+
+// K9 --------------------------------------------------------------------------------------------
 struct Spec256Args {
-    const int16_t *iq;          // [T][C][128][2]
-    int32_t *bq_state;          // [C][2][4]: bprev, aprev, sum, pad  for I and Q
+    const int16_t *iq;          // [T][C][128][2] high-passed IQ (output of k_biquad)
     int16_t *prev;              // [C][128][2] previous post-biquad block
     uint32_t *sum;              // [C][256]
     uint16_t *output;           // [C][256]
@@ -84,7 +94,6 @@ struct Spec256Args {
     int div_shift;                  // (magsq * div_magic) >> div_shift == magsq / naverage for magsq <= 2^31
     const uint32_t *tw;         // [3072] twiddleCoef_4096_q15 as (cos | sin << 16) words
     const int16_t *win;         // [256] Hann
-    int32_t b0, b1, b2, a1, a2; // Q30, feedback already negated
 };
 void launch_spec256(const Spec256Args &a, cudaStream_t st);
 

@@ -24,9 +24,9 @@ namespace {
 
 std::string g_create_error;
 
-enum KernelKind { KK_FRONT = 0, KK_NOTCH, KK_AGC, KK_FFTFILT, KK_DNR, KK_SPEC256, KK_SPEC1024, KK_PAN, KK_COUNT };
+enum KernelKind { KK_FRONT = 0, KK_NOTCH, KK_AGC, KK_FFTFILT, KK_DNR, KK_BIQUAD, KK_SPEC256, KK_SPEC1024, KK_PAN, KK_COUNT };
 const char *const kKernelNames[KK_COUNT] = {"k_front", "k_nlms_notch", "k_agc", "k_fftfilt", "k_nlms_dnr",
-                                            "k_spec256", "k_spec1024", "k_panadapter"};
+                                            "k_biquad", "k_spec256", "k_spec1024", "k_panadapter"};
 
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
 
@@ -36,6 +36,8 @@ struct rdsp_gpu {
     rdsp_gpu_config_t cfg;
     int C = 0, maxT = 1;
     cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaStream_t spec_stream = nullptr;        // the spectrum path (k_biquad, k_spec256) runs beside the audio path
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
 
     // parameters
@@ -44,8 +46,8 @@ struct rdsp_gpu {
     std::vector<int> dnr_old_level, notch_old_level;
     bool par_dirty = true;
     RdspChanParams *d_par = nullptr;
-    int *d_list_notch = nullptr, *d_list_dnr = nullptr;
-    int n_notch = 0, n_dnr = 0;
+    int *d_list_notch = nullptr, *d_list_plain = nullptr, *d_list_dnr = nullptr;
+    int n_notch = 0, n_plain = 0, n_dnr = 0;
 
     // coefficient tables
     int16_t taps[15][RDSP_FIR_TAPS];
@@ -74,6 +76,7 @@ struct rdsp_gpu {
     // scratch
     int16_t *d_mid_a = nullptr, *d_mid_b = nullptr;
     float *d_scr = nullptr, *d_dbg = nullptr;
+    int16_t *d_hp_iq = nullptr;                // high-passed IQ between k_biquad and k_spec256
     int16_t *d_in_stage = nullptr, *d_out_stage = nullptr;
 
     // tick bookkeeping (uniform over channels)
@@ -209,7 +212,7 @@ int sync_tables(rdsp_gpu *h)
     if (!h->par_dirty) return RDSP_OK;
 
     const bool notch_stage = has(h, RDSP_STAGE_NOTCH), nr_stage = has(h, RDSP_STAGE_NR);
-    std::vector<int> l_notch, l_dnr, re_notch, re_dnr;
+    std::vector<int> l_notch, l_plain, l_dnr, re_notch, re_dnr;
     for (int ch = 0; ch < h->C; ch++) {
         const rdsp_chan_params_t &p = h->par[ch];
         // Init_LMS_NR on a level change: clears ring/state/energy, keeps the coefficients
@@ -217,6 +220,8 @@ int sync_tables(rdsp_gpu *h)
         if (notch_stage && p.notch_on) {
             l_notch.push_back(ch);
             if (p.notch_level != h->notch_old_level[ch]) { re_notch.push_back(ch); h->notch_old_level[ch] = p.notch_level; }
+        } else if (notch_stage) {
+            l_plain.push_back(ch);
         }
         if (nr_stage && p.nr_kind == RDSP_NR_LMS && p.nr_level > 0) {
             l_dnr.push_back(ch);
@@ -235,7 +240,9 @@ int sync_tables(rdsp_gpu *h)
     if (rc != RDSP_OK) return rc;
     CK(cudaMemcpyAsync(h->d_par, h->dpar.data(), (size_t)h->C * sizeof(RdspChanParams), cudaMemcpyHostToDevice, h->stream));
     h->n_notch = (int)l_notch.size();
+    h->n_plain = (int)l_plain.size();
     h->n_dnr = (int)l_dnr.size();
+    if (h->n_plain) CK(cudaMemcpyAsync(h->d_list_plain, l_plain.data(), l_plain.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (h->n_notch) CK(cudaMemcpyAsync(h->d_list_notch, l_notch.data(), l_notch.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (h->n_dnr) CK(cudaMemcpyAsync(h->d_list_dnr, l_dnr.data(), l_dnr.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));      // the host staging vectors go out of scope
@@ -244,17 +251,17 @@ int sync_tables(rdsp_gpu *h)
 }
 
 struct Prof {
-    rdsp_gpu *h; int kind; ProfRec r; bool on;
-    Prof(rdsp_gpu *h_, int kind_) : h(h_), kind(kind_), on(h_->profiling) {
+    rdsp_gpu *h; int kind; ProfRec r; bool on; cudaStream_t st;
+    Prof(rdsp_gpu *h_, int kind_, cudaStream_t st_ = nullptr) : h(h_), kind(kind_), on(h_->profiling), st(st_ ? st_ : h_->stream) {
         if (on) {
             r.kind = kind;
             cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
-            cudaEventRecord(r.e0, h->stream);
+            cudaEventRecord(r.e0, st);
         }
     }
     ~Prof() {
         h->launches++;
-        if (on) { cudaEventRecord(r.e1, h->stream); h->prof_pending.push_back(r); }
+        if (on) { cudaEventRecord(r.e1, st); h->prof_pending.push_back(r); }
     }
 };
 
@@ -271,12 +278,15 @@ void prof_collect(rdsp_gpu *h)
 
 void free_all(rdsp_gpu *h)
 {
-    void *ptrs[] = {h->d_par, h->d_list_notch, h->d_list_dnr, h->d_taps, h->d_masks, h->d_tw, h->d_win256, h->d_win1024,
+    void *ptrs[] = {h->d_par, h->d_list_notch, h->d_list_plain, h->d_list_dnr, h->d_taps, h->d_masks, h->d_tw, h->d_win256, h->d_win1024,
                     h->d_tw256, h->d_fe_hist, h->d_nc_coeff, h->d_nc_prev, h->d_nc_energy, h->d_nc_first, h->d_dn_coeff,
                     h->d_dn_prev, h->d_dn_energy, h->d_dn_first, h->d_agc_env, h->d_conv_last, h->d_nfloor, h->d_bq_state,
                     h->d_spec_prev, h->d_spec_sum, h->d_spec_out, h->d_ring, h->d_spec1024_out, h->d_view, h->d_smeter,
-                    h->d_mid_a, h->d_mid_b, h->d_scr, h->d_dbg, h->d_in_stage, h->d_out_stage};
+                    h->d_mid_a, h->d_mid_b, h->d_scr, h->d_dbg, h->d_hp_iq, h->d_in_stage, h->d_out_stage};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->spec_stream) cudaStreamDestroy(h->spec_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
 }
 
@@ -372,6 +382,9 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     CKC(cudaSetDevice(cfg->device));
     CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
+    CKC(cudaStreamCreateWithFlags(&h->spec_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
 
     // host-side tables
     for (int m = 0; m < RDSP_DEMOD_COUNT; m++) rdsp_host::design_hilbert_pair(m, h->taps[m], h->taps[RDSP_DEMOD_COUNT + m]);
@@ -399,6 +412,7 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     }
     if (sm & RDSP_STAGE_NOTCH) {
         CKC(dalloc(&h->d_list_notch, C));
+        CKC(dalloc(&h->d_list_plain, C));
         CKC(dalloc(&h->d_nc_coeff, C * RDSP_LMS_NTAPS));
         CKC(dalloc(&h->d_nc_prev, C * RDSP_BLK));
         CKC(dalloc(&h->d_nc_energy, C));
@@ -434,6 +448,7 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     }
     if (sm & RDSP_STAGE_SPEC256) {
         CKC(dalloc(&h->d_bq_state, C * 8));
+        CKC(dalloc(&h->d_hp_iq, T * C * 2 * RDSP_BLK));
         CKC(dalloc(&h->d_spec_prev, C * 2 * RDSP_BLK));
         CKC(dalloc(&h->d_spec_sum, C * 256));
         CKC(dalloc(&h->d_spec_out, C * 256));
@@ -544,16 +559,26 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
     }
     cudaStream_t st = h->stream;
 
+    const bool spec_fork = has(h, RDSP_STAGE_SPEC256) && audio_path;   // spectrum path beside the audio path
+    cudaStream_t sst = spec_fork ? h->spec_stream : st;
+    if (spec_fork) {
+        CK(cudaEventRecord(h->ev_fork, st));                             // the input (and earlier calls) are in place
+        CK(cudaStreamWaitEvent(h->spec_stream, h->ev_fork, 0));
+    }
     if (has(h, RDSP_STAGE_SPEC256)) {
+        BiquadArgs b{};
+        b.iq = iq; b.out = h->d_hp_iq; b.state = h->d_bq_state; b.C = C; b.T = T;
+        b.b0 = h->bq[0]; b.b1 = h->bq[1]; b.b2 = h->bq[2]; b.a1 = h->bq[3]; b.a2 = h->bq[4];
+        { Prof pr(h, KK_BIQUAD, sst); launch_biquad(b, sst); }
         Spec256Args a{};
-        a.iq = iq; a.bq_state = h->d_bq_state; a.prev = h->d_spec_prev; a.sum = h->d_spec_sum; a.output = h->d_spec_out;
+        a.iq = h->d_hp_iq; a.prev = h->d_spec_prev; a.sum = h->d_spec_sum; a.output = h->d_spec_out;
         a.C = C; a.T = T; a.have_prev = h->spec_have_prev; a.count = h->spec_count; a.naverage = (int)h->cfg.spec256_naverage;
         int lg = 0; while ((1u << lg) < h->cfg.spec256_naverage) lg++;
         a.div_shift = 32 + lg;
         a.div_magic = ((1ull << a.div_shift) + h->cfg.spec256_naverage - 1) / h->cfg.spec256_naverage;
         a.tw = h->d_tw; a.win = h->d_win256;
-        a.b0 = h->bq[0]; a.b1 = h->bq[1]; a.b2 = h->bq[2]; a.a1 = h->bq[3]; a.a2 = h->bq[4];
-        { Prof pr(h, KK_SPEC256); launch_spec256(a, st); }
+        { Prof pr(h, KK_SPEC256, sst); launch_spec256(a, sst); }
+        if (spec_fork) CK(cudaEventRecord(h->ev_join, h->spec_stream));
         // host mirror of the uniform counters (analyze_fft256iq.cpp:73-77,99-113)
         int updates = T - (h->spec_have_prev ? 0 : 1);
         h->spec_have_prev = 1;
@@ -580,11 +605,19 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
         }
         if (notch || agc) {
             AgcArgs g{};
-            g.in_q15 = h->d_mid_a; g.in_f32 = h->d_scr; g.out_mono = ff ? h->d_mid_b : nullptr; g.out_stereo = ff ? nullptr : audio;
+            g.out_mono = ff ? h->d_mid_b : nullptr; g.out_stereo = ff ? nullptr : audio;
             g.dbg = ff ? nullptr : h->d_dbg; g.env = h->d_agc_env; g.par = h->d_par; g.C = C; g.T = T;
-            g.use_f32 = notch ? 1 : 0; g.agc_stage = agc ? 1 : 0;
+            g.agc_stage = agc ? 1 : 0;
             g.target = h->cfg.agc_target; g.max_gain = h->cfg.agc_max_gain; g.alpha_a = h->agc_alpha_a;
-            { Prof pr(h, KK_AGC); launch_agc(g, st); }
+            // channels that bypassed the notch read the front end's q15 rows ...
+            g.list = notch ? h->d_list_plain : nullptr; g.n_list = notch ? h->n_plain : C;
+            g.in_q15 = h->d_mid_a; g.in_f32 = nullptr;
+            if (g.n_list > 0) { Prof pr(h, KK_AGC); launch_agc(g, st); }
+            // ... the others read the notch's f32 error signal
+            if (notch && h->n_notch > 0) {
+                g.list = h->d_list_notch; g.n_list = h->n_notch; g.in_q15 = nullptr; g.in_f32 = h->d_scr;
+                { Prof pr(h, KK_AGC); launch_agc(g, st); }
+            }
             mono = h->d_mid_b;
         }
     }
@@ -617,6 +650,7 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
         if (n_fft) std::fill(h->spec1024_ready.begin(), h->spec1024_ready.end(), (uint8_t)1);
     }
     h->tick += T;
+    if (spec_fork) CK(cudaStreamWaitEvent(st, h->ev_join, 0));          // join: the call is complete when both paths are
     CK(cudaGetLastError());
 
     if (h->cfg.io_location == RDSP_IO_HOST && audio_path)

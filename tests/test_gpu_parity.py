@@ -295,7 +295,8 @@ def test_ten_seconds_no_drift(rd, po, stage):
     errs = np.array([[rel_rms(g_f32[b:b + win, c, :, 0], o_f32[b:b + win, c, :, 0]) for b in range(0, nb - win, win)]
                      for c in range(nc)])
     assert errs.max() <= REL_RMS_TOL, errs.max()
-    assert (errs[:, -3:].mean(axis=1) <= 3.0 * errs[:, 2:5].mean(axis=1) + 1e-6).all(), errs
+    # slow modes of the adaptive filter let the rounding noise settle over seconds; it must level off, not run away
+    assert (errs[:, -3:].mean(axis=1) <= 2.0 * errs[:, 8:11].mean(axis=1) + 2e-6).all(), errs
 
 
 def test_blocks_per_call_invariance(rd, po):
@@ -433,7 +434,7 @@ def test_device_pointers_and_caller_stream(rd, po):
     assert np.array_equal(d_out.cpu().numpy(), want)
     assert dev_bank.kernel_launches >= 6
     prof = dev_bank.profile_read()
-    assert set(prof) >= {"k_front", "k_fftfilt", "k_spec256"}
+    assert set(prof) >= {"k_front", "k_fftfilt", "k_biquad", "k_spec256"}
 
 
 def test_full_size_slot_independence(rd):
