@@ -6,15 +6,18 @@
 // error feedback carried in `sum`, output SSAT16(sum >> 14).  Integer, bit-exact.
 //
 // A saturating recurrence with error feedback is sequential in time, so one THREAD owns one stream
-// (channel x {I,Q}) with b/a history and the error accumulator in registers; a warp owns 16 channels.
-// Rows are staged with double-buffered 16-byte cp.async copies, chunk-rotated by the row index so the
-// walker's LDS.128 are conflict free; the I and Q lanes of a channel re-interleave their outputs with one
-// shuffle and results leave as coalesced 16-byte stores.
+// (channel x {I,Q}) with b/a history and the error accumulator in registers.  A warp cannot hide its own
+// dependent-issue latency, so a warp owns only 4 channels (8 walking lanes, C/4 warps in flight); rows are
+// staged with double-buffered 16-byte cp.async copies (chunk-rotated per row, conflict free), the I and Q
+// lanes of a channel re-interleave their outputs with one shuffle, and results leave as coalesced 16-byte
+// stores issued by all 32 lanes.
 //   SMLAWx(c, x) = (c * x) >> 16 is computed as __mulhi(c, x << 16): one IMAD.HI.
 #include "rdsp_common.cuh"
 #include "kernels.h"
 
 namespace {
+
+constexpr int R = 4;                                   // channels per warp
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 {
@@ -33,18 +36,18 @@ __device__ __forceinline__ int32_t mlaw(int32_t c, uint32_t x_top, int32_t acc)
 
 __global__ void __launch_bounds__(32) k_biquad(BiquadArgs a)
 {
-    __shared__ __align__(16) unsigned char s_in[2][16][512];
-    __shared__ __align__(16) unsigned char s_out[16][512];
+    __shared__ __align__(16) unsigned char s_in[2][R][512];
+    __shared__ __align__(16) unsigned char s_out[R][512];
 
     const int lane = threadIdx.x;
-    const int row = lane >> 1, iq = lane & 1;             // stream = (channel row, I or Q)
-    const int ch0 = blockIdx.x * 16;
+    const int row = (lane >> 1) & (R - 1), iq = lane & 1;   // stream = (channel row, I or Q); lanes >= 2R mirror
+    const int ch0 = blockIdx.x * R;
     const int myc = ch0 + row;
-    const bool valid = myc < a.C;
+    const bool walker = lane < 2 * R && myc < a.C;
 
     uint32_t bprev = 0, aprev = 0;                          // two previous inputs / outputs: lo = older, hi = newer
     int32_t sum = 0;
-    if (valid) {
+    if (walker) {
         const int32_t *st = a.state + ((size_t)myc * 2 + iq) * 4;
         bprev = (uint32_t)st[0]; aprev = (uint32_t)st[1]; sum = st[2];
     }
@@ -52,8 +55,8 @@ __global__ void __launch_bounds__(32) k_biquad(BiquadArgs a)
     const unsigned sh = iq ? 0u : 16u;                      // brings this stream's half-word to the top
 
     auto issue_load = [&](int t, int buf) {
-#pragma unroll 4
-        for (int r = 0; r < 16; r++)
+#pragma unroll
+        for (int r = 0; r < R; r++)
             if (ch0 + r < a.C)
                 cp_async16(&s_in[buf][r][((lane + r) & 31) * 16],
                            reinterpret_cast<const unsigned char *>(a.iq + ((size_t)t * a.C + ch0 + r) * 2 * RDSP_BLK) + lane * 16);
@@ -67,50 +70,52 @@ __global__ void __launch_bounds__(32) k_biquad(BiquadArgs a)
         else cp_async_wait<0>();
         __syncwarp();
 
-        // 4 frames (16 bytes) per iteration: two passes of the 2-sample update loop
+        if (lane < 2 * R) {
+            // 4 frames (16 bytes) per iteration: two passes of the 2-sample update loop
 #pragma unroll 2
-        for (int j = 0; j < 32; j++) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(&s_in[buf][row][((j + row) & 31) * 16]);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};     // frame = (I | Q << 16)
-            uint32_t o[2];
+            for (int j = 0; j < 32; j++) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(&s_in[buf][row][((j + row) & 31) * 16]);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};     // frame = (I | Q << 16)
+                uint32_t o[2];
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t x0 = (w[2 * h] << sh) & 0xFFFF0000u;        // earlier sample, in the top half
-                const uint32_t x1 = (w[2 * h + 1] << sh) & 0xFFFF0000u;    // later sample
-                sum = mlaw(b0, x0, sum);
-                sum = mlaw(b1, bprev & 0xFFFF0000u, sum);
-                sum = mlaw(b2, bprev << 16, sum);
-                sum = mlaw(a1, aprev & 0xFFFF0000u, sum);
-                sum = mlaw(a2, aprev << 16, sum);
-                const int32_t o_lo = sat16(sum >> 14);
-                sum &= 0x3FFF;
-                sum = mlaw(b0, x1, sum);
-                sum = mlaw(b1, x0, sum);
-                sum = mlaw(b2, bprev & 0xFFFF0000u, sum);
-                sum = mlaw(a1, (uint32_t)o_lo << 16, sum);
-                sum = mlaw(a2, aprev & 0xFFFF0000u, sum);
-                const int32_t o_hi = sat16(sum >> 14);
-                sum &= 0x3FFF;
-                bprev = (x0 >> 16) | x1;
-                aprev = mk16(o_lo, o_hi);
-                o[h] = aprev;
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t x0 = (w[2 * h] << sh) & 0xFFFF0000u;        // earlier sample, in the top half
+                    const uint32_t x1 = (w[2 * h + 1] << sh) & 0xFFFF0000u;    // later sample
+                    sum = mlaw(b0, x0, sum);
+                    sum = mlaw(b1, bprev & 0xFFFF0000u, sum);
+                    sum = mlaw(b2, bprev << 16, sum);
+                    sum = mlaw(a1, aprev & 0xFFFF0000u, sum);
+                    sum = mlaw(a2, aprev << 16, sum);
+                    const int32_t o_lo = sat16(sum >> 14);
+                    sum &= 0x3FFF;
+                    sum = mlaw(b0, x1, sum);
+                    sum = mlaw(b1, x0, sum);
+                    sum = mlaw(b2, bprev & 0xFFFF0000u, sum);
+                    sum = mlaw(a1, (uint32_t)o_lo << 16, sum);
+                    sum = mlaw(a2, aprev & 0xFFFF0000u, sum);
+                    const int32_t o_hi = sat16(sum >> 14);
+                    sum &= 0x3FFF;
+                    bprev = (x0 >> 16) | x1;
+                    aprev = mk16(o_lo, o_hi);
+                    o[h] = aprev;
+                }
+                // re-interleave: the I lane has (I0|I1), (I2|I3); the Q lane has (Q0|Q1), (Q2|Q3)
+                const uint32_t p0 = __shfl_xor_sync(0x000000ffu, o[0], 1), p1 = __shfl_xor_sync(0x000000ffu, o[1], 1);
+                uint2 outw;
+                if (iq == 0) outw = make_uint2((o[0] & 0xFFFFu) | (p0 << 16), (o[0] >> 16) | (p0 & 0xFFFF0000u));      // frames 0, 1
+                else         outw = make_uint2((p1 & 0xFFFFu) | (o[1] << 16), (p1 >> 16) | (o[1] & 0xFFFF0000u));      // frames 2, 3
+                *reinterpret_cast<uint2 *>(&s_out[row][((j + row) & 31) * 16 + iq * 8]) = outw;
             }
-            // re-interleave: the I lane has (I0|I1), (I2|I3); the Q lane has (Q0|Q1), (Q2|Q3)
-            const uint32_t p0 = __shfl_xor_sync(0xffffffffu, o[0], 1), p1 = __shfl_xor_sync(0xffffffffu, o[1], 1);
-            uint2 outw;
-            if (iq == 0) outw = make_uint2((o[0] & 0xFFFFu) | (p0 << 16), (o[0] >> 16) | (p0 & 0xFFFF0000u));      // frames 0, 1
-            else         outw = make_uint2((p1 & 0xFFFFu) | (o[1] << 16), (p1 >> 16) | (o[1] & 0xFFFF0000u));      // frames 2, 3
-            *reinterpret_cast<uint2 *>(&s_out[row][((j + row) & 31) * 16 + iq * 8]) = outw;
         }
         __syncwarp();
-#pragma unroll 4
-        for (int r = 0; r < 16; r++)
+#pragma unroll
+        for (int r = 0; r < R; r++)
             if (ch0 + r < a.C)
                 *reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(a.out + ((size_t)t * a.C + ch0 + r) * 2 * RDSP_BLK) + lane * 16) =
                     *reinterpret_cast<const int4 *>(&s_out[r][((lane + r) & 31) * 16]);
         __syncwarp();
     }
-    if (valid) {
+    if (walker) {
         int32_t *st = a.state + ((size_t)myc * 2 + iq) * 4;
         st[0] = (int32_t)bprev; st[1] = (int32_t)aprev; st[2] = sum;
     }
@@ -120,5 +125,5 @@ __global__ void __launch_bounds__(32) k_biquad(BiquadArgs a)
 
 void launch_biquad(const BiquadArgs &a, cudaStream_t st)
 {
-    k_biquad<<<(a.C + 15) / 16, 32, 0, st>>>(a);
+    k_biquad<<<(a.C + R - 1) / R, 32, 0, st>>>(a);
 }

@@ -103,9 +103,9 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
                     const float inv = __frcp_rn(energy + LMS_EPS);
                     float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll
-                    for (int i = 0; i < W; i += 2) {
-                        acc0 = fmaf(c[i], xw[(u - i + W) % W], acc0);
-                        acc1 = fmaf(c[i + 1], xw[(u - i - 1 + 2 * W) % W], acc1);
+                    for (int i = 0; i < W; i++) {
+                        if (i & 1) acc1 = fmaf(c[i], xw[(u - i + W) % W], acc1);
+                        else acc0 = fmaf(c[i], xw[(u - i + W) % W], acc0);
                     }
                     float sum = acc0 + acc1;
 #pragma unroll
@@ -164,13 +164,17 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
 void launch_nlms(const NlmsArgs &a, cudaStream_t st)
 {
     if (a.n_list <= 0) return;
-    // few channels: more lanes per channel (shorter dependent chain per sample);
-    // many channels: fewer lanes per channel (fewer shuffle/bookkeeping instructions per tap)
-    if (a.n_list >= 4096) {
-        const int cpb = NWARPS * (32 / 4);
-        k_nlms<4><<<(a.n_list + cpb - 1) / cpb, NWARPS * 32, 0, st>>>(a);
-    } else {
-        const int cpb = NWARPS * (32 / 8);
-        k_nlms<8><<<(a.n_list + cpb - 1) / cpb, NWARPS * 32, 0, st>>>(a);
+    // A warp cannot hide its own dependent-issue latency (dot -> shuffles -> update, per sample), so pick the number
+    // of lanes per channel that puts about four warps on every SM sub-partition: few channels => many lanes each.
+    const long want = 4L * 4 * 148;
+    int G = 4;
+    while (G < 32 && (long)a.n_list * G / 32 < want) G *= 2;
+    const int cpb = NWARPS * (32 / G);
+    const int grid = (a.n_list + cpb - 1) / cpb;
+    switch (G) {
+    case 4:  k_nlms<4><<<grid, NWARPS * 32, 0, st>>>(a); break;
+    case 8:  k_nlms<8><<<grid, NWARPS * 32, 0, st>>>(a); break;
+    case 16: k_nlms<16><<<grid, NWARPS * 32, 0, st>>>(a); break;
+    default: k_nlms<32><<<grid, NWARPS * 32, 0, st>>>(a); break;
     }
 }

@@ -38,10 +38,10 @@ def to_rd_params(rd, p):
 def run_both(rd, po, stage_mask, params, iq, blocks_per_call=None, **cfgkw):
     """params: list of pyoracle Params per channel.  Returns (gpu_out, gpu_f32, ora_out, ora_f32, bank, chans)."""
     nb, nc = iq.shape[:2]
-    bank = make_bank(rd, nc, stage_mask, max_blocks=nb, **cfgkw)
+    step = blocks_per_call or nb
+    bank = make_bank(rd, nc, stage_mask, max_blocks=step, **cfgkw)
     for c, p in enumerate(params):
         bank.set_mode(c, 1, to_rd_params(rd, p))
-    step = blocks_per_call or nb
     outs, f32s = [], []
     for b0 in range(0, nb, step):
         chunk = np.ascontiguousarray(iq[b0:b0 + step])
