@@ -349,6 +349,7 @@ def run_b200(args):
     e0.record(stream)
     for i in range(K):
         e2e_bank.process_blocks(T, h_in[(W + i) % NB], h_out[i % 2])
+    e2e_bank.stream_join()                             # the last device-to-host copies are part of the timed region
     e1.record(stream)
     e2e_bank.synchronize()
     barrier()

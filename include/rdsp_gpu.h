@@ -164,7 +164,15 @@ int  rdsp_gpu_process_block(rdsp_gpu_t *h, const int16_t *iq_in, int16_t *audio_
 /* n_blocks sequential ticks: iq_in [n_blocks][n_channels][128][2], same for audio_out. */
 int  rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_in, int16_t *audio_out);
 
+/* Blocks the host until every call issued so far is complete, including the device-to-host copies of
+ * RDSP_IO_HOST handles. */
 int  rdsp_gpu_synchronize(rdsp_gpu_t *h);
+
+/* RDSP_IO_HOST + async: copies run on the handle's own copy streams so that they overlap the kernels of the
+ * neighbouring calls.  rdsp_gpu_stream_join makes the handle's stream wait (on the device, without blocking
+ * the host) for all outstanding device-to-host copies, so that an event recorded on the stream afterwards
+ * covers them.  A no-op for RDSP_IO_DEVICE handles. */
+int  rdsp_gpu_stream_join(rdsp_gpu_t *h);
 
 /* Use the caller's CUDA stream (a cudaStream_t passed as void*); NULL = the handle's own. */
 int  rdsp_gpu_set_stream(rdsp_gpu_t *h, void *cuda_stream);

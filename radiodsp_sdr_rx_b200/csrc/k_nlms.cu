@@ -164,17 +164,13 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
 void launch_nlms(const NlmsArgs &a, cudaStream_t st)
 {
     if (a.n_list <= 0) return;
-    // A warp cannot hide its own dependent-issue latency (dot -> shuffles -> update, per sample), so pick the number
-    // of lanes per channel that puts about four warps on every SM sub-partition: few channels => many lanes each.
-    const long want = 4L * 4 * 148;
-    int G = 4;
-    while (G < 32 && (long)a.n_list * G / 32 < want) G *= 2;
+    // Every channel is one dependent chain (dot -> shuffles -> update, per sample); all chains are resident at once,
+    // so the kernel runs at (channels / chain latency).  Measured on B200 (profiles/): 4 or 8 lanes per channel give
+    // the same duration as 16 or 32 with a third of the instructions, which leaves issue slots to the kernels that
+    // run beside it on the spectrum stream.
+    const int G = a.n_list >= 4096 ? 4 : 8;
     const int cpb = NWARPS * (32 / G);
     const int grid = (a.n_list + cpb - 1) / cpb;
-    switch (G) {
-    case 4:  k_nlms<4><<<grid, NWARPS * 32, 0, st>>>(a); break;
-    case 8:  k_nlms<8><<<grid, NWARPS * 32, 0, st>>>(a); break;
-    case 16: k_nlms<16><<<grid, NWARPS * 32, 0, st>>>(a); break;
-    default: k_nlms<32><<<grid, NWARPS * 32, 0, st>>>(a); break;
-    }
+    if (G == 4) k_nlms<4><<<grid, NWARPS * 32, 0, st>>>(a);
+    else k_nlms<8><<<grid, NWARPS * 32, 0, st>>>(a);
 }

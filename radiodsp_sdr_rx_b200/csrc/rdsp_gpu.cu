@@ -38,6 +38,12 @@ struct rdsp_gpu {
     cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaStream_t spec_stream = nullptr;        // the spectrum path (k_biquad, k_spec256) runs beside the audio path
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // IO_HOST: copies run on their own streams over double-buffered staging, so that the H2D of call n+1 and the
+    // D2H of call n-1 overlap the kernels of call n (async handles)
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    int16_t *d_in_stage2[2] = {nullptr, nullptr}, *d_out_stage2[2] = {nullptr, nullptr};
+    unsigned long long host_calls = 0;
     std::string err;
 
     // parameters
@@ -77,7 +83,6 @@ struct rdsp_gpu {
     int16_t *d_mid_a = nullptr, *d_mid_b = nullptr;
     float *d_scr = nullptr, *d_dbg = nullptr;
     int16_t *d_hp_iq = nullptr;                // high-passed IQ between k_biquad and k_spec256
-    int16_t *d_in_stage = nullptr, *d_out_stage = nullptr;
 
     // tick bookkeeping (uniform over channels)
     int spec_have_prev = 0, spec_count = 0;
@@ -282,8 +287,17 @@ void free_all(rdsp_gpu *h)
                     h->d_tw256, h->d_fe_hist, h->d_nc_coeff, h->d_nc_prev, h->d_nc_energy, h->d_nc_first, h->d_dn_coeff,
                     h->d_dn_prev, h->d_dn_energy, h->d_dn_first, h->d_agc_env, h->d_conv_last, h->d_nfloor, h->d_bq_state,
                     h->d_spec_prev, h->d_spec_sum, h->d_spec_out, h->d_ring, h->d_spec1024_out, h->d_view, h->d_smeter,
-                    h->d_mid_a, h->d_mid_b, h->d_scr, h->d_dbg, h->d_hp_iq, h->d_in_stage, h->d_out_stage};
+                    h->d_mid_a, h->d_mid_b, h->d_scr, h->d_dbg, h->d_hp_iq};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < 2; i++) {
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+        if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+        if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+        if (h->d_in_stage2[i]) cudaFree(h->d_in_stage2[i]);
+        if (h->d_out_stage2[i]) cudaFree(h->d_out_stage2[i]);
+    }
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->spec_stream) cudaStreamDestroy(h->spec_stream);
@@ -472,8 +486,15 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     }
     if (cfg->debug_f32) CKC(dalloc(&h->d_dbg, T * C * 2 * RDSP_BLK));
     if (cfg->io_location == RDSP_IO_HOST) {
-        CKC(dalloc(&h->d_in_stage, T * C * 2 * RDSP_BLK));
-        CKC(dalloc(&h->d_out_stage, T * C * 2 * RDSP_BLK));
+        CKC(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+        CKC(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CKC(dalloc(&h->d_in_stage2[i], T * C * 2 * RDSP_BLK));
+            CKC(dalloc(&h->d_out_stage2[i], T * C * 2 * RDSP_BLK));
+            CKC(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+            CKC(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+            CKC(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
+        }
     }
 #undef CKC
     h->par_dirty = true;
@@ -531,6 +552,18 @@ int rdsp_gpu_synchronize(rdsp_gpu_t *h)
     if (!h) return RDSP_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->d2h_stream) CK(cudaStreamSynchronize(h->d2h_stream));
+    if (h->h2d_stream) CK(cudaStreamSynchronize(h->h2d_stream));
+    return RDSP_OK;
+}
+
+int rdsp_gpu_stream_join(rdsp_gpu_t *h)
+{
+    if (!h) return RDSP_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->d2h_stream) {
+        for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(h->stream, h->ev_d2h[i], 0));
+    }
     return RDSP_OK;
 }
 
@@ -552,14 +585,23 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
     const size_t io_bytes = (size_t)T * C * 2 * RDSP_BLK * sizeof(int16_t);
     const int16_t *iq = iq_in;
     int16_t *audio = audio_out;
-    if (h->cfg.io_location == RDSP_IO_HOST) {
-        CK(cudaMemcpyAsync(h->d_in_stage, iq_in, io_bytes, cudaMemcpyHostToDevice, h->stream));
-        iq = h->d_in_stage;
-        audio = h->d_out_stage;
-    }
+    const bool host_io = h->cfg.io_location == RDSP_IO_HOST;
+    const int hb = (int)(h->host_calls & 1);
     cudaStream_t st = h->stream;
+    if (host_io) {
+        // staging buffer hb was last read by the kernels of call n-2 and last drained by the D2H of call n-2
+        CK(cudaStreamWaitEvent(h->h2d_stream, h->ev_comp[hb], 0));
+        CK(cudaMemcpyAsync(h->d_in_stage2[hb], iq_in, io_bytes, cudaMemcpyHostToDevice, h->h2d_stream));
+        CK(cudaEventRecord(h->ev_h2d[hb], h->h2d_stream));
+        CK(cudaStreamWaitEvent(st, h->ev_h2d[hb], 0));
+        CK(cudaStreamWaitEvent(st, h->ev_d2h[hb], 0));
+        iq = h->d_in_stage2[hb];
+        audio = h->d_out_stage2[hb];
+    }
 
-    const bool spec_fork = has(h, RDSP_STAGE_SPEC256) && audio_path;   // spectrum path beside the audio path
+    // spectrum path beside the audio path; while per-kernel profiling is on everything runs on one stream so that
+    // each kernel's event-bracketed time is its own (not stretched by a concurrent neighbour)
+    const bool spec_fork = has(h, RDSP_STAGE_SPEC256) && audio_path && !h->profiling;
     cudaStream_t sst = spec_fork ? h->spec_stream : st;
     if (spec_fork) {
         CK(cudaEventRecord(h->ev_fork, st));                             // the input (and earlier calls) are in place
@@ -653,9 +695,19 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
     if (spec_fork) CK(cudaStreamWaitEvent(st, h->ev_join, 0));          // join: the call is complete when both paths are
     CK(cudaGetLastError());
 
-    if (h->cfg.io_location == RDSP_IO_HOST && audio_path)
-        CK(cudaMemcpyAsync(audio_out, h->d_out_stage, io_bytes, cudaMemcpyDeviceToHost, h->stream));
-    if (!h->cfg.async) CK(cudaStreamSynchronize(h->stream));
+    if (host_io) {
+        CK(cudaEventRecord(h->ev_comp[hb], st));
+        if (audio_path) {
+            CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_comp[hb], 0));
+            CK(cudaMemcpyAsync(audio_out, h->d_out_stage2[hb], io_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
+            CK(cudaEventRecord(h->ev_d2h[hb], h->d2h_stream));
+        }
+        h->host_calls++;
+    }
+    if (!h->cfg.async) {
+        CK(cudaStreamSynchronize(h->stream));
+        if (host_io) CK(cudaStreamSynchronize(h->d2h_stream));
+    }
     return RDSP_OK;
 }
 

@@ -24,7 +24,7 @@ TAPS_HILBERT_I, TAPS_HILBERT_Q, TAPS_BANDPASS = range(3)
 ABI_SYMBOLS = [
     "rdsp_gpu_default_config", "rdsp_gpu_default_params", "rdsp_gpu_create", "rdsp_gpu_destroy",
     "rdsp_gpu_set_mode", "rdsp_gpu_get_mode", "rdsp_gpu_process_block", "rdsp_gpu_process_blocks",
-    "rdsp_gpu_synchronize", "rdsp_gpu_set_stream", "rdsp_gpu_read_spectrum", "rdsp_gpu_read_audio_spectrum",
+    "rdsp_gpu_synchronize", "rdsp_gpu_stream_join", "rdsp_gpu_set_stream", "rdsp_gpu_read_spectrum", "rdsp_gpu_read_audio_spectrum",
     "rdsp_gpu_read_panadapter", "rdsp_gpu_set_taps", "rdsp_gpu_get_taps", "rdsp_gpu_set_mask", "rdsp_gpu_get_mask",
     "rdsp_gpu_read_debug_f32", "rdsp_gpu_kernel_launches", "rdsp_gpu_profile", "rdsp_gpu_profile_read",
     "rdsp_gpu_last_error", "rdsp_gpu_version",
@@ -83,6 +83,7 @@ def lib():
         L.rdsp_gpu_process_block.argtypes = [vp, vp, vp]
         L.rdsp_gpu_process_blocks.argtypes = [vp, u32, vp, vp]
         L.rdsp_gpu_synchronize.argtypes = [vp]
+        L.rdsp_gpu_stream_join.argtypes = [vp]
         L.rdsp_gpu_set_stream.argtypes = [vp, vp]
         L.rdsp_gpu_read_spectrum.argtypes = [vp, u32, u32, vp, vp]
         L.rdsp_gpu_read_audio_spectrum.argtypes = [vp, u32, u32, vp, vp]
@@ -206,6 +207,9 @@ class ReceiverBank:
 
     def synchronize(self):
         self._ck(lib().rdsp_gpu_synchronize(self._h))
+
+    def stream_join(self):
+        self._ck(lib().rdsp_gpu_stream_join(self._h))
 
     def set_stream(self, cuda_stream: int):
         self._ck(lib().rdsp_gpu_set_stream(self._h, cuda_stream))
