@@ -87,3 +87,23 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 code = "\n".join(l for l in txt.splitlines() if not l.strip().startswith(("//", "#", "*", "/*", '"""')))
                 assert "pyoracle" not in code and "liboracle" not in code and "rdsp_oracle" not in code, os.path.join(dp, f)
+
+
+def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(tmp_path, rd):
+    """the C++ stub a maintainer would use (host/rdsp_sketch_api.hpp, examples/sketch_port.cpp) builds against the ABI"""
+    import shutil
+    import subprocess
+    import torch
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("g++ not available")
+    exe = str(tmp_path / "sketch_port")
+    libdir = os.path.join(ROOT, "radiodsp_sdr_rx_b200")
+    r = subprocess.run([gxx, "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "examples", "sketch_port.cpp"),
+                        "-L" + libdir, "-lrdsp_gpu", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "4"], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stderr
+    else:
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
