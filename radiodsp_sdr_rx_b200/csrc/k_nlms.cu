@@ -6,44 +6,57 @@
 // same block).  K6 emits the estimate y (x1.1, L = R, RDSP_convolutional.h:332-336),
 // K3 emits the error d - y.
 //
-// The recurrence is sequential in time (coefficients at sample n depend on the error at n-1), so the
-// parallelism is across channels and across taps: G lanes per channel, W = 96/G taps per lane held in
-// registers together with a W-deep circular window of the delayed input (static indices through
-// unrolling by W).  Per sample: W FMAs (dot) + log2(G) xor-shuffles + W FMAs (update); the normaliser
-// 1/(energy + eps) is computed off the critical path.  Channels per warp = 32/G.
+// The textbook recurrence (per sample: 96-tap dot -> error -> 96-tap update) is one long dependent chain per
+// channel, and with only thousands of channels a B200 cannot hide it.  The kernel therefore evaluates the SAME
+// recurrence four samples at a time with the tap-sized work taken out of the chain (exact algebra, no
+// approximation; only the f32 summation order changes):
 //
-// The per-channel state in HBM is coefficients (384 B) + previous block (512 B) + energy: the CMSIS
-// state buffer (last 95 inputs) and x0 are a suffix of the previous block, so they are not stored twice.
+//     c[n+j] = c[n] + sum_{i<j} g[i] x[n+i]          (g = mu e / (energy + eps), x[m] = the 96-sample window at m)
+//     y[n+j] = c[n+j]' x[n+j] = p[j] + sum_{i<j} g[i] R[i][j],   p[j] = c[n]' x[n+j],   R[i][j] = x[n+i]' x[n+j]
+//
+//   * p[0..3] are four independent 96-tap dot products against the coefficients at the start of the group
+//     (registers, G lanes per channel, xor-shuffle reductions that pipeline);
+//   * R[i][j] = s_{j-i}(n+j) comes from three lag-autocorrelations kept as running sums (2 FMAs per lag per
+//     sample, re-anchored exactly at every call), like the energy term CMSIS itself keeps;
+//   * what remains sequential is a scalar chain of one subtract, one multiply and one FMA per sample;
+//   * the coefficient update c += sum_j g[j] x[n+j] is four independent FMAs per tap.
+//
+// G = 4 or 8 lanes per channel, W = 96/G taps per lane in registers together with a circular window of the
+// delayed input (static indices through unrolling); the block sits in shared memory with a row stride that
+// keeps every 16-byte access of a quarter-warp on distinct banks.
+//
+// The per-channel state in HBM is coefficients (384 B) + previous block (512 B) + energy: the CMSIS state
+// buffer (last 95 inputs), x0 and the lag sums are functions of the previous block, so they are not stored.
 #include "rdsp_common.cuh"
 #include "kernels.h"
 
 namespace {
 
 constexpr int NWARPS = 2;
-constexpr int XS = 257;
-
-__device__ __forceinline__ void st4(float *p, float4 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
-__device__ __forceinline__ float4 ld4(const float *p) { return make_float4(p[0], p[1], p[2], p[3]); }
+constexpr int XS = 260;                      // floats per row: 16-byte aligned, rows 4 banks apart
+constexpr int D = 4;                         // samples per group
 constexpr float LMS_EPS = 0.000000119209289f;
+
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
 template <int G>
 __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
 {
-    constexpr int W = RDSP_LMS_NTAPS / G;        // taps per lane
+    constexpr int W = RDSP_LMS_NTAPS / G;        // taps per lane (24 or 12)
+    constexpr int S = W + D;                     // circular window (slots = lane-relative sample index mod S)
     constexpr int CPW = 32 / G;                  // channels per warp
-    // [0,128) previous block / outputs, [128,256) current.  Row stride 257: the 32/G channels of a warp and the G
-    // lanes of a channel (offsets -W*g, W a multiple of 4) then hit 32 different banks on every access.
-    __shared__ float s_x[NWARPS * CPW][XS];
+    static_assert(W % 4 == 0, "taps per lane must be a multiple of 4");
+    __shared__ __align__(16) float s_x[NWARPS * CPW][XS];     // [0,128) previous block / outputs, [128,256) current
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane % G;                      // lane within the channel group
-    const int slot = warp * CPW + lane / G;
     const int li = (blockIdx.x * NWARPS + warp) * CPW + lane / G;
     const bool active = li < a.n_list;
     const int ch = active ? (a.list ? a.list[li] : li) : 0;
-    float *xb = s_x[slot];
+    float *xb = s_x[warp * CPW + lane / G];
 
-    float c[W], xw[W];
+    float c[W], u[S];
     float energy = 0.0f, mu = 0.0f;
     bool first = false;
     if (active) {
@@ -60,6 +73,26 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
 #pragma unroll
         for (int i = 0; i < W; i++) c[i] = 0.0f;
         for (int i = g; i < 32; i += G) st4(xb + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    __syncwarp();
+
+    // lag sums s_l = x[b-l]' x[b] at b = -1 (the sample before this call's first), l = 1..3, from the previous block
+    float s1, s2, s3;
+    {
+        float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+        for (int k = g; k < RDSP_LMS_NTAPS; k += G) {
+            const float xk = xb[127 - k];
+            t1 = fmaf(xb[126 - k], xk, t1);
+            t2 = fmaf(xb[125 - k], xk, t2);
+            t3 = fmaf(xb[124 - k], xk, t3);
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+            t3 += __shfl_xor_sync(0xffffffffu, t3, o);
+        }
+        s1 = t1; s2 = t2; s3 = t3;
     }
 
     for (int t = 0; t < a.T; t++) {
@@ -84,37 +117,94 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
         }
         __syncwarp();
 
-        // ---- window of this lane before sample 0: delays 1..W-1 relative to x[0 - W*g]
+        // ---- lane-relative window u[m] = x[m - W*g]; slots m mod S.  Before sample 0: m = -W .. -1
 #pragma unroll
-        for (int i = 1; i < W; i++) xw[(W - i) % W] = xb[128 - W * g - i];
+        for (int q = 0; q < W / 4; q++) {
+            const float4 v = ld4(xb + 128 - W * g - W + 4 * q);             // m = -W + 4q .. -W + 4q + 3
+            u[(S - W + 4 * q + 0) % S] = v.x; u[(S - W + 4 * q + 1) % S] = v.y;
+            u[(S - W + 4 * q + 2) % S] = v.z; u[(S - W + 4 * q + 3) % S] = v.w;
+        }
+        float4 xn_p = ld4(xb + 124);                 // x[-4..-1]
+        float4 xo_p = ld4(xb + 28);                  // x[-100..-97]
         const bool same_block_ref = first && t == 0;
 
-        for (int n0 = 0; n0 < RDSP_BLK; n0 += W) {
+        for (int n0 = 0; n0 < RDSP_BLK; n0 += S) {
 #pragma unroll
-            for (int u = 0; u < W; u++) {
-                const int n = n0 + u;
+            for (int gq = 0; gq < S / 4; gq++) {
+                const int n = n0 + 4 * gq;
                 if (n < RDSP_BLK) {
-                    xw[u] = xb[128 + n - W * g];              // newest sample of this lane's window
-                    const float xn = xb[128 + n];             // in
-                    const float x0 = xb[32 + n];              // x[n-96], leaves the window
-                    const float d = same_block_ref ? xn : xb[n];
-                    energy = __fsub_rn(energy, __fmul_rn(x0, x0));
-                    energy = __fadd_rn(energy, __fmul_rn(xn, xn));
-                    const float inv = __frcp_rn(energy + LMS_EPS);
-                    float acc0 = 0.0f, acc1 = 0.0f;
+                    const int sb = 4 * gq;                                  // slot of u[n] (n0 is a multiple of S)
+                    // ---- loads
+                    const float4 un = ld4(xb + 128 + n - W * g);
+                    u[(sb + 0) % S] = un.x; u[(sb + 1) % S] = un.y; u[(sb + 2) % S] = un.z; u[(sb + 3) % S] = un.w;
+                    const float4 xn4 = ld4(xb + 128 + n);                   // in[n..n+3]
+                    const float4 xo4 = ld4(xb + 32 + n);                    // x[n-96 .. n-93]
+                    const float4 d4 = same_block_ref ? xn4 : ld4(xb + n);   // desired
+                    const float xn[4] = {xn4.x, xn4.y, xn4.z, xn4.w};
+                    const float xo[4] = {xo4.x, xo4.y, xo4.z, xo4.w};
+                    const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+                    // recent / old samples around the group: index 4 + j <-> sample n + j
+                    const float xr[8] = {xn_p.x, xn_p.y, xn_p.z, xn_p.w, xn4.x, xn4.y, xn4.z, xn4.w};   // x[n-4 .. n+3]
+                    const float xq[8] = {xo_p.x, xo_p.y, xo_p.z, xo_p.w, xo4.x, xo4.y, xo4.z, xo4.w};   // x[n-100 .. n-93]
+
+                    // ---- p[j] = c' x[n+j] with the coefficients at the start of the group
+                    float p0[4], p1[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { p0[j] = 0.f; p1[j] = 0.f; }
 #pragma unroll
                     for (int i = 0; i < W; i++) {
-                        if (i & 1) acc1 = fmaf(c[i], xw[(u - i + W) % W], acc1);
-                        else acc0 = fmaf(c[i], xw[(u - i + W) % W], acc0);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float uv = u[(sb + j - i + 2 * S) % S];
+                            if (i & 1) p1[j] = fmaf(c[i], uv, p1[j]);
+                            else p0[j] = fmaf(c[i], uv, p0[j]);
+                        }
                     }
-                    float sum = acc0 + acc1;
+                    float p[4];
 #pragma unroll
-                    for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                    const float e = d - sum;
-                    const float w = (e * mu) * inv;
+                    for (int j = 0; j < 4; j++) p[j] = p0[j] + p1[j];
 #pragma unroll
-                    for (int i = 0; i < W; i++) c[i] = fmaf(w, xw[(u - i + W) % W], c[i]);
-                    if (g == 0) xb[n] = a.mode ? sum : e;    // slot n of the previous block is dead after d was read
+                    for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) p[j] += __shfl_xor_sync(0xffffffffu, p[j], o);
+                    }
+
+                    // ---- scalars that do not depend on the error: energy, normaliser, lag sums
+                    float qn[4], r1[4], r2[4], r3[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        energy = __fsub_rn(energy, __fmul_rn(xo[j], xo[j]));
+                        energy = __fadd_rn(energy, __fmul_rn(xn[j], xn[j]));
+                        qn[j] = mu * __frcp_rn(energy + LMS_EPS);
+                        // s_l(b) = s_l(b-1) + x[b-l] x[b] - x[b-l-96] x[b-96],  b = n + j
+                        s1 = fmaf(xr[4 + j - 1], xn[j], s1); s1 = fmaf(-xq[4 + j - 1], xo[j], s1);
+                        s2 = fmaf(xr[4 + j - 2], xn[j], s2); s2 = fmaf(-xq[4 + j - 2], xo[j], s2);
+                        s3 = fmaf(xr[4 + j - 3], xn[j], s3); s3 = fmaf(-xq[4 + j - 3], xo[j], s3);
+                        r1[j] = s1; r2[j] = s2; r3[j] = s3;
+                    }
+
+                    // ---- the sequential part: one subtract, one multiply, one FMA per sample
+                    float y[4], e[4], gj[4];
+                    y[0] = p[0];
+                    e[0] = dd[0] - y[0]; gj[0] = e[0] * qn[0];
+                    y[1] = fmaf(gj[0], r1[1], p[1]);
+                    e[1] = dd[1] - y[1]; gj[1] = e[1] * qn[1];
+                    y[2] = fmaf(gj[1], r1[2], fmaf(gj[0], r2[2], p[2]));
+                    e[2] = dd[2] - y[2]; gj[2] = e[2] * qn[2];
+                    y[3] = fmaf(gj[2], r1[3], fmaf(gj[1], r2[3], fmaf(gj[0], r3[3], p[3])));
+                    e[3] = dd[3] - y[3]; gj[3] = e[3] * qn[3];
+
+                    if (g == 0)
+                        st4(xb + n, a.mode ? make_float4(y[0], y[1], y[2], y[3]) : make_float4(e[0], e[1], e[2], e[3]));
+
+                    // ---- coefficient update c += sum_j g[j] x[n+j]
+#pragma unroll
+                    for (int i = 0; i < W; i++) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) c[i] = fmaf(gj[j], u[(sb + j - i + 2 * S) % S], c[i]);
+                    }
+                    xn_p = xn4;
+                    xo_p = xo4;
                 }
             }
         }
@@ -129,9 +219,9 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
                 int4 *dst = reinterpret_cast<int4 *>(a.out_stereo + cb * 2 * RDSP_BLK);
                 float4 *dbg = a.dbg ? reinterpret_cast<float4 *>(a.dbg + cb * 2 * RDSP_BLK) : nullptr;
                 for (int i = g; i < 32; i += G) {
-                    const float4 y = ld4(xb + 4 * i);
-                    const float f0 = (float)((double)y.x * 1.1), f1 = (float)((double)y.y * 1.1);
-                    const float f2 = (float)((double)y.z * 1.1), f3 = (float)((double)y.w * 1.1);
+                    const float4 yv = ld4(xb + 4 * i);
+                    const float f0 = (float)((double)yv.x * 1.1), f1 = (float)((double)yv.y * 1.1);
+                    const float f2 = (float)((double)yv.z * 1.1), f3 = (float)((double)yv.w * 1.1);
                     const int32_t q0 = f32_to_q15(f0), q1 = f32_to_q15(f1), q2 = f32_to_q15(f2), q3 = f32_to_q15(f3);
                     dst[i] = make_int4((int)mk16(q0, q0), (int)mk16(q1, q1), (int)mk16(q2, q2), (int)mk16(q3, q3));
                     if (dbg) {
@@ -164,10 +254,8 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
 void launch_nlms(const NlmsArgs &a, cudaStream_t st)
 {
     if (a.n_list <= 0) return;
-    // Every channel is one dependent chain (dot -> shuffles -> update, per sample); all chains are resident at once,
-    // so the kernel runs at (channels / chain latency).  Measured on B200 (profiles/): 4 or 8 lanes per channel give
-    // the same duration as 16 or 32 with a third of the instructions, which leaves issue slots to the kernels that
-    // run beside it on the spectrum stream.
+    // 4 lanes per channel minimise instructions (the reductions are two shuffle stages); below ~4k channels 8 lanes
+    // keep every SM sub-partition supplied with a warp
     const int G = a.n_list >= 4096 ? 4 : 8;
     const int cpb = NWARPS * (32 / G);
     const int grid = (a.n_list + cpb - 1) / cpb;
