@@ -16,8 +16,8 @@
 //
 //   * p[0..3] are four independent 96-tap dot products against the coefficients at the start of the group
 //     (registers, G lanes per channel, xor-shuffle reductions that pipeline);
-//   * R[i][j] = s_{j-i}(n+j) comes from three lag-autocorrelations kept as running sums (2 FMAs per lag per
-//     sample, re-anchored exactly at every call), like the energy term CMSIS itself keeps;
+//   * R[i][j] = s_{j-i}(n+j) comes from three lag-autocorrelations: anchored exactly on the register window at
+//     the start of the group (3 x 96 MACs over the G lanes), then slid over the 4 samples (2 FMAs per lag);
 //   * what remains sequential is a scalar chain of one subtract, one multiply and one FMA per sample;
 //   * the coefficient update c += sum_j g[j] x[n+j] is four independent FMAs per tap.
 //
@@ -29,6 +29,7 @@
 // buffer (last 95 inputs), x0 and the lag sums are functions of the previous block, so they are not stored.
 #include "rdsp_common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace {
 
@@ -76,25 +77,6 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
     }
     __syncwarp();
 
-    // lag sums s_l = x[b-l]' x[b] at b = -1 (the sample before this call's first), l = 1..3, from the previous block
-    float s1, s2, s3;
-    {
-        float t1 = 0.f, t2 = 0.f, t3 = 0.f;
-        for (int k = g; k < RDSP_LMS_NTAPS; k += G) {
-            const float xk = xb[127 - k];
-            t1 = fmaf(xb[126 - k], xk, t1);
-            t2 = fmaf(xb[125 - k], xk, t2);
-            t3 = fmaf(xb[124 - k], xk, t3);
-        }
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-            t1 += __shfl_xor_sync(0xffffffffu, t1, o);
-            t2 += __shfl_xor_sync(0xffffffffu, t2, o);
-            t3 += __shfl_xor_sync(0xffffffffu, t3, o);
-        }
-        s1 = t1; s2 = t2; s3 = t3;
-    }
-
     for (int t = 0; t < a.T; t++) {
         const size_t cb = (size_t)t * a.C + ch;
         // ---- stage the current block into xb[128..255]
@@ -117,12 +99,11 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
         }
         __syncwarp();
 
-        // ---- lane-relative window u[m] = x[m - W*g]; slots m mod S.  Before sample 0: m = -W .. -1
+        // ---- lane-relative window u[m] = x[m - W*g]; slots m mod S.  Before sample 0: m = -S .. -1 (all slots)
 #pragma unroll
-        for (int q = 0; q < W / 4; q++) {
-            const float4 v = ld4(xb + 128 - W * g - W + 4 * q);             // m = -W + 4q .. -W + 4q + 3
-            u[(S - W + 4 * q + 0) % S] = v.x; u[(S - W + 4 * q + 1) % S] = v.y;
-            u[(S - W + 4 * q + 2) % S] = v.z; u[(S - W + 4 * q + 3) % S] = v.w;
+        for (int q = 0; q < S / 4; q++) {
+            const float4 v = ld4(xb + 128 - W * g - S + 4 * q);             // m = -S + 4q .. -S + 4q + 3
+            u[(4 * q + 0) % S] = v.x; u[(4 * q + 1) % S] = v.y; u[(4 * q + 2) % S] = v.z; u[(4 * q + 3) % S] = v.w;
         }
         float4 xn_p = ld4(xb + 124);                 // x[-4..-1]
         float4 xo_p = ld4(xb + 28);                  // x[-100..-97]
@@ -134,6 +115,24 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
                 const int n = n0 + 4 * gq;
                 if (n < RDSP_BLK) {
                     const int sb = 4 * gq;                                  // slot of u[n] (n0 is a multiple of S)
+                    // ---- lag sums s_l(n-1) = x[n-1-l]' x[n-1], l = 1..3, anchored EXACTLY on the window at every group
+                    // (the window still holds m = n-W-4 .. n-1).  A running sum carried across groups would lose all
+                    // its digits when the signal drops by orders of magnitude inside the window, exactly where
+                    // 1/(energy + eps) amplifies every error.
+                    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < W; i++) {
+                        const float uk = u[(sb - 1 - i + 2 * S) % S];
+                        s1 = fmaf(u[(sb - 2 - i + 2 * S) % S], uk, s1);
+                        s2 = fmaf(u[(sb - 3 - i + 2 * S) % S], uk, s2);
+                        s3 = fmaf(u[(sb - 4 - i + 2 * S) % S], uk, s3);
+                    }
+#pragma unroll
+                    for (int o = G / 2; o > 0; o >>= 1) {
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                        s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+                    }
                     // ---- loads
                     const float4 un = ld4(xb + 128 + n - W * g);
                     u[(sb + 0) % S] = un.x; u[(sb + 1) % S] = un.y; u[(sb + 2) % S] = un.z; u[(sb + 3) % S] = un.w;
@@ -256,7 +255,8 @@ void launch_nlms(const NlmsArgs &a, cudaStream_t st)
     if (a.n_list <= 0) return;
     // 4 lanes per channel minimise instructions (the reductions are two shuffle stages); below ~4k channels 8 lanes
     // keep every SM sub-partition supplied with a warp
-    const int G = a.n_list >= 4096 ? 4 : 8;
+    int G = a.n_list >= 12288 ? 4 : 8;
+    if (const char *env = getenv("RDSP_NLMS_LANES")) G = atoi(env) == 4 ? 4 : 8;       // experiments only
     const int cpb = NWARPS * (32 / G);
     const int grid = (a.n_list + cpb - 1) / cpb;
     if (G == 4) k_nlms<4><<<grid, NWARPS * 32, 0, st>>>(a);
