@@ -250,9 +250,13 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
 
 }  // namespace
 
+void launch_nlms_direct(const NlmsArgs &a, cudaStream_t st);
+
 void launch_nlms(const NlmsArgs &a, cudaStream_t st)
 {
     if (a.n_list <= 0) return;
+    static const bool direct = [] { const char *e = getenv("RDSP_NLMS_IMPL"); return e && e[0] == 'd'; }();
+    if (direct) { launch_nlms_direct(a, st); return; }
     // 4 lanes per channel minimise instructions (the reductions are two shuffle stages); below ~4k channels 8 lanes
     // keep every SM sub-partition supplied with a warp
     int G = a.n_list >= 12288 ? 4 : 8;
