@@ -285,7 +285,8 @@ def run_b200(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)            # > 126 MB L2
 
     def new_bank(io):
-        cfg = rd.default_config(n_channels=C_, device=local, stage_mask=stage, max_blocks_per_call=T, io_location=io)
+        cfg = rd.default_config(n_channels=C_, device=local, stage_mask=stage, max_blocks_per_call=T, io_location=io,
+                                pipeline_chunks=args.pipeline_chunks)
         cfg.async_ = 1
         b = rd.ReceiverBank(cfg)
         # runs of identical parameters -> one set_mode per run would be ideal; the configs cycle with small periods,
@@ -387,7 +388,7 @@ def run_b200(args):
             "value": value, "unit": "MS/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "q15+f32", "data": "synthetic",
-            "config": {"workload": f"{wl}: {desc}", "channels_per_gpu": C_, "channels_total": world * C_, "blocks_per_call": T,
+            "config": {"workload": f"{wl}: {desc}", "channels_per_gpu": C_, "channels_total": world * C_, "blocks_per_call": T, "pipeline_chunks": args.pipeline_chunks or "auto",
                        "block_samples": BLK, "sample_rate_hz": FS, "sharding": "contiguous channel ranges, no collective on the hot path",
                        "l2": "256 MiB memset between timed steps; per-step CUDA events summed",
                        "realtime_channels": value / 0.0441, "realtime_channels_e2e": e2e_value / 0.0441,
@@ -427,6 +428,7 @@ def main():
     ap.add_argument("--channels", type=int, default=0, help="channels per GPU (default: the workload's)")
     ap.add_argument("--blocks-per-call", type=int, default=8)
     ap.add_argument("--input-batches", type=int, default=4)
+    ap.add_argument("--pipeline-chunks", type=int, default=0, help="wavefront chunks per call (0 = library default)")
     ap.add_argument("--cpu-channels-per-thread", type=int, default=32)
     ap.add_argument("--cpu-blocks", type=int, default=64)
     ap.add_argument("--cpu-reps", type=int, default=12)

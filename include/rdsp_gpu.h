@@ -125,6 +125,8 @@ typedef struct {
     float    agc_max_gain;       /* linear */
     float    agc_attack_ms;
     float    agc_decay_ms[4];    /* per RDSP_AGC_* mode; [RDSP_AGC_OFF] unused */
+    uint32_t pipeline_chunks;    /* process_blocks(T) advances through the stages as a wavefront of this many chunks
+                                    of blocks (0 = auto: min(T, 4); 1 = no overlap between stages; max 8) */
 } rdsp_gpu_config_t;
 
 typedef struct {

@@ -39,7 +39,7 @@ class Config(C.Structure):
         ("stage_mask", C.c_uint32), ("max_blocks_per_call", C.c_uint32), ("io_location", C.c_uint32),
         ("async_", C.c_uint32), ("debug_f32", C.c_uint32), ("spec256_naverage", C.c_uint32),
         ("agc_target", C.c_float), ("agc_max_gain", C.c_float), ("agc_attack_ms", C.c_float),
-        ("agc_decay_ms", C.c_float * 4),
+        ("agc_decay_ms", C.c_float * 4), ("pipeline_chunks", C.c_uint32),
     ]
 
 

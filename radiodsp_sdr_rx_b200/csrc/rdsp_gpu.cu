@@ -6,7 +6,8 @@
 //   audio path    : k_front (K0-K2) -> k_nlms<notch> (K3, listed channels) -> k_agc (K4)
 //                   -> k_fftfilt (K5/K8/K7) -> k_nlms<dnr> (K6, listed channels) -> k_spec1024 (K10)
 // Intermediates between kernels are int16 mono / f32 rows in handle-owned scratch (L2 resident at
-// the batch sizes of BASELINE.json); per-channel state makes one HBM round trip per call.
+// the batch sizes of BASELINE.json); per-channel state makes one HBM round trip per chunk.
+// Each stage has its own stream and the blocks of a call advance through the stages as a wavefront of chunks.
 #include "../../include/rdsp_gpu.h"
 #include "host_design.h"
 #include "kernels.h"
@@ -30,14 +31,19 @@ const char *const kKernelNames[KK_COUNT] = {"k_front", "k_nlms_notch", "k_agc", 
 
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
 
+constexpr int kStages = 8;
+constexpr int kMaxChunks = 8;
+
 }  // namespace
 
 struct rdsp_gpu {
     rdsp_gpu_config_t cfg;
     int C = 0, maxT = 1;
     cudaStream_t stream = nullptr, own_stream = nullptr;
-    cudaStream_t spec_stream = nullptr;        // the spectrum path (k_biquad, k_spec256) runs beside the audio path
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // one stream per stage of the graph + one event per (stage, chunk): the wavefront of process_blocks
+    cudaStream_t stage_stream[kStages] = {nullptr};
+    cudaEvent_t ev_stage[kStages][kMaxChunks] = {{nullptr}};
+    cudaEvent_t ev_fork = nullptr;
     // IO_HOST: copies run on their own streams over double-buffered staging, so that the H2D of call n+1 and the
     // D2H of call n-1 overlap the kernels of call n (async handles)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -299,8 +305,10 @@ void free_all(rdsp_gpu *h)
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
-    if (h->spec_stream) cudaStreamDestroy(h->spec_stream);
+    for (int s = 0; s < kStages; s++) {
+        for (int k = 0; k < kMaxChunks; k++) if (h->ev_stage[s][k]) cudaEventDestroy(h->ev_stage[s][k]);
+        if (h->stage_stream[s]) cudaStreamDestroy(h->stage_stream[s]);
+    }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
 }
 
@@ -363,6 +371,7 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     if ((sm & RDSP_STAGE_SPEC1024) && !(sm & (RDSP_STAGE_FRONTEND | RDSP_STAGE_FFTFILT))) { g_create_error = "SPEC1024 needs an audio path"; return RDSP_ERR_STATE; }
     if (cfg->spec256_naverage == 0 || cfg->spec256_naverage > 255) { g_create_error = "spec256_naverage must be 1..255"; return RDSP_ERR_RANGE; }
     if (cfg->io_location > RDSP_IO_HOST) { g_create_error = "io_location invalid"; return RDSP_ERR_RANGE; }
+    if (cfg->pipeline_chunks > (uint32_t)kMaxChunks) { g_create_error = "pipeline_chunks must be 0 (auto) .. 8"; return RDSP_ERR_RANGE; }
     if (!(cfg->agc_target > 0.f) || !(cfg->agc_max_gain > 0.f) || !(cfg->agc_attack_ms > 0.f)) { g_create_error = "AGC constants invalid"; return RDSP_ERR_RANGE; }
 
     int ndev = 0;
@@ -396,9 +405,11 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     CKC(cudaSetDevice(cfg->device));
     CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
-    CKC(cudaStreamCreateWithFlags(&h->spec_stream, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    CKC(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    for (int s = 0; s < kStages; s++) {
+        CKC(cudaStreamCreateWithFlags(&h->stage_stream[s], cudaStreamNonBlocking));
+        for (int k = 0; k < kMaxChunks; k++) CKC(cudaEventCreateWithFlags(&h->ev_stage[s][k], cudaEventDisableTiming));
+    }
 
     // host-side tables
     for (int m = 0; m < RDSP_DEMOD_COUNT; m++) rdsp_host::design_hilbert_pair(m, h->taps[m], h->taps[RDSP_DEMOD_COUNT + m]);
@@ -599,100 +610,155 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
         audio = h->d_out_stage2[hb];
     }
 
-    // spectrum path beside the audio path; while per-kernel profiling is on everything runs on one stream so that
-    // each kernel's event-bracketed time is its own (not stretched by a concurrent neighbour)
-    const bool spec_fork = has(h, RDSP_STAGE_SPEC256) && audio_path && !h->profiling;
-    cudaStream_t sst = spec_fork ? h->spec_stream : st;
-    if (spec_fork) {
+    // ---- wavefront over chunks of blocks ---------------------------------------------------------------
+    // Every stage of the graph has its own stream; the T blocks of the call are cut into chunks and stage s of
+    // chunk k waits (CUDA events) for its producers on chunk k, while stream order alone keeps a stage's own state
+    // in sequence.  So the front end of chunk k+1 runs beside the NLMS of chunk k and the spectrum path beside
+    // both: the issue-bound kernels fill the slots the latency-bound recurrences leave empty.  While per-kernel
+    // profiling is on, everything runs as one chunk on one stream so that each kernel's time is its own.
+    enum { ST_FRONT = 0, ST_NOTCH, ST_AGC, ST_FFT, ST_DNR, ST_S1024, ST_BIQ, ST_S256 };
+    const bool piped = !h->profiling;
+    int nchunks = 1;
+    if (piped) {
+        nchunks = h->cfg.pipeline_chunks ? (int)h->cfg.pipeline_chunks : 4;
+        if (nchunks > T) nchunks = T;
+        if (nchunks > kMaxChunks) nchunks = kMaxChunks;
         CK(cudaEventRecord(h->ev_fork, st));                             // the input (and earlier calls) are in place
-        CK(cudaStreamWaitEvent(h->spec_stream, h->ev_fork, 0));
+        for (int s = 0; s < kStages; s++) CK(cudaStreamWaitEvent(h->stage_stream[s], h->ev_fork, 0));
     }
-    if (has(h, RDSP_STAGE_SPEC256)) {
-        BiquadArgs b{};
-        b.iq = iq; b.out = h->d_hp_iq; b.state = h->d_bq_state; b.C = C; b.T = T;
-        b.b0 = h->bq[0]; b.b1 = h->bq[1]; b.b2 = h->bq[2]; b.a1 = h->bq[3]; b.a2 = h->bq[4];
-        { Prof pr(h, KK_BIQUAD, sst); launch_biquad(b, sst); }
-        Spec256Args a{};
-        a.iq = h->d_hp_iq; a.prev = h->d_spec_prev; a.sum = h->d_spec_sum; a.output = h->d_spec_out;
-        a.C = C; a.T = T; a.have_prev = h->spec_have_prev; a.count = h->spec_count; a.naverage = (int)h->cfg.spec256_naverage;
-        int lg = 0; while ((1u << lg) < h->cfg.spec256_naverage) lg++;
-        a.div_shift = 32 + lg;
-        a.div_magic = ((1ull << a.div_shift) + h->cfg.spec256_naverage - 1) / h->cfg.spec256_naverage;
-        a.tw = h->d_tw; a.win = h->d_win256;
-        { Prof pr(h, KK_SPEC256, sst); launch_spec256(a, sst); }
-        if (spec_fork) CK(cudaEventRecord(h->ev_join, h->spec_stream));
-        // host mirror of the uniform counters (analyze_fft256iq.cpp:73-77,99-113)
-        int updates = T - (h->spec_have_prev ? 0 : 1);
-        h->spec_have_prev = 1;
-        const int total = h->spec_count + updates;
-        if (total / (int)h->cfg.spec256_naverage > 0) std::fill(h->spec_ready.begin(), h->spec_ready.end(), (uint8_t)1);
-        h->spec_count = total % (int)h->cfg.spec256_naverage;
-    }
+    auto sstream = [&](int stage) { return piped ? h->stage_stream[stage] : st; };
+    auto wait_for = [&](int stage, int dep, int chunk) -> cudaError_t {
+        return piped ? cudaStreamWaitEvent(h->stage_stream[stage], h->ev_stage[dep][chunk], 0) : cudaSuccess;
+    };
+    auto done = [&](int stage, int chunk) -> cudaError_t {
+        return piped ? cudaEventRecord(h->ev_stage[stage][chunk], h->stage_stream[stage]) : cudaSuccess;
+    };
+    const int naverage = (int)h->cfg.spec256_naverage;
+    int lgn = 0; while ((1u << lgn) < h->cfg.spec256_naverage) lgn++;
 
-    const int16_t *mono = nullptr;
-    if (fe) {
-        const bool last = !(notch || agc || ff);
-        FrontArgs a{};
-        a.iq = iq; a.out_mono = last ? nullptr : h->d_mid_a; a.out_stereo = last ? audio : nullptr;
-        a.dbg = last ? h->d_dbg : nullptr; a.hist = h->d_fe_hist; a.par = h->d_par; a.taps = h->d_taps; a.C = C; a.T = T;
-        { Prof pr(h, KK_FRONT); launch_front(a, st); }
-        mono = h->d_mid_a;
-        if (notch && h->n_notch > 0) {
-            NlmsArgs n{};
-            n.list = h->d_list_notch; n.n_list = h->n_notch; n.C = C; n.T = T;
-            n.in_q15 = h->d_mid_a; n.out_f32 = h->d_scr;
-            n.coeff = h->d_nc_coeff; n.prev = h->d_nc_prev; n.energy = h->d_nc_energy; n.first = h->d_nc_first;
-            n.par = h->d_par; n.mode = 0;
-            { Prof pr(h, KK_NOTCH); launch_nlms(n, st); }
+    for (int k = 0; k < nchunks; k++) {
+        const int t0 = (int)((long long)T * k / nchunks), t1 = (int)((long long)T * (k + 1) / nchunks), Tc = t1 - t0;
+        const size_t o2 = (size_t)t0 * C * 2 * RDSP_BLK, o1 = (size_t)t0 * C * RDSP_BLK;     // stereo / mono row offsets
+        const int16_t *iq_k = iq + o2;
+        int16_t *audio_k = audio ? audio + o2 : nullptr;
+        float *dbg_k = h->d_dbg ? h->d_dbg + o2 : nullptr;
+
+        if (has(h, RDSP_STAGE_SPEC256)) {
+            BiquadArgs b{};
+            b.iq = iq_k; b.out = h->d_hp_iq + o2; b.state = h->d_bq_state; b.C = C; b.T = Tc;
+            b.b0 = h->bq[0]; b.b1 = h->bq[1]; b.b2 = h->bq[2]; b.a1 = h->bq[3]; b.a2 = h->bq[4];
+            { Prof pr(h, KK_BIQUAD, sstream(ST_BIQ)); launch_biquad(b, sstream(ST_BIQ)); }
+            CK(done(ST_BIQ, k));
+            Spec256Args a{};
+            a.iq = h->d_hp_iq + o2; a.prev = h->d_spec_prev; a.sum = h->d_spec_sum; a.output = h->d_spec_out;
+            a.C = C; a.T = Tc; a.have_prev = h->spec_have_prev; a.count = h->spec_count; a.naverage = naverage;
+            a.div_shift = 32 + lgn;
+            a.div_magic = ((1ull << a.div_shift) + h->cfg.spec256_naverage - 1) / h->cfg.spec256_naverage;
+            a.tw = h->d_tw; a.win = h->d_win256;
+            CK(wait_for(ST_S256, ST_BIQ, k));
+            { Prof pr(h, KK_SPEC256, sstream(ST_S256)); launch_spec256(a, sstream(ST_S256)); }
+            CK(done(ST_S256, k));
+            // host mirror of the uniform counters (analyze_fft256iq.cpp:73-77,99-113)
+            const int updates = Tc - (h->spec_have_prev ? 0 : 1);
+            h->spec_have_prev = 1;
+            const int total = h->spec_count + updates;
+            if (total / naverage > 0) std::fill(h->spec_ready.begin(), h->spec_ready.end(), (uint8_t)1);
+            h->spec_count = total % naverage;
         }
-        if (notch || agc) {
-            AgcArgs g{};
-            g.out_mono = ff ? h->d_mid_b : nullptr; g.out_stereo = ff ? nullptr : audio;
-            g.dbg = ff ? nullptr : h->d_dbg; g.env = h->d_agc_env; g.par = h->d_par; g.C = C; g.T = T;
-            g.agc_stage = agc ? 1 : 0;
-            g.target = h->cfg.agc_target; g.max_gain = h->cfg.agc_max_gain; g.alpha_a = h->agc_alpha_a;
-            // channels that bypassed the notch read the front end's q15 rows ...
-            g.list = notch ? h->d_list_plain : nullptr; g.n_list = notch ? h->n_plain : C;
-            g.in_q15 = h->d_mid_a; g.in_f32 = nullptr;
-            if (g.n_list > 0) { Prof pr(h, KK_AGC); launch_agc(g, st); }
-            // ... the others read the notch's f32 error signal
-            if (notch && h->n_notch > 0) {
-                g.list = h->d_list_notch; g.n_list = h->n_notch; g.in_q15 = nullptr; g.in_f32 = h->d_scr;
-                { Prof pr(h, KK_AGC); launch_agc(g, st); }
+
+        const int16_t *mono = nullptr;
+        int audio_src = -1;                                               // stage that completes `mono` / the audio so far
+        if (fe) {
+            const bool last = !(notch || agc || ff);
+            FrontArgs a{};
+            a.iq = iq_k; a.out_mono = last ? nullptr : h->d_mid_a + o1; a.out_stereo = last ? audio_k : nullptr;
+            a.dbg = last ? dbg_k : nullptr; a.hist = h->d_fe_hist; a.par = h->d_par; a.taps = h->d_taps; a.C = C; a.T = Tc;
+            { Prof pr(h, KK_FRONT, sstream(ST_FRONT)); launch_front(a, sstream(ST_FRONT)); }
+            CK(done(ST_FRONT, k));
+            mono = h->d_mid_a + o1;
+            audio_src = ST_FRONT;
+            if (notch) {
+                CK(wait_for(ST_NOTCH, ST_FRONT, k));
+                if (h->n_notch > 0) {
+                    NlmsArgs n{};
+                    n.list = h->d_list_notch; n.n_list = h->n_notch; n.C = C; n.T = Tc;
+                    n.in_q15 = h->d_mid_a + o1; n.out_f32 = h->d_scr + o1;
+                    n.coeff = h->d_nc_coeff; n.prev = h->d_nc_prev; n.energy = h->d_nc_energy; n.first = h->d_nc_first;
+                    n.par = h->d_par; n.mode = 0;
+                    { Prof pr(h, KK_NOTCH, sstream(ST_NOTCH)); launch_nlms(n, sstream(ST_NOTCH)); }
+                }
+                CK(done(ST_NOTCH, k));
             }
-            mono = h->d_mid_b;
+            if (notch || agc) {
+                CK(wait_for(ST_AGC, ST_FRONT, k));
+                if (notch) CK(wait_for(ST_AGC, ST_NOTCH, k));
+                AgcArgs g{};
+                g.out_mono = ff ? h->d_mid_b + o1 : nullptr; g.out_stereo = ff ? nullptr : audio_k;
+                g.dbg = ff ? nullptr : dbg_k; g.env = h->d_agc_env; g.par = h->d_par; g.C = C; g.T = Tc;
+                g.agc_stage = agc ? 1 : 0;
+                g.target = h->cfg.agc_target; g.max_gain = h->cfg.agc_max_gain; g.alpha_a = h->agc_alpha_a;
+                // channels that bypassed the notch read the front end's q15 rows ...
+                g.list = notch ? h->d_list_plain : nullptr; g.n_list = notch ? h->n_plain : C;
+                g.in_q15 = h->d_mid_a + o1; g.in_f32 = nullptr;
+                if (g.n_list > 0) { Prof pr(h, KK_AGC, sstream(ST_AGC)); launch_agc(g, sstream(ST_AGC)); }
+                // ... the others read the notch's f32 error signal
+                if (notch && h->n_notch > 0) {
+                    g.list = h->d_list_notch; g.n_list = h->n_notch; g.in_q15 = nullptr; g.in_f32 = h->d_scr + o1;
+                    { Prof pr(h, KK_AGC, sstream(ST_AGC)); launch_agc(g, sstream(ST_AGC)); }
+                }
+                CK(done(ST_AGC, k));
+                mono = h->d_mid_b + o1;
+                audio_src = ST_AGC;
+            }
         }
-    }
-    if (ff) {
-        FftFiltArgs f{};
-        f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq; f.out_stereo = audio; f.out_f32_L = h->d_scr;
-        f.dbg = h->d_dbg; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256;
-        f.par = h->d_par; f.C = C; f.T = T; f.nr_stage = nr ? 1 : 0;
-        { Prof pr(h, KK_FFTFILT); launch_fftfilt(f, st); }
-        if (nr && h->n_dnr > 0) {
-            NlmsArgs n{};
-            n.list = h->d_list_dnr; n.n_list = h->n_dnr; n.C = C; n.T = T;
-            n.in_f32 = h->d_scr; n.out_stereo = audio; n.dbg = h->d_dbg;
-            n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
-            n.par = h->d_par; n.mode = 1;
-            { Prof pr(h, KK_DNR); launch_nlms(n, st); }
+        if (ff) {
+            if (audio_src >= 0) CK(wait_for(ST_FFT, audio_src, k));
+            FftFiltArgs f{};
+            f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq_k; f.out_stereo = audio_k; f.out_f32_L = h->d_scr + o1;
+            f.dbg = dbg_k; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256;
+            f.par = h->d_par; f.C = C; f.T = Tc; f.nr_stage = nr ? 1 : 0;
+            { Prof pr(h, KK_FFTFILT, sstream(ST_FFT)); launch_fftfilt(f, sstream(ST_FFT)); }
+            CK(done(ST_FFT, k));
+            audio_src = ST_FFT;
+            if (nr) {
+                CK(wait_for(ST_DNR, ST_FFT, k));
+                if (h->n_dnr > 0) {
+                    NlmsArgs n{};
+                    n.list = h->d_list_dnr; n.n_list = h->n_dnr; n.C = C; n.T = Tc;
+                    n.in_f32 = h->d_scr + o1; n.out_stereo = audio_k; n.dbg = dbg_k;
+                    n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
+                    n.par = h->d_par; n.mode = 1;
+                    { Prof pr(h, KK_DNR, sstream(ST_DNR)); launch_nlms(n, sstream(ST_DNR)); }
+                }
+                CK(done(ST_DNR, k));
+                audio_src = ST_DNR;
+            }
         }
-    }
-    if (has(h, RDSP_STAGE_SPEC1024)) {
-        Spec1024Args s{};
-        s.audio = audio; s.ring = h->d_ring; s.output = h->d_spec1024_out; s.C = C; s.T = T; s.tick0 = h->tick;
-        s.tw = h->d_tw; s.win = h->d_win1024;
-        int n_fft = 0;
-        for (int t = 0; t < T; t++) {
-            const unsigned long long tk = h->tick + t;
-            if (tk >= 7 && ((tk - 7) & 3) == 0) n_fft++;
+        if (has(h, RDSP_STAGE_SPEC1024)) {
+            CK(wait_for(ST_S1024, audio_src, k));
+            Spec1024Args s1{};
+            s1.audio = audio_k; s1.ring = h->d_ring; s1.output = h->d_spec1024_out; s1.C = C; s1.T = Tc; s1.tick0 = h->tick;
+            s1.tw = h->d_tw; s1.win = h->d_win1024;
+            int n_fft = 0;
+            for (int t = 0; t < Tc; t++) {
+                const unsigned long long tk = h->tick + t;
+                if (tk >= 7 && ((tk - 7) & 3) == 0) n_fft++;
+            }
+            s1.any_fft = n_fft > 0;
+            { Prof pr(h, KK_SPEC1024, sstream(ST_S1024)); launch_spec1024(s1, sstream(ST_S1024)); }
+            CK(done(ST_S1024, k));
+            if (n_fft) std::fill(h->spec1024_ready.begin(), h->spec1024_ready.end(), (uint8_t)1);
         }
-        s.any_fft = n_fft > 0;
-        { Prof pr(h, KK_SPEC1024); launch_spec1024(s, st); }
-        if (n_fft) std::fill(h->spec1024_ready.begin(), h->spec1024_ready.end(), (uint8_t)1);
+        h->tick += Tc;
     }
-    h->tick += T;
-    if (spec_fork) CK(cudaStreamWaitEvent(st, h->ev_join, 0));          // join: the call is complete when both paths are
+    if (piped) {
+        // join: the call is complete on the handle's stream when every stage has finished its last chunk
+        const int used[] = {fe ? ST_FRONT : -1, (fe && notch) ? ST_NOTCH : -1, (fe && (notch || agc)) ? ST_AGC : -1, ff ? ST_FFT : -1,
+                            (ff && nr) ? ST_DNR : -1, has(h, RDSP_STAGE_SPEC1024) ? ST_S1024 : -1,
+                            has(h, RDSP_STAGE_SPEC256) ? ST_BIQ : -1, has(h, RDSP_STAGE_SPEC256) ? ST_S256 : -1};
+        for (int s : used)
+            if (s >= 0) CK(cudaStreamWaitEvent(st, h->ev_stage[s][nchunks - 1], 0));
+    }
     CK(cudaGetLastError());
 
     if (host_io) {
