@@ -5,17 +5,26 @@
 // RadioDSP_SDR_RX.ino:71-72,81-82 (library absent from the reference tree; arithmetic conventions
 // are arm_fir_fast_q15 / AudioMixer4 as stated in SURVEY.md A.4).
 //
-// Mapping: one warp per channel, 8 channels per CTA.  A 128-sample block is 4 samples per lane; the
-// 512-byte IQ block is one 128-bit load per lane.  Each q15 delay line lives in shared memory as
-// [128 history | 128 current] int16; a lane produces 4 consecutive outputs from a register sliding
-// window (8 taps x 4 outputs = 32 IMAD per 3 LDS.64 + 2 broadcast LDS.128 of taps).  The 32-bit
-// accumulator wraps (unsigned arithmetic) exactly like the CMSIS fast FIR.
+// Three 129-tap FIRs per channel = 49.5 k multiply-accumulates per 128-sample block: this kernel lives on the
+// INT32 IMAD rate (measured on B200: 123 lanes/clk/SM, the same as FFMA, while shifts / logic / min-max run at
+// half of that — tools/ubench_pipes.cu).  So the inner loop is IMAD and almost nothing else:
+//   * the delay lines sit in shared memory ALREADY UNPACKED to int32 ([128 history | 128 current]); no
+//     sign-extension or byte-permute per multiply;
+//   * a half-warp owns a channel, a lane owns 8 consecutive outputs and walks the taps 16 at a time: one chunk
+//     is 6 + 4 LDS.128 (24 samples, 16 broadcast taps) feeding 128 IMADs from registers (90 % IMAD issue);
+//   * rows are skewed by 4 words per 32 so that the eight 32-byte-strided LDS.128 of a quarter-warp touch 32
+//     distinct banks;
+//   * the 32-bit accumulators wrap (unsigned arithmetic) exactly like the CMSIS fast FIR; SSAT(acc >> 15, 16).
+// The q15 history in HBM stays int16 (768 B per channel).
 #include "rdsp_common.cuh"
 #include "kernels.h"
 
 namespace {
 
-constexpr int WARPS = 8;
+constexpr int WARPS = 4;                      // 8 channels per CTA
+constexpr int BW = 288;                       // words per delay line: 256 + skew
+
+__device__ __forceinline__ int pos(int m) { return m + ((m >> 5) << 2); }
 
 __device__ __forceinline__ int32_t mix_gain(int32_t x, int32_t mult)
 {
@@ -25,87 +34,105 @@ __device__ __forceinline__ int32_t mix_gain(int32_t x, int32_t mult)
     return (int32_t)v;
 }
 
-// buf: [0,128) history, [128,256) current block.  Outputs n = 4*lane + j, j < 4.
-__device__ __forceinline__ void fir129_x4(const int16_t *buf, const int32_t *taps, int lane, int32_t y[4])
+// buf: skewed int32 delay line, samples [0,128) history, [128,256) current.  Outputs n = 8*l16 + j, j < 8.
+__device__ __forceinline__ void fir129_x8(const int32_t *buf, const int32_t *taps, int l16, int32_t y[8])
 {
-    const uint2 *b2 = reinterpret_cast<const uint2 *>(buf);
-    uint32_t acc[4] = {0u, 0u, 0u, 0u};
-#pragma unroll 2
-    for (int c = 0; c < 16; c++) {
-        const int q = 30 + lane - 2 * c;               // (128 + 4*lane - 8c - 8) / 4
-        const uint2 w0 = b2[q], w1 = b2[q + 1], w2 = b2[q + 2];
-        int32_t s[12];
-        s[0] = lo16(w0.x); s[1] = hi16(w0.x); s[2]  = lo16(w0.y); s[3]  = hi16(w0.y);
-        s[4] = lo16(w1.x); s[5] = hi16(w1.x); s[6]  = lo16(w1.y); s[7]  = hi16(w1.y);
-        s[8] = lo16(w2.x); s[9] = hi16(w2.x); s[10] = lo16(w2.y); s[11] = hi16(w2.y);
-        const int4 t0 = *reinterpret_cast<const int4 *>(taps + 8 * c);
-        const int4 t1 = *reinterpret_cast<const int4 *>(taps + 8 * c + 4);
-        const int32_t tp[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+    uint32_t acc[8];
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+    for (int j = 0; j < 8; j++) acc[j] = 0u;
+#pragma unroll 1
+    for (int c = 0; c < 8; c++) {
+        const int base = 112 + 8 * l16 - 16 * c;           // 128 + 8*l16 - 16c - 16, a multiple of 8
+        int32_t s[24], tp[16];
 #pragma unroll
-            for (int kk = 0; kk < 8; kk++)
-                acc[j] += (uint32_t)(tp[kk] * s[8 + j - kk]);
+        for (int q = 0; q < 6; q++) {
+            const int4 v = *reinterpret_cast<const int4 *>(buf + pos(base + 4 * q));
+            s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int4 v = *reinterpret_cast<const int4 *>(taps + 16 * c + 4 * q);
+            tp[4 * q] = v.x; tp[4 * q + 1] = v.y; tp[4 * q + 2] = v.z; tp[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] += (uint32_t)(tp[kk] * s[16 + j - kk]);
     }
-    {   // tap 128 multiplies x[n-128] = history sample 4*lane + j
-        const uint2 w = b2[lane];
+    {   // tap 128 multiplies x[n-128] = history sample 8*l16 + j
+        const int4 v0 = *reinterpret_cast<const int4 *>(buf + pos(8 * l16));
+        const int4 v1 = *reinterpret_cast<const int4 *>(buf + pos(8 * l16 + 4));
         const int32_t t = taps[128];
-        acc[0] += (uint32_t)(t * lo16(w.x));
-        acc[1] += (uint32_t)(t * hi16(w.x));
-        acc[2] += (uint32_t)(t * lo16(w.y));
-        acc[3] += (uint32_t)(t * hi16(w.y));
+        acc[0] += (uint32_t)(t * v0.x); acc[1] += (uint32_t)(t * v0.y); acc[2] += (uint32_t)(t * v0.z); acc[3] += (uint32_t)(t * v0.w);
+        acc[4] += (uint32_t)(t * v1.x); acc[5] += (uint32_t)(t * v1.y); acc[6] += (uint32_t)(t * v1.z); acc[7] += (uint32_t)(t * v1.w);
     }
 #pragma unroll
-    for (int j = 0; j < 4; j++) y[j] = sat16(((int32_t)acc[j]) >> 15);
+    for (int j = 0; j < 8; j++) y[j] = sat16(((int32_t)acc[j]) >> 15);
+}
+
+__device__ __forceinline__ void store8(int32_t *buf, int m, const int32_t v[8])
+{
+    *reinterpret_cast<int4 *>(buf + pos(m)) = make_int4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<int4 *>(buf + pos(m + 4)) = make_int4(v[4], v[5], v[6], v[7]);
 }
 
 __global__ void __launch_bounds__(WARPS * 32) k_front(FrontArgs a)
 {
     __shared__ __align__(16) int32_t s_taps[15 * RDSP_TAPS_PAD];
-    __shared__ __align__(16) int16_t s_buf[WARPS][3][256];
+    __shared__ __align__(16) int32_t s_buf[WARPS * 2][3][BW];
 
     for (int i = threadIdx.x; i < 15 * RDSP_TAPS_PAD; i += WARPS * 32) s_taps[i] = a.taps[i];
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ch = blockIdx.x * WARPS + warp;
-    if (ch >= a.C) return;
+    const int half = lane >> 4, l16 = lane & 15;
+    const int slot = warp * 2 + half;
+    const int chq = blockIdx.x * (WARPS * 2) + slot;
+    const bool active = chq < a.C;
+    const int ch = active ? chq : a.C - 1;                   // idle half-warps shadow the last channel, stores masked
 
     const RdspChanParams p = a.par[ch];
     const int32_t *tapA = s_taps + (0 + p.demod) * RDSP_TAPS_PAD;
     const int32_t *tapB = s_taps + (RDSP_N_DEMOD + p.demod) * RDSP_TAPS_PAD;
     const int32_t *tapM = s_taps + (2 * RDSP_N_DEMOD + p.filter) * RDSP_TAPS_PAD;
-    int16_t *bI = s_buf[warp][0], *bQ = s_buf[warp][1], *bD = s_buf[warp][2];
-    uint2 *bI2 = reinterpret_cast<uint2 *>(bI), *bQ2 = reinterpret_cast<uint2 *>(bQ), *bD2 = reinterpret_cast<uint2 *>(bD);
+    int32_t *bI = s_buf[slot][0], *bQ = s_buf[slot][1], *bD = s_buf[slot][2];
 
-    // delay lines: hist[ch][3][128] int16
-    uint2 *hrow = reinterpret_cast<uint2 *>(a.hist + (size_t)ch * 3 * RDSP_BLK);
-    bI2[lane] = hrow[lane];
-    bQ2[lane] = hrow[32 + lane];
-    bD2[lane] = hrow[64 + lane];
+    // delay lines: hist[ch][3][128] int16, 16 bytes (8 samples) per lane and line
+    int4 *hrow = reinterpret_cast<int4 *>(a.hist + (size_t)ch * 3 * RDSP_BLK);
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        const int4 v = hrow[b * 16 + l16];
+        const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+        int32_t x[8];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { x[2 * q] = lo16(w[q]); x[2 * q + 1] = hi16(w[q]); }
+        store8(s_buf[slot][b], 8 * l16, x);
+    }
 
     const bool usb = (p.demod == 1 || p.demod == 3);
     const bool am = (p.demod == 4);
 
     for (int t = 0; t < a.T; t++) {
         const size_t cb = (size_t)t * a.C + ch;                    // channel-block index
-        const int4 v = ld_stream16(a.iq + cb * 2 * RDSP_BLK + lane * 8);
-        const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
-        int32_t xi[4], xq[4];
+        const int4 *src = reinterpret_cast<const int4 *>(a.iq + cb * 2 * RDSP_BLK) + 2 * l16;     // 8 frames = 32 bytes
+        const int4 v0 = ld_stream16(src), v1 = ld_stream16(src + 1);
+        const uint32_t w[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w,
+                               (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
+        int32_t xi[8], xq[8];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 8; j++) {
             xi[j] = mix_gain(lo16(w[j]), p.mult_i);
             xq[j] = mix_gain(hi16(w[j]), p.mult_q);
         }
-        bI2[32 + lane] = make_uint2(mk16(xi[0], xi[1]), mk16(xi[2], xi[3]));
-        bQ2[32 + lane] = make_uint2(mk16(xq[0], xq[1]), mk16(xq[2], xq[3]));
+        store8(bI, 128 + 8 * l16, xi);
+        store8(bQ, 128 + 8 * l16, xq);
         __syncwarp();
 
-        int32_t ya[4], yb[4], d[4], m[4];
-        fir129_x4(bI, tapA, lane, ya);
-        fir129_x4(bQ, tapB, lane, yb);
+        int32_t ya[8], yb[8], d[8], m[8];
+        fir129_x8(bI, tapA, l16, ya);
+        fir129_x8(bQ, tapB, l16, yb);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 8; j++) {
             if (am) {
                 uint32_t e = sqrt_u32_approx((uint32_t)(ya[j] * ya[j]) + (uint32_t)(yb[j] * yb[j]));
                 d[j] = (int32_t)min(e, 32767u);
@@ -113,38 +140,48 @@ __global__ void __launch_bounds__(WARPS * 32) k_front(FrontArgs a)
                 d[j] = usb ? sat16(ya[j] - yb[j]) : sat16(ya[j] + yb[j]);
             }
         }
-        bD2[32 + lane] = make_uint2(mk16(d[0], d[1]), mk16(d[2], d[3]));
+        store8(bD, 128 + 8 * l16, d);
         __syncwarp();
-        fir129_x4(bD, tapM, lane, m);
+        fir129_x8(bD, tapM, l16, m);
 
-        if (a.out_mono)
-            st_stream8(a.out_mono + cb * RDSP_BLK + lane * 4, make_int2((int)mk16(m[0], m[1]), (int)mk16(m[2], m[3])));
-        if (a.out_stereo)
-            st_stream16(a.out_stereo + cb * 2 * RDSP_BLK + lane * 8,
-                        make_int4((int)mk16(m[0], m[0]), (int)mk16(m[1], m[1]), (int)mk16(m[2], m[2]), (int)mk16(m[3], m[3])));
-        if (a.dbg) {
-            float4 *dp = reinterpret_cast<float4 *>(a.dbg + cb * 2 * RDSP_BLK + lane * 8);
-            const float f0 = (float)m[0] / 32768.0f, f1 = (float)m[1] / 32768.0f;
-            const float f2 = (float)m[2] / 32768.0f, f3 = (float)m[3] / 32768.0f;
-            dp[0] = make_float4(f0, f0, f1, f1);
-            dp[1] = make_float4(f2, f2, f3, f3);
+        if (active) {
+            const int4 packed = make_int4((int)mk16(m[0], m[1]), (int)mk16(m[2], m[3]), (int)mk16(m[4], m[5]), (int)mk16(m[6], m[7]));
+            if (a.out_mono) st_stream16(a.out_mono + cb * RDSP_BLK + 8 * l16, packed);
+            if (a.out_stereo) {
+                int16_t *dst = a.out_stereo + (cb * RDSP_BLK + 8 * l16) * 2;
+                st_stream16(dst, make_int4((int)mk16(m[0], m[0]), (int)mk16(m[1], m[1]), (int)mk16(m[2], m[2]), (int)mk16(m[3], m[3])));
+                st_stream16(dst + 8, make_int4((int)mk16(m[4], m[4]), (int)mk16(m[5], m[5]), (int)mk16(m[6], m[6]), (int)mk16(m[7], m[7])));
+            }
+            if (a.dbg) {
+                float4 *dp = reinterpret_cast<float4 *>(a.dbg + (cb * RDSP_BLK + 8 * l16) * 2);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float f0 = (float)m[2 * q] / 32768.0f, f1 = (float)m[2 * q + 1] / 32768.0f;
+                    dp[q] = make_float4(f0, f0, f1, f1);
+                }
+            }
         }
         __syncwarp();
-        // current block becomes history
-        bI2[lane] = bI2[32 + lane];
-        bQ2[lane] = bQ2[32 + lane];
-        bD2[lane] = bD2[32 + lane];
+        // current block becomes history (each lane moves its own 8 samples of the three lines)
+        store8(bI, 8 * l16, xi);
+        store8(bQ, 8 * l16, xq);
+        store8(bD, 8 * l16, d);
         __syncwarp();
     }
-    hrow[lane] = bI2[lane];
-    hrow[32 + lane] = bQ2[lane];
-    hrow[64 + lane] = bD2[lane];
+    if (active) {
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            const int32_t *bb = s_buf[slot][b];
+            const int4 x0 = *reinterpret_cast<const int4 *>(bb + pos(8 * l16)), x1 = *reinterpret_cast<const int4 *>(bb + pos(8 * l16 + 4));
+            hrow[b * 16 + l16] = make_int4((int)mk16(x0.x, x0.y), (int)mk16(x0.z, x0.w), (int)mk16(x1.x, x1.y), (int)mk16(x1.z, x1.w));
+        }
+    }
 }
 
 }  // namespace
 
 void launch_front(const FrontArgs &a, cudaStream_t st)
 {
-    const int grid = (a.C + WARPS - 1) / WARPS;
-    k_front<<<grid, WARPS * 32, 0, st>>>(a);
+    const int cpb = WARPS * 2;
+    k_front<<<(a.C + cpb - 1) / cpb, WARPS * 32, 0, st>>>(a);
 }
