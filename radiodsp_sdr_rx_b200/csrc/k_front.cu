@@ -21,7 +21,7 @@
 
 namespace {
 
-constexpr int WARPS = 4;                      // 8 channels per CTA
+constexpr int MAXWARPS = 8;                   // up to 16 channels per CTA (chosen per launch, see launch_front)
 constexpr int BW = 288;                       // words per delay line: 256 + skew
 
 __device__ __forceinline__ int pos(int m) { return m + ((m >> 5) << 2); }
@@ -76,18 +76,19 @@ __device__ __forceinline__ void store8(int32_t *buf, int m, const int32_t v[8])
     *reinterpret_cast<int4 *>(buf + pos(m + 4)) = make_int4(v[4], v[5], v[6], v[7]);
 }
 
-__global__ void __launch_bounds__(WARPS * 32) k_front(FrontArgs a)
+__global__ void __launch_bounds__(MAXWARPS * 32) k_front(FrontArgs a)
 {
-    __shared__ __align__(16) int32_t s_taps[15 * RDSP_TAPS_PAD];
-    __shared__ __align__(16) int32_t s_buf[WARPS * 2][3][BW];
+    extern __shared__ __align__(16) int32_t s_dyn[];
+    int32_t *s_taps = s_dyn;                                              // [15][132]
+    int32_t (*s_buf)[3][BW] = reinterpret_cast<int32_t (*)[3][BW]>(s_dyn + 15 * RDSP_TAPS_PAD);   // [2*warps][3][BW]
 
-    for (int i = threadIdx.x; i < 15 * RDSP_TAPS_PAD; i += WARPS * 32) s_taps[i] = a.taps[i];
+    for (int i = threadIdx.x; i < 15 * RDSP_TAPS_PAD; i += blockDim.x) s_taps[i] = a.taps[i];
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int half = lane >> 4, l16 = lane & 15;
     const int slot = warp * 2 + half;
-    const int chq = blockIdx.x * (WARPS * 2) + slot;
+    const int chq = blockIdx.x * (blockDim.x >> 4) + slot;
     const bool active = chq < a.C;
     const int ch = active ? chq : a.C - 1;                   // idle half-warps shadow the last channel, stores masked
 
@@ -180,8 +181,39 @@ __global__ void __launch_bounds__(WARPS * 32) k_front(FrontArgs a)
 
 }  // namespace
 
+// Pick warps per CTA (w) and resident CTAs per SM (r) so that the grid is a whole number of full waves: every
+// channel costs the same, so a ragged last wave is pure loss (8192 channels on 148 SMs = 55.35 per SM: 48 resident
+// channels would take two rounds of 48 + 7, 28 resident take two rounds of 28 + 27.4).
 void launch_front(const FrontArgs &a, cudaStream_t st)
 {
-    const int cpb = WARPS * 2;
-    k_front<<<(a.C + cpb - 1) / cpb, WARPS * 32, 0, st>>>(a);
+    static int n_sm = 0;
+    static size_t smem_max = 0;
+    if (!n_sm) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        smem_max = (size_t)v;
+        cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+    }
+    auto need = [](int w) { return (size_t)(15 * RDSP_TAPS_PAD + 2 * w * 3 * BW) * sizeof(int32_t); };
+    int best_w = 4, best_r = 4;
+    double best = -1.0;
+    for (int w = 2; w <= MAXWARPS; w++)
+        for (int r = 1; r <= 8; r++) {
+            if (w * r > 24) continue;                                     // 80 registers per thread
+            if ((need(w) + 1024) * r > smem_max + 1024) continue;
+            const long ctas = (a.C + 2 * w - 1) / (2 * w);
+            const long waves = (ctas + (long)n_sm * r - 1) / ((long)n_sm * r);
+            double eff = (double)a.C / ((double)waves * n_sm * r * 2 * w);
+            eff *= (w * r >= 12) ? 1.0 : 0.5 + (w * r) / 24.0;             // too few warps cannot cover the LDS latency
+            eff += 1e-4 * w * r;                                          // ties: prefer the fuller SM
+            if (eff > best) { best = eff; best_w = w; best_r = r; }
+        }
+    // ask for enough shared memory that exactly best_r CTAs fit on an SM
+    size_t smem = need(best_w);
+    const size_t floor_r = (smem_max + 1024) / (best_r + 1) + 16 - 1024;   // more than an (r+1)-th of the SM
+    if (smem < floor_r && floor_r <= smem_max) smem = floor_r;
+    const int cpb = 2 * best_w;
+    k_front<<<(a.C + cpb - 1) / cpb, best_w * 32, smem, st>>>(a);
 }
