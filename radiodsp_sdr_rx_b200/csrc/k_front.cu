@@ -21,7 +21,7 @@
 
 namespace {
 
-constexpr int MAXWARPS = 8;                   // up to 16 channels per CTA (chosen per launch, see launch_front)
+constexpr int MAXWARPS = 14;                  // up to 28 channels per CTA (chosen per launch, see launch_front)
 constexpr int BW = 288;                       // words per delay line: 256 + skew
 
 __device__ __forceinline__ int pos(int m) { return m + ((m >> 5) << 2); }
@@ -76,7 +76,7 @@ __device__ __forceinline__ void store8(int32_t *buf, int m, const int32_t v[8])
     *reinterpret_cast<int4 *>(buf + pos(m + 4)) = make_int4(v[4], v[5], v[6], v[7]);
 }
 
-__global__ void __launch_bounds__(MAXWARPS * 32) k_front(FrontArgs a)
+__global__ void __launch_bounds__(MAXWARPS * 32, 2) k_front(FrontArgs a)
 {
     extern __shared__ __align__(16) int32_t s_dyn[];
     int32_t *s_taps = s_dyn;                                              // [15][132]
@@ -113,10 +113,14 @@ __global__ void __launch_bounds__(MAXWARPS * 32) k_front(FrontArgs a)
     const bool usb = (p.demod == 1 || p.demod == 3);
     const bool am = (p.demod == 4);
 
+    // 8 frames = 32 bytes per lane and block; the next block is fetched while this one is filtered
+    const int4 *src0 = reinterpret_cast<const int4 *>(a.iq + (size_t)ch * 2 * RDSP_BLK) + 2 * l16;
+    const size_t blk_stride = (size_t)a.C * 2 * RDSP_BLK / 8;         // int4 units between consecutive blocks
+    int4 nv0 = ld_stream16(src0), nv1 = ld_stream16(src0 + 1);
     for (int t = 0; t < a.T; t++) {
         const size_t cb = (size_t)t * a.C + ch;                    // channel-block index
-        const int4 *src = reinterpret_cast<const int4 *>(a.iq + cb * 2 * RDSP_BLK) + 2 * l16;     // 8 frames = 32 bytes
-        const int4 v0 = ld_stream16(src), v1 = ld_stream16(src + 1);
+        const int4 v0 = nv0, v1 = nv1;
+        if (t + 1 < a.T) { nv0 = ld_stream16(src0 + (size_t)(t + 1) * blk_stride); nv1 = ld_stream16(src0 + (size_t)(t + 1) * blk_stride + 1); }
         const uint32_t w[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w,
                                (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
         int32_t xi[8], xq[8];
@@ -201,12 +205,12 @@ void launch_front(const FrontArgs &a, cudaStream_t st)
     double best = -1.0;
     for (int w = 2; w <= MAXWARPS; w++)
         for (int r = 1; r <= 8; r++) {
-            if (w * r > 24) continue;                                     // 80 registers per thread
+            if (w * r > 28) continue;                                     // 72 registers per thread (launch bounds)
             if ((need(w) + 1024) * r > smem_max + 1024) continue;
             const long ctas = (a.C + 2 * w - 1) / (2 * w);
             const long waves = (ctas + (long)n_sm * r - 1) / ((long)n_sm * r);
             double eff = (double)a.C / ((double)waves * n_sm * r * 2 * w);
-            eff *= (w * r >= 12) ? 1.0 : 0.5 + (w * r) / 24.0;             // too few warps cannot cover the LDS latency
+            eff *= (w * r >= 20) ? 1.0 : 0.4 + 0.6 * (w * r) / 20.0;       // too few warps cannot cover LDS / IMAD latency
             eff += 1e-4 * w * r;                                          // ties: prefer the fuller SM
             if (eff > best) { best = eff; best_w = w; best_r = r; }
         }
