@@ -5,26 +5,24 @@
 // RadioDSP_SDR_RX.ino:71-72,81-82 (library absent from the reference tree; arithmetic conventions
 // are arm_fir_fast_q15 / AudioMixer4 as stated in SURVEY.md A.4).
 //
-// Three 129-tap FIRs per channel = 49.5 k multiply-accumulates per 128-sample block: this kernel lives on the
-// INT32 IMAD rate (measured on B200: 123 lanes/clk/SM, the same as FFMA, while shifts / logic / min-max run at
-// half of that — tools/ubench_pipes.cu).  So the inner loop is IMAD and almost nothing else:
-//   * the delay lines sit in shared memory ALREADY UNPACKED to int32 ([128 history | 128 current]); no
-//     sign-extension or byte-permute per multiply;
-//   * a half-warp owns a channel, a lane owns 8 consecutive outputs and walks the taps 16 at a time: one chunk
-//     is 6 + 4 LDS.128 (24 samples, 16 broadcast taps) feeding 128 IMADs from registers (90 % IMAD issue);
-//   * rows are skewed by 4 words per 32 so that the eight 32-byte-strided LDS.128 of a quarter-warp touch 32
-//     distinct banks;
+// Three 129-tap FIRs per channel = 49.5 k multiply-accumulates per 128-sample block.  Measured on B200
+// (tools/ubench_pipes.cu): IMAD issues at the FFMA rate (123 lanes/clk/SM; an 8 x 16 register tile of this FIR
+// sustains 115), shifts / permutes / min-max at half of it, and shared memory delivers one 128-byte wavefront per
+// clock per SM.  A tile that re-loads its window as int32 needs one wavefront per four IMAD warp-instructions and
+// is shared-memory bound at a third of the IMAD rate (r01 profiles), so:
+//   * delay lines and taps stay PACKED int16 in shared memory ([128 history | 128 current] per line);
+//   * a half-warp owns a channel, a lane owns 8 consecutive outputs and walks the taps 16 at a time: one chunk is
+//     3 LDS.128 of samples + 2 broadcast LDS.128 of taps (1 wavefront per 8 IMAD instructions), 40 sign-extending
+//     permutes on the otherwise idle ALU pipe, and 128 IMADs from registers;
+//   * lanes are 16 bytes apart, so the sample loads are conflict free without padding;
 //   * the 32-bit accumulators wrap (unsigned arithmetic) exactly like the CMSIS fast FIR; SSAT(acc >> 15, 16).
-// The q15 history in HBM stays int16 (768 B per channel).
 #include "rdsp_common.cuh"
 #include "kernels.h"
 
 namespace {
 
 constexpr int MAXWARPS = 14;                  // up to 28 channels per CTA (chosen per launch, see launch_front)
-constexpr int BW = 288;                       // words per delay line: 256 + skew
-
-__device__ __forceinline__ int pos(int m) { return m + ((m >> 5) << 2); }
+constexpr int TROW = 136;                     // int16 per tap row (129 padded to a multiple of 8)
 
 __device__ __forceinline__ int32_t mix_gain(int32_t x, int32_t mult)
 {
@@ -34,55 +32,56 @@ __device__ __forceinline__ int32_t mix_gain(int32_t x, int32_t mult)
     return (int32_t)v;
 }
 
-// buf: skewed int32 delay line, samples [0,128) history, [128,256) current.  Outputs n = 8*l16 + j, j < 8.
-__device__ __forceinline__ void fir129_x8(const int32_t *buf, const int32_t *taps, int l16, int32_t y[8])
+__device__ __forceinline__ void unpack8(const int4 v, int32_t *d)
+{
+    d[0] = lo16((uint32_t)v.x); d[1] = hi16((uint32_t)v.x); d[2] = lo16((uint32_t)v.y); d[3] = hi16((uint32_t)v.y);
+    d[4] = lo16((uint32_t)v.z); d[5] = hi16((uint32_t)v.z); d[6] = lo16((uint32_t)v.w); d[7] = hi16((uint32_t)v.w);
+}
+__device__ __forceinline__ int4 pack8(const int32_t *v)
+{
+    return make_int4((int)mk16(v[0], v[1]), (int)mk16(v[2], v[3]), (int)mk16(v[4], v[5]), (int)mk16(v[6], v[7]));
+}
+
+// buf: int16 delay line, samples [0,128) history, [128,256) current.  Outputs n = 8*l16 + j, j < 8.
+__device__ __forceinline__ void fir129_x8(const int16_t *buf, const int16_t *taps, int l16, int32_t y[8])
 {
     uint32_t acc[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[j] = 0u;
-#pragma unroll 1
+    const int4 *b4 = reinterpret_cast<const int4 *>(buf);                  // 8 samples per int4
+    const int4 *t4 = reinterpret_cast<const int4 *>(taps);
+#pragma unroll 2
     for (int c = 0; c < 8; c++) {
-        const int base = 112 + 8 * l16 - 16 * c;           // 128 + 8*l16 - 16c - 16, a multiple of 8
+        const int q = 14 + l16 - 2 * c;                    // (128 + 8*l16 - 16c - 16) / 8
         int32_t s[24], tp[16];
-#pragma unroll
-        for (int q = 0; q < 6; q++) {
-            const int4 v = *reinterpret_cast<const int4 *>(buf + pos(base + 4 * q));
-            s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int4 v = *reinterpret_cast<const int4 *>(taps + 16 * c + 4 * q);
-            tp[4 * q] = v.x; tp[4 * q + 1] = v.y; tp[4 * q + 2] = v.z; tp[4 * q + 3] = v.w;
-        }
+        unpack8(b4[q], s); unpack8(b4[q + 1], s + 8); unpack8(b4[q + 2], s + 16);
+        unpack8(t4[2 * c], tp); unpack8(t4[2 * c + 1], tp + 8);
 #pragma unroll
         for (int kk = 0; kk < 16; kk++)
 #pragma unroll
             for (int j = 0; j < 8; j++) acc[j] += (uint32_t)(tp[kk] * s[16 + j - kk]);
     }
     {   // tap 128 multiplies x[n-128] = history sample 8*l16 + j
-        const int4 v0 = *reinterpret_cast<const int4 *>(buf + pos(8 * l16));
-        const int4 v1 = *reinterpret_cast<const int4 *>(buf + pos(8 * l16 + 4));
+        int32_t s[8];
+        unpack8(b4[l16], s);
         const int32_t t = taps[128];
-        acc[0] += (uint32_t)(t * v0.x); acc[1] += (uint32_t)(t * v0.y); acc[2] += (uint32_t)(t * v0.z); acc[3] += (uint32_t)(t * v0.w);
-        acc[4] += (uint32_t)(t * v1.x); acc[5] += (uint32_t)(t * v1.y); acc[6] += (uint32_t)(t * v1.z); acc[7] += (uint32_t)(t * v1.w);
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] += (uint32_t)(t * s[j]);
     }
 #pragma unroll
     for (int j = 0; j < 8; j++) y[j] = sat16(((int32_t)acc[j]) >> 15);
 }
 
-__device__ __forceinline__ void store8(int32_t *buf, int m, const int32_t v[8])
-{
-    *reinterpret_cast<int4 *>(buf + pos(m)) = make_int4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<int4 *>(buf + pos(m + 4)) = make_int4(v[4], v[5], v[6], v[7]);
-}
-
 __global__ void __launch_bounds__(MAXWARPS * 32, 2) k_front(FrontArgs a)
 {
-    extern __shared__ __align__(16) int32_t s_dyn[];
-    int32_t *s_taps = s_dyn;                                              // [15][132]
-    int32_t (*s_buf)[3][BW] = reinterpret_cast<int32_t (*)[3][BW]>(s_dyn + 15 * RDSP_TAPS_PAD);   // [2*warps][3][BW]
+    extern __shared__ __align__(16) int16_t s_dyn16[];
+    int16_t *s_taps = s_dyn16;                                             // [15][TROW]
+    int16_t (*s_buf)[3][256] = reinterpret_cast<int16_t (*)[3][256]>(s_dyn16 + 15 * TROW);   // [2*warps][3][256]
 
-    for (int i = threadIdx.x; i < 15 * RDSP_TAPS_PAD; i += blockDim.x) s_taps[i] = a.taps[i];
+    for (int i = threadIdx.x; i < 15 * TROW; i += blockDim.x) {
+        const int r = i / TROW, k = i % TROW;
+        s_taps[i] = k < RDSP_NTAPS ? (int16_t)a.taps[r * RDSP_TAPS_PAD + k] : (int16_t)0;
+    }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -93,22 +92,17 @@ __global__ void __launch_bounds__(MAXWARPS * 32, 2) k_front(FrontArgs a)
     const int ch = active ? chq : a.C - 1;                   // idle half-warps shadow the last channel, stores masked
 
     const RdspChanParams p = a.par[ch];
-    const int32_t *tapA = s_taps + (0 + p.demod) * RDSP_TAPS_PAD;
-    const int32_t *tapB = s_taps + (RDSP_N_DEMOD + p.demod) * RDSP_TAPS_PAD;
-    const int32_t *tapM = s_taps + (2 * RDSP_N_DEMOD + p.filter) * RDSP_TAPS_PAD;
-    int32_t *bI = s_buf[slot][0], *bQ = s_buf[slot][1], *bD = s_buf[slot][2];
+    const int16_t *tapA = s_taps + (0 + p.demod) * TROW;
+    const int16_t *tapB = s_taps + (RDSP_N_DEMOD + p.demod) * TROW;
+    const int16_t *tapM = s_taps + (2 * RDSP_N_DEMOD + p.filter) * TROW;
+    int16_t *bI = s_buf[slot][0], *bQ = s_buf[slot][1], *bD = s_buf[slot][2];
+    int4 *bI4 = reinterpret_cast<int4 *>(bI), *bQ4 = reinterpret_cast<int4 *>(bQ), *bD4 = reinterpret_cast<int4 *>(bD);
 
     // delay lines: hist[ch][3][128] int16, 16 bytes (8 samples) per lane and line
     int4 *hrow = reinterpret_cast<int4 *>(a.hist + (size_t)ch * 3 * RDSP_BLK);
-#pragma unroll
-    for (int b = 0; b < 3; b++) {
-        const int4 v = hrow[b * 16 + l16];
-        const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
-        int32_t x[8];
-#pragma unroll
-        for (int q = 0; q < 4; q++) { x[2 * q] = lo16(w[q]); x[2 * q + 1] = hi16(w[q]); }
-        store8(s_buf[slot][b], 8 * l16, x);
-    }
+    bI4[l16] = hrow[l16];
+    bQ4[l16] = hrow[16 + l16];
+    bD4[l16] = hrow[32 + l16];
 
     const bool usb = (p.demod == 1 || p.demod == 3);
     const bool am = (p.demod == 4);
@@ -129,8 +123,9 @@ __global__ void __launch_bounds__(MAXWARPS * 32, 2) k_front(FrontArgs a)
             xi[j] = mix_gain(lo16(w[j]), p.mult_i);
             xq[j] = mix_gain(hi16(w[j]), p.mult_q);
         }
-        store8(bI, 128 + 8 * l16, xi);
-        store8(bQ, 128 + 8 * l16, xq);
+        const int4 pi = pack8(xi), pq = pack8(xq);
+        bI4[16 + l16] = pi;
+        bQ4[16 + l16] = pq;
         __syncwarp();
 
         int32_t ya[8], yb[8], d[8], m[8];
@@ -145,13 +140,13 @@ __global__ void __launch_bounds__(MAXWARPS * 32, 2) k_front(FrontArgs a)
                 d[j] = usb ? sat16(ya[j] - yb[j]) : sat16(ya[j] + yb[j]);
             }
         }
-        store8(bD, 128 + 8 * l16, d);
+        const int4 pd = pack8(d);
+        bD4[16 + l16] = pd;
         __syncwarp();
         fir129_x8(bD, tapM, l16, m);
 
         if (active) {
-            const int4 packed = make_int4((int)mk16(m[0], m[1]), (int)mk16(m[2], m[3]), (int)mk16(m[4], m[5]), (int)mk16(m[6], m[7]));
-            if (a.out_mono) st_stream16(a.out_mono + cb * RDSP_BLK + 8 * l16, packed);
+            if (a.out_mono) st_stream16(a.out_mono + cb * RDSP_BLK + 8 * l16, pack8(m));
             if (a.out_stereo) {
                 int16_t *dst = a.out_stereo + (cb * RDSP_BLK + 8 * l16) * 2;
                 st_stream16(dst, make_int4((int)mk16(m[0], m[0]), (int)mk16(m[1], m[1]), (int)mk16(m[2], m[2]), (int)mk16(m[3], m[3])));
@@ -168,26 +163,22 @@ __global__ void __launch_bounds__(MAXWARPS * 32, 2) k_front(FrontArgs a)
         }
         __syncwarp();
         // current block becomes history (each lane moves its own 8 samples of the three lines)
-        store8(bI, 8 * l16, xi);
-        store8(bQ, 8 * l16, xq);
-        store8(bD, 8 * l16, d);
+        bI4[l16] = pi;
+        bQ4[l16] = pq;
+        bD4[l16] = pd;
         __syncwarp();
     }
     if (active) {
-#pragma unroll
-        for (int b = 0; b < 3; b++) {
-            const int32_t *bb = s_buf[slot][b];
-            const int4 x0 = *reinterpret_cast<const int4 *>(bb + pos(8 * l16)), x1 = *reinterpret_cast<const int4 *>(bb + pos(8 * l16 + 4));
-            hrow[b * 16 + l16] = make_int4((int)mk16(x0.x, x0.y), (int)mk16(x0.z, x0.w), (int)mk16(x1.x, x1.y), (int)mk16(x1.z, x1.w));
-        }
+        hrow[l16] = bI4[l16];
+        hrow[16 + l16] = bQ4[l16];
+        hrow[32 + l16] = bD4[l16];
     }
 }
 
 }  // namespace
 
 // Pick warps per CTA (w) and resident CTAs per SM (r) so that the grid is a whole number of full waves: every
-// channel costs the same, so a ragged last wave is pure loss (8192 channels on 148 SMs = 55.35 per SM: 48 resident
-// channels would take two rounds of 48 + 7, 28 resident take two rounds of 28 + 27.4).
+// channel costs the same, so a ragged last wave is pure loss (8192 channels on 148 SMs = 55.35 per SM).
 void launch_front(const FrontArgs &a, cudaStream_t st)
 {
     static int n_sm = 0;
@@ -200,18 +191,18 @@ void launch_front(const FrontArgs &a, cudaStream_t st)
         smem_max = (size_t)v;
         cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
     }
-    auto need = [](int w) { return (size_t)(15 * RDSP_TAPS_PAD + 2 * w * 3 * BW) * sizeof(int32_t); };
+    auto need = [](int w) { return (size_t)(15 * TROW + 2 * w * 3 * 256) * sizeof(int16_t); };
     int best_w = 4, best_r = 4;
     double best = -1.0;
     for (int w = 2; w <= MAXWARPS; w++)
-        for (int r = 1; r <= 8; r++) {
+        for (int r = 1; r <= 14; r++) {
             if (w * r > 28) continue;                                     // 72 registers per thread (launch bounds)
             if ((need(w) + 1024) * r > smem_max + 1024) continue;
             const long ctas = (a.C + 2 * w - 1) / (2 * w);
             const long waves = (ctas + (long)n_sm * r - 1) / ((long)n_sm * r);
             double eff = (double)a.C / ((double)waves * n_sm * r * 2 * w);
             eff *= (w * r >= 20) ? 1.0 : 0.4 + 0.6 * (w * r) / 20.0;       // too few warps cannot cover LDS / IMAD latency
-            eff += 1e-4 * w * r;                                          // ties: prefer the fuller SM
+            eff += 1e-4 * w * r - 1e-5 * r;                               // ties: the fuller SM, then fewer and larger CTAs
             if (eff > best) { best = eff; best_w = w; best_r = r; }
         }
     // ask for enough shared memory that exactly best_r CTAs fit on an SM

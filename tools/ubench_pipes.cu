@@ -36,6 +36,53 @@ __global__ void k(int *out, int a0, int b0)
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+// the FIR register tile: 8 accumulators x 16 taps from 24 samples, everything in registers (no memory in the loop)
+template <int MODE>
+__global__ void k_tile(int *out, const int *in)
+{
+    int s[24], tp[16];
+    unsigned acc[8];
+    float fs[24], ftp[16], facc[8];
+#pragma unroll
+    for (int i = 0; i < 24; i++) { s[i] = in[threadIdx.x + i]; fs[i] = (float)s[i]; }
+#pragma unroll
+    for (int i = 0; i < 16; i++) { tp[i] = in[64 + i]; ftp[i] = (float)tp[i]; }
+#pragma unroll
+    for (int j = 0; j < 8; j++) { acc[j] = 0; facc[j] = 0.f; }
+    for (int it = 0; it < ITERS / 8; it++) {
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (MODE == 0) acc[j] += (unsigned)(tp[kk] * s[16 + j - kk]);
+                else facc[j] = fmaf(ftp[kk], fs[16 + j - kk], facc[j]);
+            }
+        s[it & 7] += 1; fs[it & 7] += 1.f;     // keep the loop from being hoisted
+    }
+    unsigned r = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) r += acc[j] + (unsigned)facc[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (int)r;
+}
+
+template <int MODE>
+void run_tile(const char *name, int *d, int *din)
+{
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int grid = 148 * 4, block = 256;
+    k_tile<MODE><<<grid, block>>>(d, din);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    k_tile<MODE><<<grid, block>>>(d, din);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double ops = (double)grid * block * (ITERS / 8) * 128;
+    printf("%-22s %8.3f ms  %8.2f Tera lane-ops/s  = %6.1f lanes/clk/SM at 1.965 GHz\n", name, ms, ops / ms / 1e9, ops / (ms * 1e-3) / 148 / 1.965e9);
+}
+
 template <int OP>
 void run(const char *name, int *d)
 {
@@ -67,5 +114,10 @@ int main()
     run<5>("SHF + LOP3", d);
     run<6>("PRMT + IADD", d);
     run<7>("IADD + 2x IMNMX", d);
+    int *din;
+    cudaMalloc(&din, 4096 * sizeof(int));
+    cudaMemset(din, 1, 4096 * sizeof(int));
+    run_tile<0>("FIR tile IMAD 8x16", d, din);
+    run_tile<1>("FIR tile FFMA 8x16", d, din);
     return 0;
 }
