@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
                     for (int j = 0; j < 4; j++) {
                         energy = __fsub_rn(energy, __fmul_rn(xo[j], xo[j]));
                         energy = __fadd_rn(energy, __fmul_rn(xn[j], xn[j]));
-                        qn[j] = mu * __frcp_rn(energy + LMS_EPS);
+                        qn[j] = mu * __frcp_rn(fmaxf(energy + LMS_EPS, LMS_EPS));   // energy is a running difference: never divide by <= 0
                         // s_l(b) = s_l(b-1) + x[b-l] x[b] - x[b-l-96] x[b-96],  b = n + j
                         s1 = fmaf(xr[4 + j - 1], xn[j], s1); s1 = fmaf(-xq[4 + j - 1], xo[j], s1);
                         s2 = fmaf(xr[4 + j - 2], xn[j], s2); s2 = fmaf(-xq[4 + j - 2], xo[j], s2);

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms_direct(NlmsArgs a)
                     const float d = same_block_ref ? xn : xb[n];
                     energy = __fsub_rn(energy, __fmul_rn(x0, x0));
                     energy = __fadd_rn(energy, __fmul_rn(xn, xn));
-                    const float inv = __frcp_rn(energy + LMS_EPS);
+                    const float inv = __frcp_rn(fmaxf(energy + LMS_EPS, LMS_EPS));   // never divide by <= 0
                     float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll
                     for (int i = 0; i < W; i++) {
