@@ -6,83 +6,77 @@
 // stages quarter / halve, the last stage halves => net gain 1/N.  Every butterfly of a stage is
 // independent of the others, so any assignment of butterflies to threads reproduces the sequential
 // result bit for bit; stages are separated by a barrier.  Output is in bit-reversed order (the caller
-// reads word bitrev(i) for bin i instead of permuting).
+// reads element bitrev(i) for bin i instead of permuting).
 //
-// Sample word = (re | im << 16); twiddle word k of tw = (cos | sin << 16)(2 pi k / 4096).
+// The ARM code works on packed (re | im << 16) words with SIMD instructions; on B200 shifts, permutes and
+// min/max issue at half the IMAD rate (tools/ubench_pipes.cu), so here a sample is an UNPACKED int2 (re, im)
+// in shared memory and every lane operation is written on 32-bit integers: no pack / unpack per operation,
+// the same results.  Two facts keep it exact and short:
+//   * stage 1 cannot saturate: its inputs are pre-scaled to [-8192, 8191], so every sum / difference it forms
+//     stays inside int16 and QADD16 / QSUB16 / QASX / QSAX reduce to plain adds;
+//   * (SMUAD >> 16, SMUSDX & 0xFFFF0000) = arithmetic >> 16 of the two 32-bit wrap-around sums.
+// Element i is stored at P(i) = i + 4 * (i >> 4) (one 32-byte skew per 128 bytes) to spread the strided
+// accesses of the late stages over the banks.  Twiddle k = (cos, sin)(2 pi k / 4096) as int2.
 #pragma once
-#include "rdsp_common.cuh"
+#include <cuda_runtime.h>
+#include <stdint.h>
 
 #define QHD __host__ __device__ __forceinline__
 
 namespace q15fft {
 
-QHD int32_t s16(int32_t v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 : v); }
-QHD int32_t lo(uint32_t a) { return (int32_t)(int16_t)(a & 0xFFFFu); }
-QHD int32_t hi(uint32_t a) { return ((int32_t)a) >> 16; }
-QHD uint32_t mk(int32_t l, int32_t h) { return ((uint32_t)l & 0xFFFFu) | ((uint32_t)h << 16); }
-QHD uint32_t shadd(uint32_t a, uint32_t b) { return mk((lo(a) + lo(b)) >> 1, (hi(a) + hi(b)) >> 1); }
-QHD uint32_t shsub(uint32_t a, uint32_t b) { return mk((lo(a) - lo(b)) >> 1, (hi(a) - hi(b)) >> 1); }
-QHD uint32_t qadd(uint32_t a, uint32_t b) { return mk(s16(lo(a) + lo(b)), s16(hi(a) + hi(b))); }
-QHD uint32_t qsub(uint32_t a, uint32_t b) { return mk(s16(lo(a) - lo(b)), s16(hi(a) - hi(b))); }
-QHD uint32_t qasx(uint32_t a, uint32_t b) { return mk(s16(lo(a) - hi(b)), s16(hi(a) + lo(b))); }
-QHD uint32_t qsax(uint32_t a, uint32_t b) { return mk(s16(lo(a) + hi(b)), s16(hi(a) - lo(b))); }
-QHD uint32_t shasx(uint32_t a, uint32_t b) { return mk((lo(a) - hi(b)) >> 1, (hi(a) + lo(b)) >> 1); }
-QHD uint32_t shsax(uint32_t a, uint32_t b) { return mk((lo(a) + hi(b)) >> 1, (hi(a) - lo(b)) >> 1); }
-QHD uint32_t quarter(uint32_t a) { return mk(lo(a) >> 2, hi(a) >> 2); }      // SHADD16(SHADD16(a,0),0)
-// twiddle * sample, both products keep their top 16 bits (SMUAD >> 16, SMUSDX & 0xFFFF0000)
-QHD uint32_t cmul(uint32_t c, uint32_t r)
+QHD int P(int i) { return i + ((i >> 4) << 2); }
+QHD int padded(int n) { return n + (n >> 2); }
+
+QHD int s16(int v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 : v); }
+// twiddle * sample: top 16 bits of the two wrap-around 32-bit sums
+QHD int2 cmul(int2 c, int2 r)
 {
-    const uint32_t re = (uint32_t)(lo(c) * lo(r)) + (uint32_t)(hi(c) * hi(r));
-    const uint32_t im = (uint32_t)(lo(c) * hi(r)) - (uint32_t)(hi(c) * lo(r));
-    return (im & 0xFFFF0000u) | (re >> 16);
+    const uint32_t re = (uint32_t)(c.x * r.x) + (uint32_t)(c.y * r.y);   // SMUAD
+    const uint32_t im = (uint32_t)(c.x * r.y) - (uint32_t)(c.y * r.x);   // SMUSDX
+    return make_int2(((int32_t)re) >> 16, ((int32_t)im) >> 16);
 }
 
-// first stage, butterfly i in [0, N/4); mod = 4096 / N
-QHD void first(uint32_t *src, const uint32_t *tw, int N, int mod, int i)
+// first stage, butterfly i in [0, N/4); mod = 4096 / N.  No saturation can occur (see header).
+QHD void first(int2 *src, const int2 *tw, int N, int mod, int i)
 {
     const int n2 = N >> 2, ic = i * mod;
-    uint32_t *p0 = src + i, *p1 = p0 + n2, *p2 = p1 + n2, *p3 = p2 + n2;
-    const uint32_t xa = quarter(*p0), xb = quarter(*p1), xc = quarter(*p2), xd = quarter(*p3);
-    uint32_t R = qadd(xa, xc), S = qsub(xa, xc);
-    const uint32_t T2 = qadd(xb, xd);
-    *p0 = shadd(R, T2);
-    R = qsub(R, T2);
-    *p1 = cmul(tw[2 * ic], R);
-    const uint32_t T = qsub(xb, xd);
-    R = qasx(S, T);
-    S = qsax(S, T);
-    *p2 = cmul(tw[ic], S);
-    *p3 = cmul(tw[3 * ic], R);
+    int2 *p0 = src + P(i), *p1 = src + P(i + n2), *p2 = src + P(i + 2 * n2), *p3 = src + P(i + 3 * n2);
+    int2 xa = *p0, xb = *p1, xc = *p2, xd = *p3;
+    xa.x >>= 2; xa.y >>= 2; xb.x >>= 2; xb.y >>= 2; xc.x >>= 2; xc.y >>= 2; xd.x >>= 2; xd.y >>= 2;
+    const int Rx = xa.x + xc.x, Ry = xa.y + xc.y, Sx = xa.x - xc.x, Sy = xa.y - xc.y;
+    const int Tx = xb.x + xd.x, Ty = xb.y + xd.y, Ux = xb.x - xd.x, Uy = xb.y - xd.y;
+    *p0 = make_int2((Rx + Tx) >> 1, (Ry + Ty) >> 1);
+    *p1 = cmul(tw[2 * ic], make_int2(Rx - Tx, Ry - Ty));
+    *p2 = cmul(tw[ic], make_int2(Sx + Uy, Sy - Ux));          // QSAX(S, T): xa - xc - j (xb - xd)
+    *p3 = cmul(tw[3 * ic], make_int2(Sx - Uy, Sy + Ux));      // QASX(S, T): xa - xc + j (xb - xd)
 }
 
 // middle stage with group span n1 and quarter span n2 = n1/4, twiddle step mod; butterfly b in [0, N/4)
-QHD void middle(uint32_t *src, const uint32_t *tw, int n1, int n2, int mod, int b)
+QHD void middle(int2 *src, const int2 *tw, int n1, int n2, int mod, int b)
 {
-    const int j = b % n2, grp = b / n2, ic = j * mod;
-    uint32_t *p0 = src + j + grp * n1, *p1 = p0 + n2, *p2 = p1 + n2, *p3 = p2 + n2;
-    const uint32_t xa = *p0, xb = *p1, xc = *p2, xd = *p3;
-    uint32_t R = qadd(xa, xc), S = qsub(xa, xc);
-    uint32_t T = qadd(xb, xd);
-    *p0 = shadd(shadd(R, T), 0u);
-    R = shsub(R, T);
-    *p1 = cmul(tw[2 * ic], R);
-    T = qsub(xb, xd);
-    R = shasx(S, T);
-    S = shsax(S, T);
-    *p2 = cmul(tw[ic], S);
-    *p3 = cmul(tw[3 * ic], R);
+    const int j = b % n2, grp = b / n2, ic = j * mod, i0 = j + grp * n1;
+    int2 *p0 = src + P(i0), *p1 = src + P(i0 + n2), *p2 = src + P(i0 + 2 * n2), *p3 = src + P(i0 + 3 * n2);
+    const int2 xa = *p0, xb = *p1, xc = *p2, xd = *p3;
+    const int Rx = s16(xa.x + xc.x), Ry = s16(xa.y + xc.y), Sx = s16(xa.x - xc.x), Sy = s16(xa.y - xc.y);
+    const int Tx = s16(xb.x + xd.x), Ty = s16(xb.y + xd.y), Ux = s16(xb.x - xd.x), Uy = s16(xb.y - xd.y);
+    *p0 = make_int2(((Rx + Tx) >> 1) >> 1, ((Ry + Ty) >> 1) >> 1);
+    *p1 = cmul(tw[2 * ic], make_int2((Rx - Tx) >> 1, (Ry - Ty) >> 1));
+    *p2 = cmul(tw[ic], make_int2((Sx + Uy) >> 1, (Sy - Ux) >> 1));        // SHSAX(S, T)
+    *p3 = cmul(tw[3 * ic], make_int2((Sx - Uy) >> 1, (Sy + Ux) >> 1));    // SHASX(S, T)
 }
 
-// last stage, butterfly b in [0, N/4) on words 4b..4b+3
-QHD void last(uint32_t *src, int b)
+// last stage, butterfly b in [0, N/4) on elements 4b..4b+3
+QHD void last(int2 *src, int b)
 {
-    uint32_t *w = src + 4 * b;
-    const uint32_t xa = w[0], xb = w[1], xc = w[2], xd = w[3];
-    const uint32_t R = qadd(xa, xc), T = qadd(xb, xd), S = qsub(xa, xc), U = qsub(xb, xd);
-    w[0] = shadd(R, T);
-    w[1] = shsub(R, T);
-    w[2] = shsax(S, U);
-    w[3] = shasx(S, U);
+    int2 *w = src + P(4 * b);                                  // 4b..4b+3 never straddle a skew boundary
+    const int2 xa = w[0], xb = w[1], xc = w[2], xd = w[3];
+    const int Rx = s16(xa.x + xc.x), Ry = s16(xa.y + xc.y), Sx = s16(xa.x - xc.x), Sy = s16(xa.y - xc.y);
+    const int Tx = s16(xb.x + xd.x), Ty = s16(xb.y + xd.y), Ux = s16(xb.x - xd.x), Uy = s16(xb.y - xd.y);
+    w[0] = make_int2((Rx + Tx) >> 1, (Ry + Ty) >> 1);
+    w[1] = make_int2((Rx - Tx) >> 1, (Ry - Ty) >> 1);
+    w[2] = make_int2((Sx + Uy) >> 1, (Sy - Ux) >> 1);          // SHSAX(S, U)
+    w[3] = make_int2((Sx - Uy) >> 1, (Sy + Ux) >> 1);          // SHASX(S, U)
 }
 
 QHD uint32_t bitrev(uint32_t i, int bits)

@@ -6,18 +6,19 @@
 // error feedback carried in `sum`, output SSAT16(sum >> 14).  Integer, bit-exact.
 //
 // A saturating recurrence with error feedback is sequential in time, so one THREAD owns one stream
-// (channel x {I,Q}) with b/a history and the error accumulator in registers.  A warp cannot hide its own
-// dependent-issue latency, so a warp owns only 4 channels (8 walking lanes, C/4 warps in flight); rows are
-// staged with double-buffered 16-byte cp.async copies (chunk-rotated per row, conflict free), the I and Q
-// lanes of a channel re-interleave their outputs with one shuffle, and results leave as coalesced 16-byte
-// stores issued by all 32 lanes.
+// (channel x {I,Q}) with b/a history and the error accumulator in registers; a warp owns 16 channels (every
+// lane walks).  The kernel sits on the spectrum branch of the graph, which runs beside the (longer) audio branch,
+// so what counts is not its latency but how few issue slots it takes from the kernels running next to it.
+// Rows are staged with double-buffered 16-byte cp.async copies (chunk-rotated per row, conflict free), the I
+// and Q lanes of a channel re-interleave their outputs with one shuffle, and results leave as coalesced
+// 16-byte stores.
 //   SMLAWx(c, x) = (c * x) >> 16 is computed as __mulhi(c, x << 16): one IMAD.HI.
 #include "rdsp_common.cuh"
 #include "kernels.h"
 
 namespace {
 
-constexpr int R = 4;                                   // channels per warp
+constexpr int R = 16;                                  // channels per warp: all 32 lanes walk a stream
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 {
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(32) k_biquad(BiquadArgs a)
                     o[h] = aprev;
                 }
                 // re-interleave: the I lane has (I0|I1), (I2|I3); the Q lane has (Q0|Q1), (Q2|Q3)
-                const uint32_t p0 = __shfl_xor_sync(0x000000ffu, o[0], 1), p1 = __shfl_xor_sync(0x000000ffu, o[1], 1);
+                const uint32_t p0 = __shfl_xor_sync(0xffffffffu, o[0], 1), p1 = __shfl_xor_sync(0xffffffffu, o[1], 1);
                 uint2 outw;
                 if (iq == 0) outw = make_uint2((o[0] & 0xFFFFu) | (p0 << 16), (o[0] >> 16) | (p0 & 0xFFFF0000u));      // frames 0, 1
                 else         outw = make_uint2((p1 & 0xFFFFu) | (o[1] << 16), (p1 >> 16) | (o[1] & 0xFFFF0000u));      // frames 2, 3

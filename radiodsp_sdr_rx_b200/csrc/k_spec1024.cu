@@ -15,11 +15,11 @@
 
 namespace {
 
-constexpr int WARPS = 4;
+constexpr int WARPS = 2;
 
 __global__ void __launch_bounds__(WARPS * 32) k_spec1024(Spec1024Args a)
 {
-    __shared__ uint32_t s_fft[WARPS][1024];
+    __shared__ __align__(8) int2 s_fft[WARPS][1024 + 256];        // unpacked (re, im), skewed (fft_q15.cuh)
     __shared__ __align__(16) int16_t s_ring[WARPS][8][RDSP_BLK];
     __shared__ int16_t s_win[1024];
 
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec1024(Spec1024Args a)
 #pragma unroll
     for (int s = 0; s < 8; s++) ring2[s * 32 + lane] = gring[s * 32 + lane];
     __syncwarp();
-    uint32_t *fb = s_fft[warp];
+    int2 *fb = s_fft[warp];
 
     for (int t = 0; t < a.T; t++) {
         const unsigned long long tick = a.tick0 + t;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec1024(Spec1024Args a)
                 const int i = lane + 32 * j;                       // frame sample index
                 const int b = i >> 7, n = i & 127;
                 const int32_t smp = s_ring[warp][(int)((tick + 1 + b) & 7ull)][n];
-                fb[i] = ((uint32_t)((smp * (int32_t)s_win[i]) >> 15)) & 0xFFFFu;     // imaginary part 0
+                fb[q15fft::P(i)] = make_int2((int16_t)((smp * (int32_t)s_win[i]) >> 15), 0);     // imaginary part 0
             }
             __syncwarp();
 #pragma unroll 2
@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec1024(Spec1024Args a)
 #pragma unroll 4
             for (int j = 0; j < 16; j++) {
                 const int i = lane + 32 * j;
-                const uint32_t w = fb[__brev((unsigned)i) >> 22];
-                const uint32_t magsq = (uint32_t)(lo16(w) * lo16(w)) + (uint32_t)(hi16(w) * hi16(w));
+                const int2 w = fb[q15fft::P((int)(__brev((unsigned)i) >> 22))];
+                const uint32_t magsq = (uint32_t)(w.x * w.x) + (uint32_t)(w.y * w.y);
                 a.output[(size_t)ch * 512 + i] = (uint16_t)sqrt_u32_approx(magsq);
             }
             __syncwarp();

@@ -19,7 +19,7 @@ constexpr int WARPS = 8;
 
 __global__ void __launch_bounds__(WARPS * 32) k_spec256(Spec256Args a)
 {
-    __shared__ uint32_t s_fft[WARPS][256];
+    __shared__ __align__(8) int2 s_fft[WARPS][256 + 64];          // unpacked (re, im), skewed (fft_q15.cuh)
     __shared__ int16_t s_win[256];
 
     for (int i = threadIdx.x; i < 256; i += WARPS * 32) s_win[i] = a.win[i];
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec256(Spec256Args a)
 #pragma unroll
     for (int j = 0; j < 4; j++) { w0[j] = s_win[lane + 32 * j]; w1[j] = s_win[128 + lane + 32 * j]; }
     int have_prev = a.have_prev, count = a.count;
-    uint32_t *fb = s_fft[warp];
+    int2 *fb = s_fft[warp];
 
     for (int t = 0; t < a.T; t++) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.iq + ((size_t)t * a.C + ch) * 2 * RDSP_BLK);
@@ -51,8 +51,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec256(Spec256Args a)
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int n = lane + 32 * j;
-                fb[n] = mk16((lo16(pw[j]) * w0[j]) >> 15, (hi16(pw[j]) * w0[j]) >> 15);
-                fb[128 + n] = mk16((lo16(cw[j]) * w1[j]) >> 15, (hi16(cw[j]) * w1[j]) >> 15);
+                // (v * w) >> 15 stored back into an int16 by the reference: keep the low 16 bits, sign-extended
+                fb[q15fft::P(n)] = make_int2((int16_t)((lo16(pw[j]) * w0[j]) >> 15), (int16_t)((hi16(pw[j]) * w0[j]) >> 15));
+                fb[q15fft::P(128 + n)] = make_int2((int16_t)((lo16(cw[j]) * w1[j]) >> 15), (int16_t)((hi16(cw[j]) * w1[j]) >> 15));
             }
             __syncwarp();
             q15fft::first(fb, a.tw, 256, 16, lane);
@@ -70,8 +71,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec256(Spec256Args a)
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int i = lane + 32 * j;
-                const uint32_t w = fb[__brev((unsigned)i) >> 24];
-                const uint32_t magsq = (uint32_t)(lo16(w) * lo16(w)) + (uint32_t)(hi16(w) * hi16(w));
+                const int2 w = fb[q15fft::P((int)(__brev((unsigned)i) >> 24))];
+                const uint32_t magsq = (uint32_t)(w.x * w.x) + (uint32_t)(w.y * w.y);
                 const uint32_t q = (uint32_t)(((unsigned long long)magsq * a.div_magic) >> a.div_shift);   // magsq / naverage, exact
                 sum[j] = (count == 0) ? q : sum[j] + q;
             }

@@ -92,7 +92,7 @@ struct Spec256Args {
     int naverage;
     unsigned long long div_magic;   // ceil(2^div_shift / naverage), div_shift = 32 + ceil(log2 naverage):
     int div_shift;                  // (magsq * div_magic) >> div_shift == magsq / naverage for magsq <= 2^31
-    const uint32_t *tw;         // [3072] twiddleCoef_4096_q15 as (cos | sin << 16) words
+    const int2 *tw;             // [3072] twiddleCoef_4096_q15 as (cos, sin) int pairs
     const int16_t *win;         // [256] Hann
 };
 void launch_spec256(const Spec256Args &a, cudaStream_t st);
@@ -105,7 +105,7 @@ struct Spec1024Args {
     int C, T;
     unsigned long long tick0;   // global tick index of block 0 of this call
     int any_fft;                // some tick of this call completes a 1024-sample frame
-    const uint32_t *tw;         // [3072]
+    const int2 *tw;             // [3072]
     const int16_t *win;         // [1024] Hann
 };
 void launch_spec1024(const Spec1024Args &a, cudaStream_t st);

@@ -69,7 +69,7 @@ struct rdsp_gpu {
     std::vector<float> masks;                  // [n][512]
     int masks_uploaded = 0, mask_cap = 0;
     float2 *d_masks = nullptr;
-    uint32_t *d_tw = nullptr;
+    int2 *d_tw = nullptr;
     int16_t *d_win256 = nullptr, *d_win1024 = nullptr;
     float2 *d_tw256 = nullptr;
     int32_t bq[5];
@@ -469,7 +469,9 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
         CKC(dalloc(&h->d_tw, (size_t)3072));
         std::vector<uint32_t> tw(3072);
         rdsp_host::make_twiddle_4096_q15(tw.data());
-        CKC(cudaMemcpy(h->d_tw, tw.data(), tw.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        std::vector<int2> tw2(3072);
+        for (int k = 0; k < 3072; k++) tw2[k] = make_int2((int16_t)(tw[k] & 0xFFFFu), (int16_t)(tw[k] >> 16));
+        CKC(cudaMemcpy(h->d_tw, tw2.data(), tw2.size() * sizeof(int2), cudaMemcpyHostToDevice));
     }
     if (sm & RDSP_STAGE_SPEC256) {
         CKC(dalloc(&h->d_bq_state, C * 8));

@@ -55,7 +55,7 @@ static void test_fft256_lanes()
     CHECK(d < 2e-5 * maxmag, "fft256 lanes vs oracle arm_cfft_f32: %g", d);
 }
 
-static void q15_fft_product(uint32_t *buf, const uint32_t *tw, int N)
+static void q15_fft_product(int2 *buf, const int2 *tw, int N)
 {
     const int nb = N / 4;
     for (int b = 0; b < nb; b++) q15fft::first(buf, tw, N, 4096 / N, b);
@@ -70,26 +70,34 @@ static void q15_fft_product(uint32_t *buf, const uint32_t *tw, int N)
 
 static void test_q15_fft(int N, int mode)
 {
-    std::vector<uint32_t> tw(3072);
-    rdsp_host::make_twiddle_4096_q15(tw.data());
-    CHECK(memcmp(tw.data(), oracle_twiddle_4096_q15(), 3072 * 4) == 0, "q15 twiddle table differs from oracle");
-    std::vector<uint32_t> a(N), b(N);
+    std::vector<uint32_t> tww(3072);
+    rdsp_host::make_twiddle_4096_q15(tww.data());
+    CHECK(memcmp(tww.data(), oracle_twiddle_4096_q15(), 3072 * 4) == 0, "q15 twiddle table differs from oracle");
+    std::vector<int2> tw(3072);
+    for (int k = 0; k < 3072; k++) tw[k] = make_int2((int16_t)(tww[k] & 0xFFFFu), (int16_t)(tww[k] >> 16));
+    std::vector<uint32_t> a(N);
+    std::vector<int2> b(q15fft::padded(N));
     for (int i = 0; i < N; i++) {
         int re, im;
         if (mode == 0) { re = (int)(rnd() % 65536) - 32768; im = (int)(rnd() % 65536) - 32768; }
         else if (mode == 1) { re = (rnd() & 1) ? 32767 : -32768; im = (rnd() & 1) ? 32767 : -32768; }
+        else if (mode == 3) { re = (i & 1) ? 32767 : -32768; im = (i & 2) ? -32768 : 32767; }
         else { re = (int)lrint(20000 * cos(2 * M_PI * 7 * i / N)); im = (int)lrint(20000 * sin(2 * M_PI * 7 * i / N)); }
         a[i] = ((uint32_t)(uint16_t)(int16_t)re) | ((uint32_t)(uint16_t)(int16_t)im << 16);
+        b[q15fft::P(i)] = make_int2(re, im);
     }
-    b = a;
     arm_cfft_radix4_instance_q15 inst;
     arm_cfft_radix4_init_q15(&inst, (uint16_t)N, 0, 1);
     arm_cfft_radix4_q15(&inst, reinterpret_cast<q15_t *>(a.data()));
     q15_fft_product(b.data(), tw.data(), N);
     int bits = 0; while ((1 << bits) < N) bits++;
     int bad = 0;
-    for (int i = 0; i < N; i++) if (a[i] != b[q15fft::bitrev((uint32_t)i, bits)]) bad++;
-    CHECK(bad == 0, "q15 FFT N=%d mode=%d: %d words differ", N, mode, bad);
+    for (int i = 0; i < N; i++) {
+        const int2 g = b[q15fft::P((int)q15fft::bitrev((uint32_t)i, bits))];
+        const int re = (int16_t)(a[i] & 0xFFFF), im = (int16_t)(a[i] >> 16);
+        if (g.x != re || g.y != im) bad++;
+    }
+    CHECK(bad == 0, "q15 FFT N=%d mode=%d: %d bins differ", N, mode, bad);
     if (mode == 2) {   // sanity: tone at bin 7 with gain 1/N
         const int re = (int16_t)(a[7] & 0xFFFF);
         CHECK(abs(re - 20000) < 64, "q15 FFT tone bin value %d", re);
@@ -157,8 +165,8 @@ static void test_design_tables()
 int main()
 {
     test_fft256_lanes();
-    for (int mode = 0; mode < 3; mode++) { test_q15_fft(256, mode); test_q15_fft(1024, mode); }
-    for (int r = 0; r < 20; r++) { test_q15_fft(256, 0); test_q15_fft(1024, 0); }
+    for (int mode = 0; mode < 4; mode++) { test_q15_fft(256, mode); test_q15_fft(1024, mode); }
+    for (int r = 0; r < 200; r++) { test_q15_fft(256, r & 1); test_q15_fft(1024, r & 1); }
     test_div_magic();
     test_design_tables();
     printf(g_fail ? "FAILED (%d)\n" : "ALL OK\n", g_fail);
