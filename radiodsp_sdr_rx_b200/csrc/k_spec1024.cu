@@ -22,11 +22,14 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec1024(Spec1024Args a)
     __shared__ __align__(8) int2 s_fft[WARPS][1024 + 256];        // unpacked (re, im), skewed (fft_q15.cuh)
     __shared__ __align__(16) int16_t s_ring[WARPS][8][RDSP_BLK];
     __shared__ int16_t s_win[1024];
+    __shared__ __align__(8) int2 s_tw[768];                       // twiddle k*4 of the 4096-table, k < 768
+    __shared__ __align__(16) uint16_t s_o[WARPS][512];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ch = blockIdx.x * WARPS + warp;
     if (a.any_fft) {
         for (int i = threadIdx.x; i < 1024; i += WARPS * 32) s_win[i] = a.win[i];
+        for (int i = threadIdx.x; i < 768; i += WARPS * 32) s_tw[i] = a.tw[4 * i];
         __syncthreads();
     }
     if (ch >= a.C) return;
@@ -69,26 +72,35 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec1024(Spec1024Args a)
             }
             __syncwarp();
 #pragma unroll 2
-            for (int r = 0; r < 8; r++) q15fft::first(fb, a.tw, 1024, 4, lane + 32 * r);
+            for (int r = 0; r < 8; r++) q15fft::first(fb, s_tw, 1024, 1, lane + 32 * r);      // steps in units of the 1024-table
             __syncwarp();
 #pragma unroll 2
-            for (int r = 0; r < 8; r++) q15fft::middle(fb, a.tw, 256, 64, 16, lane + 32 * r);
+            for (int r = 0; r < 8; r++) q15fft::middle(fb, s_tw, 256, 64, 4, lane + 32 * r);
             __syncwarp();
 #pragma unroll 2
-            for (int r = 0; r < 8; r++) q15fft::middle(fb, a.tw, 64, 16, 64, lane + 32 * r);
+            for (int r = 0; r < 8; r++) q15fft::middle(fb, s_tw, 64, 16, 16, lane + 32 * r);
             __syncwarp();
 #pragma unroll 2
-            for (int r = 0; r < 8; r++) q15fft::middle(fb, a.tw, 16, 4, 256, lane + 32 * r);
+            for (int r = 0; r < 8; r++) q15fft::middle(fb, s_tw, 16, 4, 64, lane + 32 * r);
             __syncwarp();
 #pragma unroll 2
             for (int r = 0; r < 8; r++) q15fft::last(fb, lane + 32 * r);
             __syncwarp();
+            // bins 0..511 sit at the EVEN elements (bin = bitrev10(element)); walk the elements, stage the u16 results
+            // in natural order, store them coalesced
 #pragma unroll 4
             for (int j = 0; j < 16; j++) {
-                const int i = lane + 32 * j;
-                const int2 w = fb[q15fft::P((int)(__brev((unsigned)i) >> 22))];
+                const int e = 2 * (lane + 32 * j);
+                const int2 w = fb[q15fft::P(e)];
                 const uint32_t magsq = (uint32_t)(w.x * w.x) + (uint32_t)(w.y * w.y);
-                a.output[(size_t)ch * 512 + i] = (uint16_t)sqrt_u32_approx(magsq);
+                s_o[warp][__brev((unsigned)e) >> 22] = (uint16_t)sqrt_u32_approx(magsq);
+            }
+            __syncwarp();
+            {
+                const uint4 *so = reinterpret_cast<const uint4 *>(s_o[warp]);
+                uint4 *go = reinterpret_cast<uint4 *>(a.output + (size_t)ch * 512);
+                go[lane] = so[lane];
+                go[lane + 32] = so[lane + 32];
             }
             __syncwarp();
         }

@@ -21,16 +21,20 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec256(Spec256Args a)
 {
     __shared__ __align__(8) int2 s_fft[WARPS][256 + 64];          // unpacked (re, im), skewed (fft_q15.cuh)
     __shared__ int16_t s_win[256];
+    __shared__ __align__(8) int2 s_tw[192];                       // twiddle k*16 of the 4096-table, k < 192
 
     for (int i = threadIdx.x; i < 256; i += WARPS * 32) s_win[i] = a.win[i];
+    for (int i = threadIdx.x; i < 192; i += WARPS * 32) s_tw[i] = a.tw[16 * i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ch = blockIdx.x * WARPS + warp;
     if (ch >= a.C) return;
 
+    // register j holds bin bitrev8(lane + 32 j): the FFT leaves bin i at element bitrev(i), so walking the ELEMENTS
+    // lane + 32 j keeps the shared-memory reads of the |.|^2 loop contiguous (the sums are only loaded / stored once per call)
     uint32_t sum[8], pw[4];
 #pragma unroll
-    for (int j = 0; j < 8; j++) sum[j] = a.sum[(size_t)ch * 256 + lane + 32 * j];
+    for (int j = 0; j < 8; j++) sum[j] = a.sum[(size_t)ch * 256 + (__brev((unsigned)(lane + 32 * j)) >> 24)];
     {
         const uint32_t *pr = reinterpret_cast<const uint32_t *>(a.prev + (size_t)ch * 2 * RDSP_BLK);
 #pragma unroll
@@ -56,22 +60,21 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec256(Spec256Args a)
                 fb[q15fft::P(128 + n)] = make_int2((int16_t)((lo16(cw[j]) * w1[j]) >> 15), (int16_t)((hi16(cw[j]) * w1[j]) >> 15));
             }
             __syncwarp();
-            q15fft::first(fb, a.tw, 256, 16, lane);
-            q15fft::first(fb, a.tw, 256, 16, lane + 32);
+            q15fft::first(fb, s_tw, 256, 1, lane);                 // twiddle steps in units of the 256-point table
+            q15fft::first(fb, s_tw, 256, 1, lane + 32);
             __syncwarp();
-            q15fft::middle(fb, a.tw, 64, 16, 64, lane);
-            q15fft::middle(fb, a.tw, 64, 16, 64, lane + 32);
+            q15fft::middle(fb, s_tw, 64, 16, 4, lane);
+            q15fft::middle(fb, s_tw, 64, 16, 4, lane + 32);
             __syncwarp();
-            q15fft::middle(fb, a.tw, 16, 4, 256, lane);
-            q15fft::middle(fb, a.tw, 16, 4, 256, lane + 32);
+            q15fft::middle(fb, s_tw, 16, 4, 16, lane);
+            q15fft::middle(fb, s_tw, 16, 4, 16, lane + 32);
             __syncwarp();
             q15fft::last(fb, lane);
             q15fft::last(fb, lane + 32);
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const int i = lane + 32 * j;
-                const int2 w = fb[q15fft::P((int)(__brev((unsigned)i) >> 24))];
+                const int2 w = fb[q15fft::P(lane + 32 * j)];           // = bin bitrev8(lane + 32 j)
                 const uint32_t magsq = (uint32_t)(w.x * w.x) + (uint32_t)(w.y * w.y);
                 const uint32_t q = (uint32_t)(((unsigned long long)magsq * a.div_magic) >> a.div_shift);   // magsq / naverage, exact
                 sum[j] = (count == 0) ? q : sum[j] + q;
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec256(Spec256Args a)
                 count = 0;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const int i = lane + 32 * j;
+                    const int i = (int)(__brev((unsigned)(lane + 32 * j)) >> 24);
                     a.output[(size_t)ch * 256 + (255 - (i ^ 128))] = (uint16_t)sqrt_u32_approx(sum[j]);
                 }
             }
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec256(Spec256Args a)
     }
 
 #pragma unroll
-    for (int j = 0; j < 8; j++) a.sum[(size_t)ch * 256 + lane + 32 * j] = sum[j];
+    for (int j = 0; j < 8; j++) a.sum[(size_t)ch * 256 + (__brev((unsigned)(lane + 32 * j)) >> 24)] = sum[j];
     uint32_t *pr = reinterpret_cast<uint32_t *>(a.prev + (size_t)ch * 2 * RDSP_BLK);
 #pragma unroll
     for (int j = 0; j < 4; j++) pr[lane + 32 * j] = pw[j];
