@@ -232,6 +232,23 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
         }
         __syncwarp();
         for (int i = g; i < 32; i += G) st4(xb + 4 * i, ld4(xb + 128 + 4 * i));   // current block becomes the previous one
+        // Safety net, outside the reference's arithmetic: when the running energy has lost its digits the recurrence can
+        // run away to inf / NaN (it does in the reference too, and its coefficients then stay NaN for ever because
+        // Init_LMS_NR never clears them).  A channel whose filter went non-finite restarts from zero coefficients.
+        {
+            float chk = energy;
+#pragma unroll
+            for (int i = 0; i < W; i++) chk += c[i];
+            bool bad = !isfinite(chk);
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) bad |= (__shfl_xor_sync(0xffffffffu, (int)bad, o) != 0);
+            if (bad) {
+#pragma unroll
+                for (int i = 0; i < W; i++) c[i] = 0.0f;
+                energy = 0.0f;
+                for (int i = g; i < 32; i += G) st4(xb + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));   // like Init_LMS_NR: history cleared too
+            }
+        }
         __syncwarp();
     }
 
