@@ -106,6 +106,24 @@ PIPE_OPS = {"k_front": 3 * 129 * 128, "k_nlms_notch": 128 * (96 * 2 + 8), "k_nlm
 
 
 # ---------------------------------------------------------------------------------------------
+def ncu_traffic(kernel: str, workload: str, C_: int, T: int):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), valid for the
+    configuration it was taken on (cfg5, 8192 channels, 8 blocks per launch); None otherwise."""
+    if workload != "cfg5" or C_ != 8192 or T != 8:
+        return None
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None
+    k = json.load(open(files[-1]))["kernels"]
+    name = {"k_nlms_notch": "k_nlms<8>", "k_nlms_dnr": "k_nlms<8>", "k_agc": "k_agc<0>"}.get(kernel, kernel)
+    rows = k.get(name)
+    if not rows:
+        return None
+    row = max(rows, key=lambda r: r["grid"]) if kernel != "k_nlms_notch" else min(rows, key=lambda r: r["grid"])
+    return row["dram_bytes"]
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -378,7 +396,7 @@ def run_b200(args):
             frac_ch = {"k_nlms_notch": 0.25 if wl == "cfg5" else 1.0, "k_nlms_dnr": 0.8 if wl == "cfg5" else 1.0}.get(dom, 1.0)
             pipe_ach = PIPE_OPS.get(dom, 0) * frac_ch * C_ * T / (per_launch_ms * 1e-3)
             roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "alg_bytes_per_channel_block": ab.get(dom),
+                    "traffic": ncu_traffic(dom, wl, C_, T), "peak_source": peak_src, "alg_bytes_per_channel_block": ab.get(dom),
                     "ms_per_launch": per_launch_ms,
                     "binding": "fp32/int32 pipe (sequential NLMS / 129-tap q15 FIRs), not HBM — see DESIGN.md",
                     "pipe": {"achieved_Tlaneops": pipe_ach / 1e12, "peak_Tlaneops": pipe_peak / 1e12, "frac": pipe_ach / pipe_peak}}
