@@ -19,6 +19,7 @@
  *   rdsp_gpu_read_spectrum     FFT.available() + FFT.output[256]          analyze_fft256iq.h:61-67,99
  *   rdsp_gpu_read_audio_spectrum  AudioFFT.available() + output[512]      RadioDSP_SDR_RX.ino:58,87,222; RDSP_display.h:219
  *   rdsp_gpu_read_panadapter   Update_Panadapter / Update_smeter maths    RDSP_display.h:260-280,366-374
+ *   rdsp_gpu_read_waterfall    WaterfallData history + colour classes     RDSP_display.h:30,282-319
  *   rdsp_gpu_set_taps          (coefficient tables are data; AudioSDR filter presets)
  *   rdsp_gpu_set_mask          init_filter_mask() result as data          RDSP_convolutional.h:87-110
  *   rdsp_gpu_destroy           (none: the sketch never tears down)
@@ -187,6 +188,11 @@ int  rdsp_gpu_read_audio_spectrum(rdsp_gpu_t *h, uint32_t ch_first, uint32_t ch_
 /* Panadapter trace (RDSP_display.h:260-280) u16[256] and S-meter level (RDSP_display.h:366-374,
  * value passed to displayPeak before its IIR) computed on the device from the last spectrum. */
 int  rdsp_gpu_read_panadapter(rdsp_gpu_t *h, uint32_t ch_first, uint32_t ch_count, uint16_t *trace, float *smeter);
+/* Waterfall history (RDSP_display.h:30,282-319): every rdsp_gpu_read_panadapter call pushes the new trace line
+ * (SpectrumView[2x], x <= 127) on top of a 50-row history kept on the device.  rows [ch_count][50][128] uint16 (row 0
+ * newest), colour (optional) [ch_count][50][128] = the sketch's colour class of each cell: 6 red >= 75, 5 magenta >= 50,
+ * 4 orange >= 40, 3 yellow >= 25, 2 blue >= 15, 1 navy >= 5, 0 black. */
+int  rdsp_gpu_read_waterfall(rdsp_gpu_t *h, uint32_t ch_first, uint32_t ch_count, uint16_t *rows, uint8_t *colour);
 
 /* Coefficient tables are data.  taps: n_taps (= RDSP_FIR_TAPS) q15 values. */
 int  rdsp_gpu_set_taps(rdsp_gpu_t *h, int kind, int index, const int16_t *taps, uint32_t n_taps);

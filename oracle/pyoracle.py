@@ -86,6 +86,7 @@ def lib():
         L.rdsp_oracle_chan_read_spectrum.argtypes = [C.c_void_p, C.c_void_p]
         L.rdsp_oracle_chan_read_audio_spectrum.argtypes = [C.c_void_p, C.c_void_p]
         L.rdsp_oracle_chan_read_panadapter.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        L.rdsp_oracle_chan_read_waterfall.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rdsp_oracle_chan_get_mask.argtypes = [C.c_void_p, C.c_void_p]
         L.rdsp_oracle_chan_set_mask.argtypes = [C.c_void_p, C.c_void_p]
         L.rdsp_oracle_calc_cplx_fir.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
@@ -192,6 +193,12 @@ class OracleChan:
         s = C.c_float()
         lib().rdsp_oracle_chan_read_panadapter(self._h, _ptr(out), C.byref(s))
         return out, s.value
+
+    def read_waterfall(self):
+        rows = np.zeros((50, 128), np.uint16)
+        col = np.zeros((50, 128), np.uint8)
+        lib().rdsp_oracle_chan_read_waterfall(self._h, _ptr(rows), _ptr(col))
+        return rows, col
 
     def get_mask(self):
         m = np.zeros(512, np.float32)

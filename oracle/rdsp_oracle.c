@@ -238,6 +238,7 @@ struct rdsp_oracle_chan {
     oracle_fft1024_t fft1024;
     /* K11 */
     uint16_t spectrum_view[256], spectrum_view_old[256];
+    uint16_t waterfall[50][128];             /* WaterfallData[MAX_WATERFALL][..], RDSP_display.h:30; cols 0..127 used */
 };
 
 /* setup() defaults, RadioDSP_SDR_RX.ino:117-148,183 (the oracle keeps its own copy so that it
@@ -590,6 +591,18 @@ void rdsp_oracle_bank_process(rdsp_oracle_chan_t **chans, uint32_t ch_first, uin
                                  audio + (size_t)ch * 2 * BLK, stride, 0, 0);
 }
 
+/* waterfall rows [50][128] (row 0 newest) and the colour class of every cell, thresholds of RDSP_display.h:299-318
+ * with low = 0: 6 red >= 75, 5 magenta >= 50, 4 orange >= 40, 3 yellow >= 25, 2 blue >= 15, 1 navy >= 5, 0 black */
+void rdsp_oracle_chan_read_waterfall(rdsp_oracle_chan_t *c, uint16_t *rows, uint8_t *colour)
+{
+    memcpy(rows, c->waterfall, sizeof(c->waterfall));
+    if (!colour) return;
+    for (int i = 0; i < 50 * 128; i++) {
+        const int v = rows[i], low = 0;
+        colour[i] = v >= low + 75 ? 6 : v >= low + 50 ? 5 : v >= low + 40 ? 4 : v >= low + 25 ? 3 : v >= low + 15 ? 2 : v >= low + 5 ? 1 : 0;
+    }
+}
+
 int rdsp_oracle_chan_read_spectrum(rdsp_oracle_chan_t *c, uint16_t *out)
 {
     int avail = c->outputflag;                                       /* available(), analyze_fft256iq.h:61-67 */
@@ -622,6 +635,11 @@ void rdsp_oracle_chan_read_panadapter(rdsp_oracle_chan_t *c, uint16_t *trace, fl
         c->spectrum_view_old[x] = c->spectrum_view[x];
     }
     memcpy(trace, c->spectrum_view, sizeof(c->spectrum_view));
+    /* waterfall, RDSP_display.h:282-297: the new line is SpectrumView[2x], x <= 127; every older line moves one row
+     * down.  The reference's loop also copies row -1 into row 0 (out of bounds); restated without
+     * that read: row 0 keeps the new line. */
+    for (int row = 50 - 1; row >= 1; row--) memcpy(c->waterfall[row], c->waterfall[row - 1], sizeof(c->waterfall[0]));
+    for (int x = 0; x <= 127; x++) c->waterfall[0][x] = c->spectrum_view[x * 2];
     float specVal = 0.0;
     for (int m = 75; m <= 85; m++) specVal = specVal + c->output[m];
     *smeter = ARD_ABS(specVal / 5);

@@ -49,6 +49,7 @@ void rdsp_oracle_chan_spec256_raw(rdsp_oracle_chan_t *c, const int16_t *i_blk, c
 int  rdsp_oracle_chan_read_spectrum(rdsp_oracle_chan_t *c, uint16_t *out256);        /* returns available() */
 int  rdsp_oracle_chan_read_audio_spectrum(rdsp_oracle_chan_t *c, uint16_t *out512);
 void rdsp_oracle_chan_read_panadapter(rdsp_oracle_chan_t *c, uint16_t *trace256, float *smeter);
+void rdsp_oracle_chan_read_waterfall(rdsp_oracle_chan_t *c, uint16_t *rows50x128, uint8_t *colour50x128);
 void rdsp_oracle_chan_get_mask(rdsp_oracle_chan_t *c, float *mask512);
 void rdsp_oracle_chan_set_mask(rdsp_oracle_chan_t *c, const float *mask512);
 

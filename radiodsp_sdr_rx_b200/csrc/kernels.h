@@ -115,7 +115,18 @@ struct PanArgs {
     const uint16_t *spec;       // [C][256]
     uint16_t *view;             // [C][256] SpectrumView (state: SpectrumViewOld)
     float *smeter;              // [C]
+    uint16_t *waterfall;        // [C][50][128] ring, or nullptr
+    const int *wf_head;         // [ch_count] ring slot that receives the new line of channel ch_first + i
     int ch_first, ch_count;
 };
 void launch_panadapter(const PanArgs &a, cudaStream_t st);
+
+struct WaterfallArgs {
+    const uint16_t *ring;       // [C][50][128]
+    const int *wf_head;         // [ch_count] slot of the newest line
+    uint16_t *rows;             // [ch_count][50][128], row 0 newest
+    uint8_t *colour;            // [ch_count][50][128] colour class 0..6, or nullptr
+    int ch_first, ch_count;
+};
+void launch_waterfall_read(const WaterfallArgs &a, cudaStream_t st);
 

@@ -84,6 +84,7 @@ struct rdsp_gpu {
     int32_t *d_bq_state = nullptr; int16_t *d_spec_prev = nullptr; uint32_t *d_spec_sum = nullptr; uint16_t *d_spec_out = nullptr;
     int16_t *d_ring = nullptr; uint16_t *d_spec1024_out = nullptr;
     uint16_t *d_view = nullptr; float *d_smeter = nullptr;
+    uint16_t *d_waterfall = nullptr; int *d_wf_head = nullptr; std::vector<int> wf_head;   // [C][50][128] ring + newest slot
 
     // scratch
     int16_t *d_mid_a = nullptr, *d_mid_b = nullptr;
@@ -293,6 +294,7 @@ void free_all(rdsp_gpu *h)
                     h->d_tw256, h->d_fe_hist, h->d_nc_coeff, h->d_nc_prev, h->d_nc_energy, h->d_nc_first, h->d_dn_coeff,
                     h->d_dn_prev, h->d_dn_energy, h->d_dn_first, h->d_agc_env, h->d_conv_last, h->d_nfloor, h->d_bq_state,
                     h->d_spec_prev, h->d_spec_sum, h->d_spec_out, h->d_ring, h->d_spec1024_out, h->d_view, h->d_smeter,
+                    h->d_waterfall, h->d_wf_head,
                     h->d_mid_a, h->d_mid_b, h->d_scr, h->d_dbg, h->d_hp_iq};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 2; i++) {
@@ -482,6 +484,9 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
         CKC(dalloc(&h->d_win256, (size_t)256));
         CKC(dalloc(&h->d_view, C * 256));
         CKC(dalloc(&h->d_smeter, C));
+        CKC(dalloc(&h->d_waterfall, C * 50 * 128));
+        CKC(dalloc(&h->d_wf_head, C));
+        h->wf_head.assign(C, 0);
         int16_t w[256];
         rdsp_host::make_hann_q15(w, 256);
         CKC(cudaMemcpy(h->d_win256, w, sizeof(w), cudaMemcpyHostToDevice));
@@ -819,13 +824,44 @@ int rdsp_gpu_read_panadapter(rdsp_gpu_t *h, uint32_t ch_first, uint32_t ch_count
     if (!has(h, RDSP_STAGE_SPEC256)) { h->err = "handle has no SPEC256 stage"; return RDSP_ERR_STATE; }
     if (ch_count == 0 || (uint64_t)ch_first + ch_count > (uint64_t)h->C) { h->err = "channel range out of bounds"; return RDSP_ERR_RANGE; }
     CK(cudaSetDevice(h->cfg.device));
+    // older waterfall lines "move one row down": the head of each channel's ring steps back and takes the new line
+    for (uint32_t i = 0; i < ch_count; i++) h->wf_head[ch_first + i] = (h->wf_head[ch_first + i] + 49) % 50;
+    CK(cudaMemcpyAsync(h->d_wf_head, &h->wf_head[ch_first], ch_count * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     PanArgs a{};
     a.spec = h->d_spec_out; a.view = h->d_view; a.smeter = h->d_smeter; a.ch_first = (int)ch_first; a.ch_count = (int)ch_count;
+    a.waterfall = h->d_waterfall; a.wf_head = h->d_wf_head;
     { Prof pr(h, KK_PAN); launch_panadapter(a, h->stream); }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(trace, h->d_view + (size_t)ch_first * 256, (size_t)ch_count * 256 * sizeof(uint16_t), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(smeter, h->d_smeter + ch_first, (size_t)ch_count * sizeof(float), cudaMemcpyDeviceToHost));
+    return RDSP_OK;
+}
+
+int rdsp_gpu_read_waterfall(rdsp_gpu_t *h, uint32_t ch_first, uint32_t ch_count, uint16_t *rows, uint8_t *colour)
+{
+    if (!h || !rows) return RDSP_ERR_INVALID;
+    if (!has(h, RDSP_STAGE_SPEC256)) { h->err = "handle has no SPEC256 stage"; return RDSP_ERR_STATE; }
+    if (ch_count == 0 || (uint64_t)ch_first + ch_count > (uint64_t)h->C) { h->err = "channel range out of bounds"; return RDSP_ERR_RANGE; }
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)ch_count * 50 * 128;
+    uint16_t *d_rows = nullptr;
+    uint8_t *d_col = nullptr;
+    CK(cudaMalloc((void **)&d_rows, n * sizeof(uint16_t)));
+    if (colour && cudaMalloc((void **)&d_col, n) != cudaSuccess) { cudaFree(d_rows); h->err = "out of device memory"; return RDSP_ERR_NOMEM; }
+    cudaError_t e = cudaMemcpyAsync(h->d_wf_head, &h->wf_head[ch_first], ch_count * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        WaterfallArgs w{};
+        w.ring = h->d_waterfall; w.wf_head = h->d_wf_head; w.rows = d_rows; w.colour = d_col; w.ch_first = (int)ch_first; w.ch_count = (int)ch_count;
+        { Prof pr(h, KK_PAN); launch_waterfall_read(w, h->stream); }
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(rows, d_rows, n * sizeof(uint16_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && colour) e = cudaMemcpy(colour, d_col, n, cudaMemcpyDeviceToHost);
+    cudaFree(d_rows);
+    if (d_col) cudaFree(d_col);
+    if (e != cudaSuccess) { h->err = std::string("read_waterfall: ") + cudaGetErrorString(e); return RDSP_ERR_CUDA; }
     return RDSP_OK;
 }
 

@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 #include "../../include/rdsp_gpu.h"
+#include "rdsp_controls.hpp"
 
 namespace rdsp {
 
@@ -135,5 +136,16 @@ private:
     Bank &b_;
     uint32_t ch_;
 };
+
+// ---- rdsp_controls.hpp: SketchControls<ChannelRadio> drives one channel of a bank ------------------------------
+inline ChannelRadio::ChannelRadio(Bank &b, uint32_t ch) : bank_(b), ch_(ch) {}
+inline uint32_t ChannelRadio::setDemodMode(int m) { auto p = bank_.get(ch_); p.demod = m; bank_.set(ch_, p); return 0; }
+inline void ChannelRadio::setAudioFilter(int f) { auto p = bank_.get(ch_); p.audio_filter = f; bank_.set(ch_, p); }
+inline void ChannelRadio::setAGCmode(int m) { agc_mode_ = m; if (agc_on_) { auto p = bank_.get(ch_); p.agc_mode = m; bank_.set(ch_, p); } }
+inline void ChannelRadio::enableAGC() { agc_on_ = true; auto p = bank_.get(ch_); p.agc_mode = agc_mode_; bank_.set(ch_, p); }
+inline void ChannelRadio::enableALSfilter() { auto p = bank_.get(ch_); p.notch_on = 1; bank_.set(ch_, p); }
+inline void ChannelRadio::disableALSfilter() { auto p = bank_.get(ch_); p.notch_on = 0; bank_.set(ch_, p); }
+inline void ChannelRadio::reInitializeFilter(double lo, double hi) { rdsp::reInitializeFilter(bank_, ch_, lo, hi); }
+inline void ChannelRadio::set_nr_level(int level) { rdsp::set_nr_level(bank_, ch_, level); }
 
 }  // namespace rdsp

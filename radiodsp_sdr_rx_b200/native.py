@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "rdsp_gpu_default_config", "rdsp_gpu_default_params", "rdsp_gpu_create", "rdsp_gpu_destroy",
     "rdsp_gpu_set_mode", "rdsp_gpu_get_mode", "rdsp_gpu_process_block", "rdsp_gpu_process_blocks",
     "rdsp_gpu_synchronize", "rdsp_gpu_stream_join", "rdsp_gpu_set_stream", "rdsp_gpu_read_spectrum", "rdsp_gpu_read_audio_spectrum",
-    "rdsp_gpu_read_panadapter", "rdsp_gpu_set_taps", "rdsp_gpu_get_taps", "rdsp_gpu_set_mask", "rdsp_gpu_get_mask",
+    "rdsp_gpu_read_panadapter", "rdsp_gpu_read_waterfall", "rdsp_gpu_set_taps", "rdsp_gpu_get_taps", "rdsp_gpu_set_mask", "rdsp_gpu_get_mask",
     "rdsp_gpu_read_debug_f32", "rdsp_gpu_kernel_launches", "rdsp_gpu_profile", "rdsp_gpu_profile_read",
     "rdsp_gpu_last_error", "rdsp_gpu_version",
 ]
@@ -88,6 +88,7 @@ def lib():
         L.rdsp_gpu_read_spectrum.argtypes = [vp, u32, u32, vp, vp]
         L.rdsp_gpu_read_audio_spectrum.argtypes = [vp, u32, u32, vp, vp]
         L.rdsp_gpu_read_panadapter.argtypes = [vp, u32, u32, vp, vp]
+        L.rdsp_gpu_read_waterfall.argtypes = [vp, u32, u32, vp, vp]
         L.rdsp_gpu_set_taps.argtypes = [vp, i32, i32, vp, u32]
         L.rdsp_gpu_get_taps.argtypes = [vp, i32, i32, vp, u32]
         L.rdsp_gpu_set_mask.argtypes = [vp, u32, u32, vp]
@@ -235,6 +236,13 @@ class ReceiverBank:
         sm = np.zeros(n, np.float32)
         self._ck(lib().rdsp_gpu_read_panadapter(self._h, ch_first, n, trace.ctypes.data, sm.ctypes.data))
         return trace, sm
+
+    def read_waterfall(self, ch_first=0, ch_count=None, colour=True):
+        n = self.n_channels - ch_first if ch_count is None else ch_count
+        rows = np.zeros((n, 50, 128), np.uint16)
+        col = np.zeros((n, 50, 128), np.uint8) if colour else None
+        self._ck(lib().rdsp_gpu_read_waterfall(self._h, ch_first, n, rows.ctypes.data, col.ctypes.data if colour else None))
+        return rows, col
 
     def read_debug_f32(self, n_blocks: int, ch_first=0, ch_count=None) -> np.ndarray:
         n = self.n_channels - ch_first if ch_count is None else ch_count

@@ -207,6 +207,12 @@ def test_spec256_bit_exact(rd, po, nav, blocks_per_call):
             o_trace, o_sm = ch.read_panadapter()
             assert np.array_equal(trace[c], o_trace) and sm[c] == np.float32(o_sm), (b0, c)
     assert n_ready > 0
+    # waterfall history kept on the device: rows and colour classes equal the oracle's (row 0 = newest line)
+    rows, col = bank.read_waterfall()
+    for c, ch in enumerate(chans):
+        o_rows, o_col = ch.read_waterfall()
+        assert np.array_equal(rows[c], o_rows) and np.array_equal(col[c], o_col), c
+    assert rows.any()
 
 
 @pytest.mark.parametrize("blocks_per_call", [1, 3, 8, 13])

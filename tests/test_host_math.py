@@ -23,3 +23,16 @@ def test_device_math_on_host(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_control_plane_port(tmp_path):
+    """host/rdsp_controls.hpp (mode / filter / AGC / NR cycling, PBT stepping) against the tables of RDSP_controls.h"""
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("g++ not available")
+    exe = str(tmp_path / "test_controls")
+    r = subprocess.run([gxx, "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests/host/test_controls.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr

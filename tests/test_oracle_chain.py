@@ -151,3 +151,19 @@ def test_panadapter_postprocessing(po):
     assert trace.dtype == np.uint16 and int(np.argmax(trace)) in (118, 119, 120)
     t2, _ = ch.read_panadapter()                          # time smoothing converges upwards
     assert t2[119] >= trace[119]
+
+
+def test_waterfall_history(po):
+    """RDSP_display.h:282-319: each refresh pushes SpectrumView[2x] on top, older lines move down one row"""
+    cfg = po.default_config(stage_mask=po.STAGE_SPEC256, spec256_naverage=1)
+    ch = po.OracleChan(cfg)
+    lines = []
+    for k in range(4):
+        ch.process(_tone_iq((8 + 6 * k) * FS / 256, 3, amp=9000))
+        trace, _ = ch.read_panadapter()
+        lines.append(trace[0::2].copy())
+    rows, col = ch.read_waterfall()
+    for r in range(4):
+        assert np.array_equal(rows[r], lines[3 - r])
+    assert not rows[4:].any()
+    assert col.max() <= 6 and ((rows >= 75) == (col == 6)).all() and ((rows < 5) == (col == 0)).all()
