@@ -1,0 +1,663 @@
+// k_front_tc.cu — K0+K1+K2 on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).
+//
+// Same arithmetic as k_front.cu (the CUDA-core version, kept as cross-check): AudioMixer4 gain / IQ balance, the
+// +-45 degree Hilbert FIR pair, sideband sum or AM envelope, audio band-pass FIR — all q15 with the 32-bit wrap-around
+// accumulator of arm_fir_fast_q15 and SSAT(acc >> 15, 16); bit-exact against oracle/rdsp_oracle.c:stage_frontend.
+// Replaces the AudioSDRpreProcessor -> AudioSDR front half of the graph wired at RadioDSP_SDR_RX.ino:71-72,81-82.
+//
+// Toeplitz formulation (north_star: "only if it measurably wins on ncu" — it does, see profiles/):
+//   * one MMA row = one channel, K = time.  A[row][k] is simply the channel's delay line (K-major = the natural
+//     row layout), B[k][n] = h[128 + n - k] is a constant banded Toeplitz image of the 129 taps (built on the host,
+//     once per tap row), D[row][n] = 32 consecutive outputs.  K = 160 = 128 + 32: 24 % padding, no other waste.
+//   * q15 x q15 in Z/2^32 from int8 tensor-core products: x = 256 xh + xl (xh signed, xl unsigned), same for h:
+//         x h = 65536 xh hh + 256 (xh hl + xl hh) + xl hl
+//     Three TMEM accumulators (ll, mid, hh), four MMAs per 32-byte K step with the four signedness combinations of
+//     kind::i8.  No partial sum exceeds 2^24, the recombination wraps in 32-bit registers like the CMSIS accumulator.
+//   * delay lines live in shared memory as two byte planes per line (I', Q', demodulated), each a ring of six
+//     32-sample slices in the canonical no-swizzle K-major core-matrix layout (8 rows x 16 bytes): slice =
+//     [2 k-groups][128 rows][16 B].  An MMA K step reads one slice, so the ring never moves data: chunk c reads slices
+//     c .. c+4 (mod 6) and the loader fills slice c+5 meanwhile.
+//   * one CTA = one tile of 128 channels that share their three tap rows (host-built tile table; channels of a tile
+//     need not be contiguous) and one time segment of the call's T blocks, walked as chunks of 32 samples through a
+//     warp-specialised pipeline (loader / MMA issue / two epilogues, see k_front_tc below).
+//   * the loop bodies are deliberately NOT unrolled beyond 8 outputs: four roles run four different instruction streams
+//     on every SM sub-partition, and the first fully unrolled version spent 30 % of its issue slots waiting for
+//     instruction fetch (ncu: stall_no_inst) with 134 KB of SASS.
+#include "rdsp_common.cuh"
+#include "kernels.h"
+#include <vector>
+#include <map>
+#include <array>
+#include <cstring>
+
+namespace {
+
+constexpr int ROWS = 128;                     // channels per tile = MMA M
+constexpr int NOUT = 32;                      // outputs per chunk = MMA N
+constexpr int KSTEPS = 5;                     // 160 bytes of K, 32 per MMA
+constexpr int SLICES = 6;
+constexpr int SLICE_B = 2 * ROWS * 16;        // 4096: [2 k-groups][128 rows][16 bytes]
+constexpr int PLANE_B = SLICES * SLICE_B;     // 24576
+constexpr int TOEP_PLANE_B = 10 * NOUT * 16;  // 5120: [10 k-groups][32 outputs][16 bytes]
+constexpr int TOEP_SET_B = 2 * TOEP_PLANE_B;  // lo plane, hi plane
+
+constexpr int W_E2 = 4, W_LD = 8, W_MMA = 12, NWARPS = 13;    // warps 0-3 are epilogue 1
+constexpr int NTHREADS = NWARPS * 32;
+
+constexpr int OFF_RING = 0;                                   // [line 0..2][plane 0..1][PLANE_B]
+constexpr int OFF_TAPS = 6 * PLANE_B;                         // [set 0..2][plane 0..1][TOEP_PLANE_B]
+constexpr int OFF_STAGE = OFF_TAPS + 3 * TOEP_SET_B;          // loader staging [2][4 warps][8 items][32 lanes][16 B]
+constexpr int STAGE_B = 4 * 8 * 32 * 16;                      // 16384 per buffer
+constexpr int OFF_META = OFF_STAGE + 2 * STAGE_B;             // per-row parameters, barriers, sqrt seed table
+constexpr int META_B = ROWS * 16 + 128 + 80;
+constexpr int SMEM_B = OFF_META + META_B;
+static_assert(SMEM_B <= 227 * 1024, "shared memory budget");
+
+constexpr int TM_COLS = 512;                  // TMEM columns: two x [I ll|mid|hh][Q ll|mid|hh] x 32, one x [ll|mid|hh] x 32
+constexpr int TM_ACC1B = 192, TM_ACC2P = 384; // acc1[0] @0, acc1[1] @192, acc2 @384 (480 of 512 columns)
+
+// mbarriers (index = chunk parity unless single):
+constexpr int B_IN_FULL = 0, B_M1_DONE = 2, B_E1_DONE = 4, B_M2_DONE = 6, B_E2_DONE = 8;
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 @4, a_format @7, b_format @10 (1 = signed),
+// K-major A and B, N >> 3 @17, M >> 4 @24
+constexpr uint32_t IDESC_BASE = (2u << 4) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+constexpr uint32_t IDESC_UU = IDESC_BASE;
+constexpr uint32_t IDESC_SU = IDESC_BASE | (1u << 7);
+constexpr uint32_t IDESC_US = IDESC_BASE | (1u << 10);
+constexpr uint32_t IDESC_SS = IDESC_BASE | (1u << 7) | (1u << 10);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, no swizzle, K-major: start >> 4 @0, LBO >> 4 @16 (between the two 16-byte K groups),
+// SBO >> 4 @32 (between 8-row groups), version 1 @46
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes)
+{
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+    const uint32_t hi = (128u >> 4) | (1u << 14);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(saddr), "l"(g), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// AudioMixer4 gain: sat16((mult * x) >> 16).  mult = 65536 mh + ml (ml unsigned): the shift distributes exactly,
+// (mult x) >> 16 = mh x + ((ml x) >> 16), and |ml x| < 2^31 — three 32-bit operations, unity gain included.
+__device__ __forceinline__ int32_t mix_gain_tc(int32_t x, int32_t mh, int32_t ml)
+{
+    return sat16(mh * x + ((ml * x) >> 16));
+}
+
+// sqrt_uint32_approx (two Newton steps from a table seed, rdsp_common.cuh) with its two divisions done by a float
+// estimate and an exact fix-up: the quotients stay below 2^18, where the estimate is off by at most one.  The
+// int <-> float conversions use the 2^23 magic number (FADD / LOP, full rate) instead of I2F / F2I (16 lanes/clk/SM).
+__device__ __forceinline__ float small_u2f(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }   // v < 2^23
+__device__ __forceinline__ uint32_t udiv_small_q(uint32_t n, float n_f, uint32_t d)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(small_u2f(d)));
+    uint32_t q = __float_as_uint(n_f * r + 8388608.0f) & 0x7FFFFFu;
+    int32_t rem = (int32_t)(n - q * d);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const bool lo = rem < 0, hi = rem >= (int32_t)d;
+        q += hi ? 1u : (lo ? 0xFFFFFFFFu : 0u);
+        rem += hi ? -(int32_t)d : (lo ? (int32_t)d : 0);
+    }
+    return q;
+}
+__device__ __forceinline__ uint32_t sqrt_u32_approx_fast(uint32_t in, const uint16_t *guess /* shared copy of c_sqrt_guess */)
+{
+    const float in_f = fmaf(small_u2f(in >> 16), 65536.0f, small_u2f(in & 0xFFFFu));
+    uint32_t n = guess[__clz((int)in)];                                 // branch free: in == 0 falls out at the end
+    n = (udiv_small_q(in, in_f, n) + n) >> 1;
+    n = (udiv_small_q(in, in_f, n) + n) >> 1;
+    return in == 0u ? 0u : n;
+}
+
+__device__ __forceinline__ int32_t recombine(uint32_t ll, uint32_t mid, uint32_t hh)
+{
+    const uint32_t acc = ll + (mid << 8) + (hh << 16);                   // wraps like the CMSIS fast-FIR accumulator
+    return sat16(((int32_t)acc) >> 15);
+}
+
+struct TcSmem {
+    uint8_t *base;
+    __device__ __forceinline__ uint8_t *ring(int line, int plane) const { return base + OFF_RING + (line * 2 + plane) * PLANE_B; }
+    __device__ __forceinline__ uint8_t *taps(int set, int plane) const { return base + OFF_TAPS + (set * 2 + plane) * TOEP_PLANE_B; }
+    __device__ __forceinline__ uint8_t *stage(int buf, int lw) const { return base + OFF_STAGE + buf * STAGE_B + lw * (STAGE_B / 4); }
+    __device__ __forceinline__ int *row_ch() const { return reinterpret_cast<int *>(base + OFF_META); }
+    __device__ __forceinline__ int *row_mi() const { return reinterpret_cast<int *>(base + OFF_META + ROWS * 4); }
+    __device__ __forceinline__ int *row_mq() const { return reinterpret_cast<int *>(base + OFF_META + ROWS * 8); }
+    __device__ __forceinline__ int *row_usb() const { return reinterpret_cast<int *>(base + OFF_META + ROWS * 12); }
+    __device__ __forceinline__ uint64_t *bars() const { return reinterpret_cast<uint64_t *>(base + OFF_META + ROWS * 16); }
+    __device__ __forceinline__ uint32_t *tmem_ptr() const { return reinterpret_cast<uint32_t *>(base + OFF_META + ROWS * 16 + 96); }
+    __device__ __forceinline__ uint16_t *sqrt_guess() const { return reinterpret_cast<uint16_t *>(base + OFF_META + ROWS * 16 + 128); }
+};
+
+// ---- loader -------------------------------------------------------------------------------------------------------
+// 32 IQ frames of every row -> gain -> byte planes of the I' and Q' rings.  A warp instruction covers 8 rows x 64 bytes
+// (4 lanes x 16 B per row): full 32-byte sectors from HBM, and each of the four 32-bit plane stores of a lane lands in a
+// 128-byte contiguous run (8 rows x 16 B): conflict free.  Four warps share the 32 (row group, k-group) items of a
+// chunk; the 8 x 16 bytes of a lane go through a private cp.async staging slot, one chunk period ahead of their use.
+__device__ __forceinline__ void fetch_chunk(const TcSmem &s, const FrontArgs &a, int t, int cq, int buf, int lw, int lane)
+{
+    const int rr = lane >> 2, q = lane & 3;
+    const uint32_t st = smem_u32(s.stage(buf, lw)) + lane * 16;
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+        const int i = lw + 4 * k, g = i & 1, row = (i >> 1) * 8 + rr;
+        const int ch = s.row_ch()[row];
+        const int16_t *src = a.iq + (((size_t)t * a.C + (ch >= 0 ? ch : 0)) * RDSP_BLK + cq * NOUT + g * 16 + q * 4) * 2;
+        cp_async16(st + k * 512, src, ch >= 0 ? 16u : 0u);               // padding rows: zero fill
+    }
+    cp_async_commit();
+}
+
+__device__ __forceinline__ void split_chunk(const TcSmem &s, int buf, int slice, int lw, int lane)
+{
+    const int rr = lane >> 2, q = lane & 3;
+    const uint8_t *st = s.stage(buf, lw) + lane * 16;
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+        const int i = lw + 4 * k, g = i & 1, row = (i >> 1) * 8 + rr;
+        const int4 v = *reinterpret_cast<const int4 *>(st + k * 512);
+        uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+        const int mi = s.row_mi()[row], mq = s.row_mq()[row];
+        const int mih = mi >> 16, mil = mi & 0xFFFF, mqh = mq >> 16, mql = mq & 0xFFFF;
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[j] = mk16(mix_gain_tc(lo16(w[j]), mih, mil), mix_gain_tc(hi16(w[j]), mqh, mql));
+        // word = [I lo, I hi, Q lo, Q hi]; 4 x 4 byte transpose
+        const uint32_t i01 = prmt(w[0], w[1], 0x5140), q01 = prmt(w[0], w[1], 0x7362);
+        const uint32_t i23 = prmt(w[2], w[3], 0x5140), q23 = prmt(w[2], w[3], 0x7362);
+        const int off = slice * SLICE_B + g * (ROWS * 16) + row * 16 + q * 4;
+        *reinterpret_cast<uint32_t *>(s.ring(0, 0) + off) = prmt(i01, i23, 0x5410);
+        *reinterpret_cast<uint32_t *>(s.ring(0, 1) + off) = prmt(i01, i23, 0x7632);
+        *reinterpret_cast<uint32_t *>(s.ring(1, 0) + off) = prmt(q01, q23, 0x5410);
+        *reinterpret_cast<uint32_t *>(s.ring(1, 1) + off) = prmt(q01, q23, 0x7632);
+    }
+}
+
+// ---- delay-line state <-> ring, all warps -------------------------------------------------------------------------
+// One warp item = 8 rows x 64 bytes of one line (lane = k-group select, row, 8-sample half): 64-byte runs in HBM,
+// 128-byte runs in shared memory.  192 items per tile.
+template <bool STORE>
+__device__ __forceinline__ void state_io(const TcSmem &s, int16_t *hist, int first_slice, int warp, int lane)
+{
+    const int kgsel = lane >> 4, row8 = (lane >> 1) & 7, half = lane & 1;
+#pragma unroll 1
+    for (int item = warp; item < 3 * 16 * 4; item += NWARPS) {
+        const int line = item >> 6, rg = (item >> 2) & 15, kg = (item & 3) * 2 + kgsel;
+        const int row = rg * 8 + row8, ch = s.row_ch()[row];
+        const int off = ((first_slice + (kg >> 1)) % SLICES) * SLICE_B + (kg & 1) * (ROWS * 16) + row * 16 + half * 8;
+        int2 *plo = reinterpret_cast<int2 *>(s.ring(line, 0) + off), *phi = reinterpret_cast<int2 *>(s.ring(line, 1) + off);
+        int4 *g = ch >= 0 ? reinterpret_cast<int4 *>(hist + ((size_t)ch * 3 + line) * RDSP_BLK + (kg * 2 + half) * 8) : nullptr;
+        if (STORE) {
+            if (g) {
+                const int2 lo = *plo, hi = *phi;
+                *g = make_int4((int)prmt((uint32_t)lo.x, (uint32_t)hi.x, 0x5140), (int)prmt((uint32_t)lo.x, (uint32_t)hi.x, 0x7362),
+                               (int)prmt((uint32_t)lo.y, (uint32_t)hi.y, 0x5140), (int)prmt((uint32_t)lo.y, (uint32_t)hi.y, 0x7362));
+            }
+        } else {
+            int4 v = make_int4(0, 0, 0, 0);
+            if (g) v = *g;
+            *plo = make_int2((int)prmt((uint32_t)v.x, (uint32_t)v.y, 0x6420), (int)prmt((uint32_t)v.z, (uint32_t)v.w, 0x6420));
+            *phi = make_int2((int)prmt((uint32_t)v.x, (uint32_t)v.y, 0x7531), (int)prmt((uint32_t)v.z, (uint32_t)v.w, 0x7531));
+        }
+    }
+}
+
+// ---- MMA issue ----------------------------------------------------------------------------------------------------
+// one 129-tap FIR over 128 rows x 32 outputs: 5 K steps x 4 byte-plane products into (ll, mid, hh) at tmem_d
+__device__ __forceinline__ void issue_fir(uint32_t ring_lo, uint32_t ring_hi, uint32_t taps_lo, uint32_t taps_hi, uint32_t tmem_d, int c)
+{
+    int sl = c % SLICES;
+#pragma unroll 1
+    for (int ks = 0; ks < KSTEPS; ks++) {
+        const uint32_t so = (uint32_t)(sl * SLICE_B);
+        const uint64_t a_lo = make_desc(ring_lo + so, ROWS * 16), a_hi = make_desc(ring_hi + so, ROWS * 16);
+        const uint64_t b_lo = make_desc(taps_lo + ks * 2 * NOUT * 16, NOUT * 16), b_hi = make_desc(taps_hi + ks * 2 * NOUT * 16, NOUT * 16);
+        mma_i8(tmem_d + 0 * NOUT, a_lo, b_lo, IDESC_UU, ks > 0);
+        mma_i8(tmem_d + 1 * NOUT, a_hi, b_lo, IDESC_SU, ks > 0);
+        mma_i8(tmem_d + 1 * NOUT, a_lo, b_hi, IDESC_US, 1);
+        mma_i8(tmem_d + 2 * NOUT, a_hi, b_hi, IDESC_SS, ks > 0);
+        sl = sl + 1 == SLICES ? 0 : sl + 1;
+    }
+}
+
+// ---- epilogues ----------------------------------------------------------------------------------------------------
+// epilogue 1: I' and Q' accumulators -> q15 -> sideband sum / envelope -> D slice (byte planes), 8 outputs per round
+template <bool AM>
+__device__ __forceinline__ void epilogue1(const TcSmem &s, uint32_t tmem_row, int row, int slice, bool usb)
+{
+#pragma unroll 1
+    for (int it = 0; it < 4; it++) {
+        uint32_t v[6][8];
+#pragma unroll
+        for (int k = 0; k < 6; k++) tmem_ld8(tmem_row + k * NOUT + it * 8, v[k]);
+        tmem_ld_wait();
+        int32_t d[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int32_t ya = recombine(v[0][j], v[1][j], v[2][j]);
+            const int32_t yb = recombine(v[3][j], v[4][j], v[5][j]);
+            if (AM) {
+                const uint32_t e = sqrt_u32_approx_fast((uint32_t)(ya * ya) + (uint32_t)(yb * yb), s.sqrt_guess());
+                d[j] = (int32_t)min(e, 32767u);
+            } else {
+                d[j] = sat16(usb ? ya - yb : ya + yb);
+            }
+        }
+        const uint32_t p01 = prmt((uint32_t)d[0], (uint32_t)d[1], 0x5140), p23 = prmt((uint32_t)d[2], (uint32_t)d[3], 0x5140);   // [l0 l1 h0 h1]
+        const uint32_t p45 = prmt((uint32_t)d[4], (uint32_t)d[5], 0x5140), p67 = prmt((uint32_t)d[6], (uint32_t)d[7], 0x5140);
+        const int off = slice * SLICE_B + (it >> 1) * (ROWS * 16) + row * 16 + (it & 1) * 8;
+        *reinterpret_cast<int2 *>(s.ring(2, 0) + off) = make_int2((int)prmt(p01, p23, 0x5410), (int)prmt(p45, p67, 0x5410));
+        *reinterpret_cast<int2 *>(s.ring(2, 1) + off) = make_int2((int)prmt(p01, p23, 0x7632), (int)prmt(p45, p67, 0x7632));
+    }
+}
+
+// epilogue 2: band-pass accumulators -> q15 -> audio rows
+__device__ __forceinline__ void epilogue2(const FrontArgs &a, uint32_t tmem_row, int ch, int t, int cq)
+{
+    const size_t cb = (size_t)t * a.C + (ch >= 0 ? ch : 0);
+#pragma unroll 1
+    for (int h8 = 0; h8 < 4; h8++) {
+        uint32_t v[3][8];
+#pragma unroll
+        for (int k = 0; k < 3; k++) tmem_ld8(tmem_row + k * NOUT + h8 * 8, v[k]);
+        tmem_ld_wait();
+        int32_t m[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) m[j] = recombine(v[0][j], v[1][j], v[2][j]);
+        if (ch < 0) continue;
+        const size_t n0 = cb * RDSP_BLK + cq * NOUT + h8 * 8;
+        if (a.out_mono)
+            st_stream16(a.out_mono + n0, make_int4((int)mk16(m[0], m[1]), (int)mk16(m[2], m[3]), (int)mk16(m[4], m[5]), (int)mk16(m[6], m[7])));
+        if (a.out_stereo) {
+            int16_t *dst = a.out_stereo + n0 * 2;
+            st_stream16(dst, make_int4((int)mk16(m[0], m[0]), (int)mk16(m[1], m[1]), (int)mk16(m[2], m[2]), (int)mk16(m[3], m[3])));
+            st_stream16(dst + 8, make_int4((int)mk16(m[4], m[4]), (int)mk16(m[5], m[5]), (int)mk16(m[6], m[6]), (int)mk16(m[7], m[7])));
+        }
+        if (a.dbg) {
+            float4 *dp = reinterpret_cast<float4 *>(a.dbg + n0 * 2);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float f0 = (float)m[2 * q] / 32768.0f, f1 = (float)m[2 * q + 1] / 32768.0f;
+                dp[q] = make_float4(f0, f0, f1, f1);
+            }
+        }
+    }
+}
+
+#ifdef RDSP_TC_PROF
+__device__ unsigned long long g_tc_prof[16];
+__device__ unsigned long long g_tc_cta[4096][2];
+#define TCP_BEGIN long long tp_ = clock64()
+#define TCP(i) do { if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0) { const long long n_ = clock64(); g_tc_prof[i] += n_ - tp_; tp_ = n_; } } while (0)
+#define TCQ(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) { const long long n_ = clock64(); g_tc_prof[i] += n_ - tq_; tq_ = n_; } } while (0)
+#else
+#define TCP_BEGIN do { } while (0)
+#define TCP(i) do { } while (0)
+#define TCQ(i) do { } while (0)
+#endif
+
+// ---- the kernel: warp-specialised pipeline over the chunks of one tile -----------------------------------------------
+//   warps 0-3   epilogue 1 (TMEM lane quadrant = warp)         warps 8-11  loader (HBM -> gain -> byte planes)
+//   warps 4-7   epilogue 2 (quadrant = warp - 4)               warp 12     MMA issue (one lane)
+//   in_full[2]   loader -> MMA      chunk c's I'/Q' slice is in shared memory                      (128 arrivals)
+//   m1_done[2]   MMA -> E1, loader  Hilbert-pair MMAs of chunk c retired: acc1[c&1] valid, slice c%6 free (commit)
+//   e1_done[2]   E1 -> MMA          acc1[c&1] drained and the D slice of chunk c written           (128 arrivals)
+//   m2_done[2]   MMA -> E2, E1      band-pass MMAs of chunk c retired: acc2 valid, D slice c%6 free     (commit)
+//   e2_done      E2 -> MMA          acc2 drained                                                    (128 arrivals)
+// The band-pass MMAs of chunk c-1 are issued after the Hilbert MMAs of chunk c, so epilogue 1 overlaps tensor work.
+__global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTables tb)
+{
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    TcSmem s{s_raw};
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, seg = blockIdx.y;
+    const int4 rows = tb.tile_rows[tile];                                 // x, y, z = Toeplitz images; w = AM flag
+    const bool am = rows.w != 0;
+#ifdef RDSP_TC_PROF
+    unsigned long long gt0_;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0_));
+    long long tq_ = clock64();
+#endif
+
+    // this CTA's share of the T blocks: outputs of blocks [t_store, t_end); a later segment first rebuilds its
+    // delay lines from the input itself (block t0-1 as I'/Q' history, block t0 = t_store-1 as warm-up for the D line)
+    const int t_store = tb.seg_bounds[seg], t_end = tb.seg_bounds[seg + 1];
+    const int t0 = seg ? t_store - 1 : 0;
+    const int nch = 4 * (t_end - t0);
+
+    // ---- prologue (all warps) ----
+    if (threadIdx.x < ROWS) {
+        const int row = threadIdx.x;
+        const int ch = tb.tile_ch[tile * ROWS + row];
+        RdspChanParams p{};
+        if (ch >= 0) p = a.par[ch];
+        s.row_ch()[row] = ch;
+        s.row_mi()[row] = ch >= 0 ? p.mult_i : 65536;
+        s.row_mq()[row] = ch >= 0 ? p.mult_q : 65536;
+        s.row_usb()[row] = (p.demod == 1 || p.demod == 3) ? 1 : 0;
+        if (row < 33) s.sqrt_guess()[row] = c_sqrt_guess[row];
+    }
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+        const int set = k == 0 ? rows.x : (k == 1 ? rows.y : rows.z);
+        const int4 *src = reinterpret_cast<const int4 *>(tb.toep + (size_t)set * TOEP_SET_B);
+        int4 *dst = reinterpret_cast<int4 *>(s.taps(k, 0));
+        for (int i = threadIdx.x; i < TOEP_SET_B / 16; i += NTHREADS) dst[i] = src[i];
+    }
+    const uint32_t bar0 = smem_u32(s.bars());
+    auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    if (threadIdx.x == 0) {
+        mbar_init(bar(B_IN_FULL), ROWS); mbar_init(bar(B_IN_FULL + 1), ROWS);
+        mbar_init(bar(B_M1_DONE), 1); mbar_init(bar(B_M1_DONE + 1), 1);
+        mbar_init(bar(B_E1_DONE), ROWS); mbar_init(bar(B_E1_DONE + 1), ROWS);
+        mbar_init(bar(B_M2_DONE), 1); mbar_init(bar(B_M2_DONE + 1), 1);
+        mbar_init(bar(B_E2_DONE), ROWS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();                                                       // row parameters visible
+    if (seg == 0) {
+        state_io<false>(s, a.hist, 0, warp, lane);                         // delay lines of the previous call -> slices 0..3
+    } else {
+        if (warp >= W_LD && warp < W_LD + 4) {
+#pragma unroll 1
+            for (int cq = 0; cq < 4; cq++) {
+                fetch_chunk(s, a, t0 - 1, cq, cq & 1, warp - W_LD, lane);
+                cp_async_wait<0>();
+                split_chunk(s, cq & 1, cq, warp - W_LD, lane);
+            }
+        } else if (threadIdx.x < ROWS) {
+            // demodulated line: zero history (its warm-up block only has to flush the band-pass through)
+            const int4 z = make_int4(0, 0, 0, 0);
+#pragma unroll 1
+            for (int kg = 0; kg < 8; kg++) {
+                const int off = (kg >> 1) * SLICE_B + (kg & 1) * (ROWS * 16) + threadIdx.x * 16;
+                *reinterpret_cast<int4 *>(s.ring(2, 0) + off) = z;
+                *reinterpret_cast<int4 *>(s.ring(2, 1) + off) = z;
+            }
+        }
+    }
+    if (warp == W_MMA) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(s.tmem_ptr())), "r"(TM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s.tmem_ptr();
+    TCQ(13);
+
+    if (warp >= W_LD && warp < W_LD + 4) {
+        // ===== loader =====
+        const int lw = warp - W_LD;
+        fetch_chunk(s, a, t0, 0, 0, lw, lane);
+        TCP_BEGIN;
+#pragma unroll 1
+        for (int c = 0; c < nch; c++) {
+            if (c + 1 < nch) {
+                fetch_chunk(s, a, t0 + ((c + 1) >> 2), (c + 1) & 3, (c + 1) & 1, lw, lane);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            // slice (c+4)%6 was the oldest slice of chunk c-2
+            if (c >= 2) mbar_wait(bar(B_M1_DONE + (c & 1)), ((c - 2) >> 1) & 1);
+            if (lw == 0) TCP(0);
+            split_chunk(s, c & 1, (c + 4) % SLICES, lw, lane);
+            fence_async_smem();
+            mbar_arrive(bar(B_IN_FULL + (c & 1)));
+            if (lw == 0) TCP(1);
+        }
+    } else if (warp == W_MMA) {
+        // ===== MMA issue =====
+        if (lane == 0) {
+            const uint32_t rI0 = smem_u32(s.ring(0, 0)), rI1 = smem_u32(s.ring(0, 1)), rQ0 = smem_u32(s.ring(1, 0)), rQ1 = smem_u32(s.ring(1, 1));
+            const uint32_t rD0 = smem_u32(s.ring(2, 0)), rD1 = smem_u32(s.ring(2, 1));
+            const uint32_t tA0 = smem_u32(s.taps(0, 0)), tA1 = smem_u32(s.taps(0, 1)), tB0 = smem_u32(s.taps(1, 0)), tB1 = smem_u32(s.taps(1, 1));
+            const uint32_t tM0 = smem_u32(s.taps(2, 0)), tM1 = smem_u32(s.taps(2, 1));
+            TCP_BEGIN;
+#pragma unroll 1
+            for (int c = 0; c <= nch; c++) {
+                if (c < nch) {
+                    mbar_wait(bar(B_IN_FULL + (c & 1)), (c >> 1) & 1);
+                    TCP(2);
+                    if (c >= 2) mbar_wait(bar(B_E1_DONE + (c & 1)), ((c - 2) >> 1) & 1);
+                    TCP(3);
+                    tc_fence_after();
+                    const uint32_t acc1 = tmem + (c & 1) * TM_ACC1B;
+                    issue_fir(rI0, rI1, tA0, tA1, acc1, c);
+                    issue_fir(rQ0, rQ1, tB0, tB1, acc1 + 3 * NOUT, c);
+                    mma_commit(bar(B_M1_DONE + (c & 1)));
+                    TCP(4);
+                }
+                if (c >= 1) {
+                    const int cc = c - 1;
+                    mbar_wait(bar(B_E1_DONE + (cc & 1)), (cc >> 1) & 1);
+                    TCP(5);
+                    if (cc >= 1) mbar_wait(bar(B_E2_DONE), (cc - 1) & 1);
+                    TCP(6);
+                    tc_fence_after();
+                    issue_fir(rD0, rD1, tM0, tM1, tmem + TM_ACC2P, cc);
+                    mma_commit(bar(B_M2_DONE + (cc & 1)));
+                    TCP(7);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp < W_E2) {
+        // ===== epilogue 1 =====
+        const int row = threadIdx.x;
+        const bool usb = s.row_usb()[row] != 0;
+        const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+        TCP_BEGIN;
+#pragma unroll 1
+        for (int c = 0; c < nch; c++) {
+            mbar_wait(bar(B_M1_DONE + (c & 1)), (c >> 1) & 1);
+            if (warp == 0) TCP(8);
+            // D slice (c+4)%6 was the oldest slice of the band-pass MMAs of chunk c-2
+            if (c >= 2) mbar_wait(bar(B_M2_DONE + (c & 1)), ((c - 2) >> 1) & 1);
+            if (warp == 0) TCP(9);
+            tc_fence_after();
+            if (am) epilogue1<true>(s, tmem_row + (c & 1) * TM_ACC1B, row, (c + 4) % SLICES, usb);
+            else epilogue1<false>(s, tmem_row + (c & 1) * TM_ACC1B, row, (c + 4) % SLICES, usb);
+            tc_fence_before();
+            fence_async_smem();
+            mbar_arrive(bar(B_E1_DONE + (c & 1)));
+            if (warp == 0) TCP(10);
+        }
+    } else {
+        // ===== epilogue 2 =====
+        const int row = threadIdx.x - W_E2 * 32;
+        const int ch = s.row_ch()[row];
+        const uint32_t tmem_row = tmem + ((uint32_t)((warp - W_E2) * 32) << 16) + TM_ACC2P;
+        TCP_BEGIN;
+#pragma unroll 1
+        for (int c = 0; c < nch; c++) {
+            const int t = t0 + (c >> 2);
+            mbar_wait(bar(B_M2_DONE + (c & 1)), (c >> 1) & 1);
+            if (warp == W_E2) TCP(11);
+            tc_fence_after();
+            epilogue2(a, tmem_row, t >= t_store ? ch : -1, t, c & 3);
+            tc_fence_before();
+            mbar_arrive(bar(B_E2_DONE));
+            if (warp == W_E2) TCP(12);
+        }
+    }
+
+    // ---- state for the next call: the last 128 samples of each line = slices nch .. nch+3 ----
+    tc_fence_before();
+    __syncthreads();
+    TCQ(14);
+    if (seg == (int)gridDim.y - 1) state_io<true>(s, a.hist_out, nch % SLICES, warp, lane);
+    if (warp == W_MMA) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TM_COLS) : "memory");
+    }
+    TCQ(15);
+#ifdef RDSP_TC_PROF
+    if (threadIdx.x == 0) {
+        unsigned long long gt1_;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1_));
+        const int id = blockIdx.y * gridDim.x + blockIdx.x;
+        if (id < 4096) { g_tc_cta[id][0] = gt0_; g_tc_cta[id][1] = gt1_; }
+    }
+#endif
+}
+
+}  // namespace
+
+// ---- host side: Toeplitz images and the tile table ---------------------------------------------------------------
+
+void front_tc_build_toeplitz(const int16_t *taps /*[15][stride]*/, int stride, uint8_t *out /*[15][TOEP_SET_B]*/)
+{
+    for (int r = 0; r < 15; r++)
+        for (int plane = 0; plane < 2; plane++)
+            for (int kg = 0; kg < 10; kg++)
+                for (int n = 0; n < NOUT; n++)
+                    for (int b = 0; b < 16; b++) {
+                        const int k = kg * 16 + b, tap = 128 + n - k;
+                        uint8_t v = 0;
+                        if (tap >= 0 && tap <= 128) {
+                            const uint16_t h = (uint16_t)taps[(size_t)r * stride + tap];
+                            v = plane ? (uint8_t)(h >> 8) : (uint8_t)(h & 0xFF);
+                        }
+                        out[(size_t)r * TOEP_SET_B + plane * TOEP_PLANE_B + (kg * NOUT + n) * 16 + b] = v;
+                    }
+}
+
+// Channels that share their three tap rows (by content) and the AM flag form a class; classes are cut into tiles of 128.
+int front_tc_build_tiles(const RdspChanParams *par, int C, const int16_t *taps, int stride,
+                         std::vector<int> &tile_ch, std::vector<int4> &tile_rows)
+{
+    int canon[15];
+    for (int r = 0; r < 15; r++) {
+        canon[r] = r;
+        for (int q = 0; q < r; q++)
+            if (!memcmp(taps + (size_t)q * stride, taps + (size_t)r * stride, RDSP_NTAPS * sizeof(int16_t))) { canon[r] = q; break; }
+    }
+    std::map<std::array<int, 4>, std::vector<int>> classes;
+    for (int ch = 0; ch < C; ch++) {
+        const RdspChanParams &p = par[ch];
+        const std::array<int, 4> key = {canon[p.demod], canon[RDSP_N_DEMOD + p.demod], canon[2 * RDSP_N_DEMOD + p.filter], p.demod == 4 ? 1 : 0};
+        classes[key].push_back(ch);
+    }
+    tile_ch.clear();
+    tile_rows.clear();
+    for (auto &kv : classes) {
+        const std::vector<int> &v = kv.second;
+        for (size_t i = 0; i < v.size(); i += ROWS) {
+            tile_rows.push_back(make_int4(kv.first[0], kv.first[1], kv.first[2], kv.first[3]));
+            for (int r = 0; r < ROWS; r++) tile_ch.push_back(i + r < v.size() ? v[i + r] : -1);
+        }
+    }
+    return (int)tile_rows.size();
+}
+
+#ifdef RDSP_TC_PROF
+void front_tc_read_prof(unsigned long long *out, bool reset)
+{
+    cudaMemcpyFromSymbol(out, g_tc_prof, sizeof(g_tc_prof));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z)); }
+}
+void front_tc_read_cta(unsigned long long *out) { cudaMemcpyFromSymbol(out, g_tc_cta, sizeof(g_tc_cta)); }
+#endif
+
+size_t front_tc_toeplitz_bytes() { return (size_t)15 * TOEP_SET_B; }
+
+// Segments: with fewer tiles than SMs the T blocks of a tile are cut into up to 8 time segments, one CTA each.  A later
+// segment pays about 1.25 blocks of warm-up (one block of loads, one of Hilbert MMAs), so the cut points balance
+// n_0 against n_s + 1.25.
+void front_tc_plan_segments(int n_tiles, int T, int n_sm, int *bounds, int *n_seg)
+{
+    int S = n_tiles > 0 ? n_sm / n_tiles : 1;
+    if (S > 8) S = 8;
+    while (S > 1) {
+        // segment s > 0 must start at block >= 2 and hold at least one block
+        const double target = (T + 1.25 * (S - 1)) / S;
+        int n0 = (int)(target + 0.5);
+        if (n0 < 2) n0 = 2;
+        if (T - n0 >= S - 1 && target - 1.25 >= 0.5) {
+            bounds[0] = 0; bounds[1] = n0;
+            int left = T - n0;
+            for (int k = 1; k < S; k++) {
+                int n = (left + (S - k) - 1) / (S - k);
+                bounds[k + 1] = bounds[k] + n;
+                left -= n;
+            }
+            break;
+        }
+        S--;
+    }
+    if (S <= 1) { S = 1; bounds[0] = 0; bounds[1] = T; }
+    *n_seg = S;
+}
+
+void launch_front_tc(const FrontArgs &a_in, const FrontTcTables &tb_in, cudaStream_t st)
+{
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(k_front_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B);
+    }
+    FrontArgs a = a_in;
+    FrontTcTables tb = tb_in;
+    if (!a.hist_out) a.hist_out = a.hist;
+    int S = 1;
+    front_tc_plan_segments(tb.n_tiles, a.T, n_sm, tb.seg_bounds, &S);
+    if (S > 1 && a.hist_out == a.hist) { S = 1; tb.seg_bounds[0] = 0; tb.seg_bounds[1] = a.T; }   // in-place state: one segment
+    k_front_tc<<<dim3(tb.n_tiles, S), NTHREADS, SMEM_B, st>>>(a, tb);
+}

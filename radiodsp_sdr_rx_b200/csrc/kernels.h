@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 #include "rdsp_common.cuh"
 
 // K0+K1+K2 -----------------------------------------------------------------------------------
@@ -11,11 +12,27 @@ struct FrontArgs {
     int16_t *out_stereo;        // [T][C][128][2]    or nullptr (front end is the last stage)
     float *dbg;                 // [T][C][128][2]    or nullptr
     int16_t *hist;              // [C][3][128] delay lines: I', Q', demodulated
+    int16_t *hist_out;          // k_front_tc only: where the new delay lines go (nullptr = in place; a second buffer lets
+                                // the blocks of a call be cut into concurrent time segments)
     const RdspChanParams *par;  // [C]
     const int32_t *taps;        // [15][132]: hilbert_i[5], hilbert_q[5], bandpass[5]
     int C, T;
 };
 void launch_front(const FrontArgs &a, cudaStream_t st);
+
+// K0+K1+K2 on tcgen05 (k_front_tc.cu): channels grouped into tiles of 128 that share their tap rows
+struct FrontTcTables {
+    const int *tile_ch;         // [n_tiles][128] channel of every MMA row, -1 = padding
+    const int4 *tile_rows;      // [n_tiles] Toeplitz image index of the I', Q' and band-pass taps; w = AM envelope
+    const uint8_t *toep;        // [15][2][5120] banded Toeplitz byte planes of the tap rows (front_tc_build_toeplitz)
+    int n_tiles;
+    int seg_bounds[9];          // filled by launch_front_tc: block range of every time segment
+};
+void launch_front_tc(const FrontArgs &a, const FrontTcTables &tb, cudaStream_t st);
+size_t front_tc_toeplitz_bytes();
+void front_tc_build_toeplitz(const int16_t *taps, int stride, uint8_t *out);
+int front_tc_build_tiles(const RdspChanParams *par, int C, const int16_t *taps, int stride,
+                         std::vector<int> &tile_ch, std::vector<int4> &tile_rows);
 
 // K3 / K6: normalised LMS ----------------------------------------------------------------------
 struct NlmsArgs {

@@ -76,7 +76,12 @@ struct rdsp_gpu {
     float agc_alpha_a = 0.f, agc_alpha_d[4] = {0.f, 0.f, 0.f, 0.f};
 
     // per-channel state
-    int16_t *d_fe_hist = nullptr;
+    int16_t *d_fe_hist = nullptr;              // delay lines of the front end; k_front_tc ping-pongs between the two
+    int16_t *d_fe_hist2 = nullptr;             // buffers so that a call's blocks can run as concurrent time segments
+    int fe_hist_cur = 0;
+    bool front_tc = true;                      // RDSP_FRONT_IMPL=cuda-core selects k_front.cu (cross-check)
+    uint8_t *d_toep = nullptr;                 // Toeplitz byte planes of the 15 tap rows
+    int *d_tile_ch = nullptr; int4 *d_tile_rows = nullptr; int n_tiles = 0, tile_cap = 0;
     float *d_nc_coeff = nullptr, *d_nc_prev = nullptr, *d_nc_energy = nullptr; uint8_t *d_nc_first = nullptr;
     float *d_dn_coeff = nullptr, *d_dn_prev = nullptr, *d_dn_energy = nullptr; uint8_t *d_dn_first = nullptr;
     float *d_agc_env = nullptr;
@@ -218,8 +223,14 @@ int sync_tables(rdsp_gpu *h)
         for (int r = 0; r < 15; r++)
             for (int k = 0; k < RDSP_FIR_TAPS; k++) t[(size_t)r * RDSP_TAPS_PAD + k] = h->taps[r][k];
         CK(cudaMemcpyAsync(h->d_taps, t.data(), t.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        std::vector<uint8_t> toep(front_tc_toeplitz_bytes());
+        if (h->d_toep) {
+            front_tc_build_toeplitz(&h->taps[0][0], RDSP_FIR_TAPS, toep.data());
+            CK(cudaMemcpyAsync(h->d_toep, toep.data(), toep.size(), cudaMemcpyHostToDevice, h->stream));
+        }
         CK(cudaStreamSynchronize(h->stream));
         h->taps_dirty = false;
+        h->par_dirty = true;                   // tiles group channels by tap-row content
     }
     if (!h->par_dirty) return RDSP_OK;
 
@@ -251,6 +262,21 @@ int sync_tables(rdsp_gpu *h)
     int rc = upload_masks(h);
     if (rc != RDSP_OK) return rc;
     CK(cudaMemcpyAsync(h->d_par, h->dpar.data(), (size_t)h->C * sizeof(RdspChanParams), cudaMemcpyHostToDevice, h->stream));
+    std::vector<int> tile_ch; std::vector<int4> tile_rows;
+    if (has(h, RDSP_STAGE_FRONTEND)) {
+        // k_front_tc: channels that share their tap rows, in tiles of 128 MMA rows
+        h->n_tiles = front_tc_build_tiles(h->dpar.data(), h->C, &h->taps[0][0], RDSP_FIR_TAPS, tile_ch, tile_rows);
+        if (h->n_tiles > h->tile_cap) {
+            if (h->d_tile_ch) cudaFree(h->d_tile_ch);
+            if (h->d_tile_rows) cudaFree(h->d_tile_rows);
+            h->d_tile_ch = nullptr; h->d_tile_rows = nullptr;
+            h->tile_cap = h->n_tiles + 32;
+            CK(cudaMalloc((void **)&h->d_tile_ch, (size_t)h->tile_cap * 128 * sizeof(int)));
+            CK(cudaMalloc((void **)&h->d_tile_rows, (size_t)h->tile_cap * sizeof(int4)));
+        }
+        CK(cudaMemcpyAsync(h->d_tile_ch, tile_ch.data(), tile_ch.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_tile_rows, tile_rows.data(), tile_rows.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    }
     h->n_notch = (int)l_notch.size();
     h->n_plain = (int)l_plain.size();
     h->n_dnr = (int)l_dnr.size();
@@ -290,7 +316,8 @@ void prof_collect(rdsp_gpu *h)
 
 void free_all(rdsp_gpu *h)
 {
-    void *ptrs[] = {h->d_par, h->d_list_notch, h->d_list_plain, h->d_list_dnr, h->d_taps, h->d_masks, h->d_tw, h->d_win256, h->d_win1024,
+    void *ptrs[] = {h->d_fe_hist2, h->d_toep, h->d_tile_ch, h->d_tile_rows,
+                    h->d_par, h->d_list_notch, h->d_list_plain, h->d_list_dnr, h->d_taps, h->d_masks, h->d_tw, h->d_win256, h->d_win1024,
                     h->d_tw256, h->d_fe_hist, h->d_nc_coeff, h->d_nc_prev, h->d_nc_energy, h->d_nc_first, h->d_dn_coeff,
                     h->d_dn_prev, h->d_dn_energy, h->d_dn_first, h->d_agc_env, h->d_conv_last, h->d_nfloor, h->d_bq_state,
                     h->d_spec_prev, h->d_spec_sum, h->d_spec_out, h->d_ring, h->d_spec1024_out, h->d_view, h->d_smeter,
@@ -435,6 +462,9 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     CKC(dalloc(&h->d_taps, (size_t)15 * RDSP_TAPS_PAD));
     if (sm & RDSP_STAGE_FRONTEND) {
         CKC(dalloc(&h->d_fe_hist, C * 3 * RDSP_BLK));
+        CKC(dalloc(&h->d_fe_hist2, C * 3 * RDSP_BLK));
+        CKC(dalloc(&h->d_toep, front_tc_toeplitz_bytes()));
+        if (const char *e = getenv("RDSP_FRONT_IMPL")) h->front_tc = !(e[0] == 'c' || e[0] == 'C');
         CKC(dalloc(&h->d_mid_a, T * C * RDSP_BLK));
     }
     if (sm & RDSP_STAGE_NOTCH) {
@@ -679,8 +709,25 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
             const bool last = !(notch || agc || ff);
             FrontArgs a{};
             a.iq = iq_k; a.out_mono = last ? nullptr : h->d_mid_a + o1; a.out_stereo = last ? audio_k : nullptr;
-            a.dbg = last ? dbg_k : nullptr; a.hist = h->d_fe_hist; a.par = h->d_par; a.taps = h->d_taps; a.C = C; a.T = Tc;
-            { Prof pr(h, KK_FRONT, sstream(ST_FRONT)); launch_front(a, sstream(ST_FRONT)); }
+            a.dbg = last ? dbg_k : nullptr; a.par = h->d_par; a.taps = h->d_taps; a.C = C; a.T = Tc;
+            if (h->front_tc) {
+                // the tensor-core front end takes the whole call in one launch (tiles x time segments fill the SMs);
+                // later chunks of the wavefront only see its completion event
+                if (k == 0) {
+                    a.T = T;
+                    a.hist = h->fe_hist_cur ? h->d_fe_hist2 : h->d_fe_hist;
+                    a.hist_out = h->fe_hist_cur ? h->d_fe_hist : h->d_fe_hist2;
+                    h->fe_hist_cur ^= 1;
+                    FrontTcTables tb{};
+                    tb.tile_ch = h->d_tile_ch; tb.tile_rows = h->d_tile_rows; tb.toep = h->d_toep; tb.n_tiles = h->n_tiles;
+                    Prof pr(h, KK_FRONT, sstream(ST_FRONT));
+                    launch_front_tc(a, tb, sstream(ST_FRONT));
+                }
+            } else {
+                a.hist = h->fe_hist_cur ? h->d_fe_hist2 : h->d_fe_hist;
+                Prof pr(h, KK_FRONT, sstream(ST_FRONT));
+                launch_front(a, sstream(ST_FRONT));
+            }
             CK(done(ST_FRONT, k));
             mono = h->d_mid_a + o1;
             audio_src = ST_FRONT;
