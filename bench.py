@@ -117,6 +117,8 @@ def ncu_traffic(kernel: str, workload: str, C_: int, T: int):
         return None
     k = json.load(open(files[-1]))["kernels"]
     name = {"k_nlms_notch": "k_nlms<8>", "k_nlms_dnr": "k_nlms<8>", "k_agc": "k_agc<0>"}.get(kernel, kernel)
+    if kernel == "k_front" and "k_front_tc" in k:
+        name = "k_front_tc"
     rows = k.get(name)
     if not rows:
         return None
@@ -398,7 +400,8 @@ def run_b200(args):
             roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": ncu_traffic(dom, wl, C_, T), "peak_source": peak_src, "alg_bytes_per_channel_block": ab.get(dom),
                     "ms_per_launch": per_launch_ms,
-                    "binding": "fp32/int32 pipe (sequential NLMS / 129-tap q15 FIRs), not HBM — see DESIGN.md",
+                    "binding": ("tcgen05 kind::i8 tensor pipe fed from shared memory (operand fetch bound), not HBM — see DESIGN.md"
+                                if dom == "k_front" else "fp32/int32 pipe and recurrence latency (sequential NLMS / AGC, q15 FFTs), not HBM — see DESIGN.md"),
                     "pipe": {"achieved_Tlaneops": pipe_ach / 1e12, "peak_Tlaneops": pipe_peak / 1e12, "frac": pipe_ach / pipe_peak}}
         step_bytes = ab["_step"] * C_ * T
         line = {
@@ -449,7 +452,7 @@ def main():
     ap.add_argument("--pipeline-chunks", type=int, default=0, help="wavefront chunks per call (0 = library default)")
     ap.add_argument("--cpu-channels-per-thread", type=int, default=32)
     ap.add_argument("--cpu-blocks", type=int, default=64)
-    ap.add_argument("--cpu-reps", type=int, default=12)
+    ap.add_argument("--cpu-reps", type=int, default=96, help="repetitions of the CPU sample (default: about 12 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -52,6 +52,20 @@ QHD void first(int2 *src, const int2 *tw, int N, int mod, int i)
     *p3 = cmul(tw[3 * ic], make_int2(Sx - Uy, Sy + Ux));      // QASX(S, T): xa - xc + j (xb - xd)
 }
 
+// first stage of a REAL input frame (imaginary parts are zero: AudioAnalyzeFFT1024 feeds (sample, 0) pairs): the same
+// arithmetic with the zero terms dropped
+QHD void first_real(int2 *src, const int2 *tw, int N, int mod, int i)
+{
+    const int n2 = N >> 2, ic = i * mod;
+    int2 *p0 = src + P(i), *p1 = src + P(i + n2), *p2 = src + P(i + 2 * n2), *p3 = src + P(i + 3 * n2);
+    const int xa = p0->x >> 2, xb = p1->x >> 2, xc = p2->x >> 2, xd = p3->x >> 2;
+    const int Rx = xa + xc, Sx = xa - xc, Tx = xb + xd, Ux = xb - xd;
+    *p0 = make_int2((Rx + Tx) >> 1, 0);
+    *p1 = cmul(tw[2 * ic], make_int2(Rx - Tx, 0));
+    *p2 = cmul(tw[ic], make_int2(Sx, -Ux));
+    *p3 = cmul(tw[3 * ic], make_int2(Sx, Ux));
+}
+
 // middle stage with group span n1 and quarter span n2 = n1/4, twiddle step mod; butterfly b in [0, N/4)
 QHD void middle(int2 *src, const int2 *tw, int n1, int n2, int mod, int b)
 {

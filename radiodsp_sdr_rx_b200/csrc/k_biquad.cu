@@ -42,9 +42,9 @@ __global__ void __launch_bounds__(32) k_biquad(BiquadArgs a)
 
     const int lane = threadIdx.x;
     const int row = (lane >> 1) & (R - 1), iq = lane & 1;   // stream = (channel row, I or Q); lanes >= 2R mirror
-    const int ch0 = blockIdx.x * R;
+    const int ch0 = a.ch0 + blockIdx.x * R, ch_end = a.ch0 + a.n;
     const int myc = ch0 + row;
-    const bool walker = lane < 2 * R && myc < a.C;
+    const bool walker = lane < 2 * R && myc < ch_end;
 
     uint32_t bprev = 0, aprev = 0;                          // two previous inputs / outputs: lo = older, hi = newer
     int32_t sum = 0;
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(32) k_biquad(BiquadArgs a)
     auto issue_load = [&](int t, int buf) {
 #pragma unroll
         for (int r = 0; r < R; r++)
-            if (ch0 + r < a.C)
+            if (ch0 + r < ch_end)
                 cp_async16(&s_in[buf][r][((lane + r) & 31) * 16],
                            reinterpret_cast<const unsigned char *>(a.iq + ((size_t)t * a.C + ch0 + r) * 2 * RDSP_BLK) + lane * 16);
         cp_async_commit();
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(32) k_biquad(BiquadArgs a)
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < R; r++)
-            if (ch0 + r < a.C)
+            if (ch0 + r < ch_end)
                 *reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(a.out + ((size_t)t * a.C + ch0 + r) * 2 * RDSP_BLK) + lane * 16) =
                     *reinterpret_cast<const int4 *>(&s_out[r][((lane + r) & 31) * 16]);
         __syncwarp();
@@ -126,5 +126,5 @@ __global__ void __launch_bounds__(32) k_biquad(BiquadArgs a)
 
 void launch_biquad(const BiquadArgs &a, cudaStream_t st)
 {
-    k_biquad<<<(a.C + R - 1) / R, 32, 0, st>>>(a);
+    if (a.n > 0) k_biquad<<<(a.n + R - 1) / R, 32, 0, st>>>(a);
 }

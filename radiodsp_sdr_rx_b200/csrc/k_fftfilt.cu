@@ -30,8 +30,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_fftfilt(FftFiltArgs a)
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ch = blockIdx.x * WARPS + warp;
-    if (ch >= a.C) return;
+    const int lc = blockIdx.x * WARPS + warp;
+    if (lc >= a.n) return;
+    const int ch = a.ch0 + lc;
     float2 *buf = s_buf[warp];
 
     const RdspChanParams p = a.par[ch];
@@ -146,5 +147,5 @@ __global__ void __launch_bounds__(WARPS * 32) k_fftfilt(FftFiltArgs a)
 
 void launch_fftfilt(const FftFiltArgs &a, cudaStream_t st)
 {
-    k_fftfilt<<<(a.C + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(a);
+    if (a.n > 0) k_fftfilt<<<(a.n + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(a);
 }

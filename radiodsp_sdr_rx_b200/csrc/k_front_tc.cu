@@ -134,33 +134,6 @@ __device__ __forceinline__ int32_t mix_gain_tc(int32_t x, int32_t mh, int32_t ml
     return sat16(mh * x + ((ml * x) >> 16));
 }
 
-// sqrt_uint32_approx (two Newton steps from a table seed, rdsp_common.cuh) with its two divisions done by a float
-// estimate and an exact fix-up: the quotients stay below 2^18, where the estimate is off by at most one.  The
-// int <-> float conversions use the 2^23 magic number (FADD / LOP, full rate) instead of I2F / F2I (16 lanes/clk/SM).
-__device__ __forceinline__ float small_u2f(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }   // v < 2^23
-__device__ __forceinline__ uint32_t udiv_small_q(uint32_t n, float n_f, uint32_t d)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(small_u2f(d)));
-    uint32_t q = __float_as_uint(n_f * r + 8388608.0f) & 0x7FFFFFu;
-    int32_t rem = (int32_t)(n - q * d);
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const bool lo = rem < 0, hi = rem >= (int32_t)d;
-        q += hi ? 1u : (lo ? 0xFFFFFFFFu : 0u);
-        rem += hi ? -(int32_t)d : (lo ? (int32_t)d : 0);
-    }
-    return q;
-}
-__device__ __forceinline__ uint32_t sqrt_u32_approx_fast(uint32_t in, const uint16_t *guess /* shared copy of c_sqrt_guess */)
-{
-    const float in_f = fmaf(small_u2f(in >> 16), 65536.0f, small_u2f(in & 0xFFFFu));
-    uint32_t n = guess[__clz((int)in)];                                 // branch free: in == 0 falls out at the end
-    n = (udiv_small_q(in, in_f, n) + n) >> 1;
-    n = (udiv_small_q(in, in_f, n) + n) >> 1;
-    return in == 0u ? 0u : n;
-}
-
 __device__ __forceinline__ int32_t recombine(uint32_t ll, uint32_t mid, uint32_t hh)
 {
     const uint32_t acc = ll + (mid << 8) + (hh << 16);                   // wraps like the CMSIS fast-FIR accumulator

@@ -36,6 +36,10 @@ namespace {
 constexpr int NWARPS = 2;
 constexpr int XS = 260;                      // floats per row: 16-byte aligned, rows 4 banks apart
 constexpr int D = 4;                         // samples per group
+#ifndef RDSP_NLMS_ANCHOR
+#define RDSP_NLMS_ANCHOR 2
+#endif
+constexpr int ANCHOR = RDSP_NLMS_ANCHOR;     // groups between exact re-anchorings of the lag sums (S/4 is a multiple)
 constexpr float LMS_EPS = 0.000000119209289f;
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
@@ -109,29 +113,32 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
         float4 xo_p = ld4(xb + 28);                  // x[-100..-97]
         const bool same_block_ref = first && t == 0;
 
+        float s1 = 0.f, s2 = 0.f, s3 = 0.f;
         for (int n0 = 0; n0 < RDSP_BLK; n0 += S) {
 #pragma unroll
             for (int gq = 0; gq < S / 4; gq++) {
                 const int n = n0 + 4 * gq;
                 if (n < RDSP_BLK) {
                     const int sb = 4 * gq;                                  // slot of u[n] (n0 is a multiple of S)
-                    // ---- lag sums s_l(n-1) = x[n-1-l]' x[n-1], l = 1..3, anchored EXACTLY on the window at every group
-                    // (the window still holds m = n-W-4 .. n-1).  A running sum carried across groups would lose all
-                    // its digits when the signal drops by orders of magnitude inside the window, exactly where
-                    // 1/(energy + eps) amplifies every error.
-                    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    // ---- lag sums s_l(n-1) = x[n-1-l]' x[n-1], l = 1..3, anchored EXACTLY on the window every ANCHOR
+                    // groups (the window still holds m = n-W-4 .. n-1) and slid over the samples in between.  A running
+                    // sum carried for long would lose all its digits when the signal drops by orders of magnitude
+                    // inside the window, exactly where 1/(energy + eps) amplifies every error.
+                    if (gq % ANCHOR == 0) {
+                        s1 = 0.f; s2 = 0.f; s3 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < W; i++) {
-                        const float uk = u[(sb - 1 - i + 2 * S) % S];
-                        s1 = fmaf(u[(sb - 2 - i + 2 * S) % S], uk, s1);
-                        s2 = fmaf(u[(sb - 3 - i + 2 * S) % S], uk, s2);
-                        s3 = fmaf(u[(sb - 4 - i + 2 * S) % S], uk, s3);
-                    }
+                        for (int i = 0; i < W; i++) {
+                            const float uk = u[(sb - 1 - i + 2 * S) % S];
+                            s1 = fmaf(u[(sb - 2 - i + 2 * S) % S], uk, s1);
+                            s2 = fmaf(u[(sb - 3 - i + 2 * S) % S], uk, s2);
+                            s3 = fmaf(u[(sb - 4 - i + 2 * S) % S], uk, s3);
+                        }
 #pragma unroll
-                    for (int o = G / 2; o > 0; o >>= 1) {
-                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                        s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+                        for (int o = G / 2; o > 0; o >>= 1) {
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                            s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+                        }
                     }
                     // ---- loads
                     const float4 un = ld4(xb + 128 + n - W * g);
@@ -174,7 +181,15 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
                     for (int j = 0; j < 4; j++) {
                         energy = __fsub_rn(energy, __fmul_rn(xo[j], xo[j]));
                         energy = __fadd_rn(energy, __fmul_rn(xn[j], xn[j]));
-                        qn[j] = mu * __frcp_rn(fmaxf(energy + LMS_EPS, LMS_EPS));   // energy is a running difference: never divide by <= 0
+                        // energy is a running difference: never divide by <= 0.  MUFU.RCP + one Newton step (error below
+                        // 1 ulp; the reference divides, which this path never reproduced bit for bit anyway)
+                        {
+                            const float den = fmaxf(energy + LMS_EPS, LMS_EPS);
+                            float r;
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+                            r = fmaf(r, fmaf(-den, r, 1.0f), r);
+                            qn[j] = mu * r;
+                        }
                         // s_l(b) = s_l(b-1) + x[b-l] x[b] - x[b-l-96] x[b-96],  b = n + j
                         s1 = fmaf(xr[4 + j - 1], xn[j], s1); s1 = fmaf(-xq[4 + j - 1], xo[j], s1);
                         s2 = fmaf(xr[4 + j - 2], xn[j], s2); s2 = fmaf(-xq[4 + j - 2], xo[j], s2);
@@ -274,8 +289,11 @@ void launch_nlms(const NlmsArgs &a, cudaStream_t st)
     if (a.n_list <= 0) return;
     static const bool direct = [] { const char *e = getenv("RDSP_NLMS_IMPL"); return e && e[0] == 'd'; }();
     if (direct) { launch_nlms_direct(a, st); return; }
-    // 4 lanes per channel minimise instructions (the reductions are two shuffle stages); below ~4k channels 8 lanes
-    // keep every SM sub-partition supplied with a warp
+    // 4 lanes per channel minimise instructions (the reductions are two shuffle stages, 30 % fewer instructions per
+    // sample); 8 lanes halve the dependent chain of a group.  Measured (8 blocks per launch, us, G = 4 / G = 8):
+    // 2048 channels 170 / 100, 6554 channels 167 / 165, 8192 channels 165 / 211, 16384 channels 324 / 336.
+    // The two forms sum in different orders, so the switch sits above the per-GPU channel counts of the configs:
+    // a handle and its channel-range shards then run the same form and agree bit for bit (tests/test_gpu_parity.py).
     int G = a.n_list >= 12288 ? 4 : 8;
     if (const char *env = getenv("RDSP_NLMS_LANES")) G = atoi(env) == 4 ? 4 : 8;       // experiments only
     const int cpb = NWARPS * (32 / G);

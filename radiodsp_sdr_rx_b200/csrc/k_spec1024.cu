@@ -21,9 +21,11 @@ constexpr int NT = 64;
 __global__ void __launch_bounds__(NT) k_spec1024(Spec1024Args a)
 {
     __shared__ __align__(16) int2 s_fft[1024 + 256];              // unpacked (re, im), skewed (fft_q15.cuh)
+    __shared__ uint16_t s_guess[34];
+    if (threadIdx.x < 33) s_guess[threadIdx.x] = c_sqrt_guess[threadIdx.x];
 
     const int tid = threadIdx.x;
-    const int ch = blockIdx.x;
+    const int ch = a.ch0 + blockIdx.x;
     int16_t *ring = a.ring + (size_t)ch * 8 * RDSP_BLK;
     uint2 *gring = reinterpret_cast<uint2 *>(ring);               // 32 uint2 (4 samples each) per slot
 
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(NT) k_spec1024(Spec1024Args a)
         }
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < 4; r++) q15fft::first(s_fft, a.tw, 1024, 4, tid + NT * r);
+        for (int r = 0; r < 4; r++) q15fft::first_real(s_fft, a.tw, 1024, 4, tid + NT * r);
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < 4; r++) q15fft::middle(s_fft, a.tw, 256, 64, 16, tid + NT * r);
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(NT) k_spec1024(Spec1024Args a)
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int2 w = s_fft[q15fft::P(2 * (tid + NT * j))];
-            v[j] = (uint16_t)sqrt_u32_approx((uint32_t)(w.x * w.x) + (uint32_t)(w.y * w.y));
+            v[j] = (uint16_t)sqrt_u32_approx_fast((uint32_t)(w.x * w.x) + (uint32_t)(w.y * w.y), s_guess);
         }
         __syncthreads();
         uint16_t *s_o = reinterpret_cast<uint16_t *>(s_fft);
@@ -85,5 +87,5 @@ __global__ void __launch_bounds__(NT) k_spec1024(Spec1024Args a)
 
 void launch_spec1024(const Spec1024Args &a, cudaStream_t st)
 {
-    k_spec1024<<<a.C, NT, 0, st>>>(a);
+    if (a.n > 0) k_spec1024<<<a.n, NT, 0, st>>>(a);
 }

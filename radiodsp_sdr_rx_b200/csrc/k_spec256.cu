@@ -27,8 +27,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec256(Spec256Args a)
     for (int i = threadIdx.x; i < 192; i += WARPS * 32) s_tw[i] = a.tw[16 * i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ch = blockIdx.x * WARPS + warp;
-    if (ch >= a.C) return;
+    const int lc = blockIdx.x * WARPS + warp;
+    if (lc >= a.n) return;
+    const int ch = a.ch0 + lc;
 
     // register j holds bin bitrev8(lane + 32 j): the FFT leaves bin i at element bitrev(i), so walking the ELEMENTS
     // lane + 32 j keeps the shared-memory reads of the |.|^2 loop contiguous (the sums are only loaded / stored once per call)
@@ -105,5 +106,5 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec256(Spec256Args a)
 
 void launch_spec256(const Spec256Args &a, cudaStream_t st)
 {
-    k_spec256<<<(a.C + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(a);
+    if (a.n > 0) k_spec256<<<(a.n + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(a);
 }

@@ -55,8 +55,9 @@ void launch_nlms(const NlmsArgs &a, cudaStream_t st);
 
 // K4: AGC + output gain -------------------------------------------------------------------------
 struct AgcArgs {
-    const int *list;            // channels to run (nullptr: 0..n_list-1)
+    const int *list;            // channels to run (nullptr: ch0 .. ch0 + n_list - 1)
     int n_list;
+    int ch0;
     const int16_t *in_q15;      // [T][C][128] q15 rows (channels that bypass the notch) ...
     const float *in_f32;        // ... or [T][C][128] f32 rows (channels whose notch ran); exactly one is set
     int16_t *out_mono;          // [T][C][128]    or nullptr
@@ -83,6 +84,7 @@ struct FftFiltArgs {
     const float2 *tw256;        // [256] (cos, sin)(2*pi*k/256)
     const RdspChanParams *par;
     int C, T;
+    int ch0, n;                 // channel range of this launch: [ch0, ch0 + n)
     int nr_stage;               // RDSP_STAGE_NR present
 };
 void launch_fftfilt(const FftFiltArgs &a, cudaStream_t st);
@@ -93,6 +95,7 @@ struct BiquadArgs {
     int16_t *out;               // [T][C][128][2] high-passed IQ
     int32_t *state;             // [C][2][4]: bprev, aprev, sum, pad  for I and Q
     int C, T;
+    int ch0, n;                 // channel range of this launch: [ch0, ch0 + n)
     int32_t b0, b1, b2, a1, a2; // Q30, feedback already negated
 };
 void launch_biquad(const BiquadArgs &a, cudaStream_t st);
@@ -104,6 +107,7 @@ struct Spec256Args {
     uint32_t *sum;              // [C][256]
     uint16_t *output;           // [C][256]
     int C, T;
+    int ch0, n;                 // channel range of this launch: [ch0, ch0 + n)
     int have_prev;              // 0 on the very first tick
     int count;                  // averaging counter at the first tick of this call
     int naverage;
@@ -120,6 +124,7 @@ struct Spec1024Args {
     int16_t *ring;              // [C][8][128] last blocks of L, slot = tick mod 8
     uint16_t *output;           // [C][512]
     int C, T;
+    int ch0, n;                 // channel range of this launch: [ch0, ch0 + n)
     unsigned long long tick0;   // global tick index of block 0 of this call
     int any_fft;                // some tick of this call completes a 1024-sample frame
     const int2 *tw;             // [3072]

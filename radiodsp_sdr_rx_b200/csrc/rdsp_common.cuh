@@ -71,6 +71,35 @@ __device__ __forceinline__ uint32_t sqrt_u32_approx(uint32_t in)
     return n;
 }
 
+// The same function with its two divisions done by a float estimate and an exact fix-up (the quotients stay below
+// 2^18, where the estimate is off by at most one; two correction rounds are applied).  The int <-> float
+// conversions use the 2^23 magic number (FADD / LOP, full rate) instead of I2F / F2I (16 lanes/clk/SM), and the seed
+// table is read through `guess` (a shared-memory copy of c_sqrt_guess: lanes index it divergently, which constant
+// memory would serialise).  Bit-identical to sqrt_u32_approx for every input (tools/front_tc_check, test_gpu_parity).
+__device__ __forceinline__ float rdsp_small_u2f(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }   // v < 2^23
+__device__ __forceinline__ uint32_t rdsp_udiv_small_q(uint32_t n, float n_f, uint32_t d)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(rdsp_small_u2f(d)));
+    uint32_t q = __float_as_uint(n_f * r + 8388608.0f) & 0x7FFFFFu;
+    int32_t rem = (int32_t)(n - q * d);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const bool lo = rem < 0, hi = rem >= (int32_t)d;
+        q += hi ? 1u : (lo ? 0xFFFFFFFFu : 0u);
+        rem += hi ? -(int32_t)d : (lo ? (int32_t)d : 0);
+    }
+    return q;
+}
+__device__ __forceinline__ uint32_t sqrt_u32_approx_fast(uint32_t in, const uint16_t *guess)
+{
+    const float in_f = fmaf(rdsp_small_u2f(in >> 16), 65536.0f, rdsp_small_u2f(in & 0xFFFFu));
+    uint32_t n = guess[__clz((int)in)];                                 // branch free: in == 0 falls out at the end
+    n = (rdsp_udiv_small_q(in, in_f, n) + n) >> 1;
+    n = (rdsp_udiv_small_q(in, in_f, n) + n) >> 1;
+    return in == 0u ? 0u : n;
+}
+
 // arm_float_to_q15: truncate toward zero, saturate
 __device__ __forceinline__ int32_t f32_to_q15(float v)
 {

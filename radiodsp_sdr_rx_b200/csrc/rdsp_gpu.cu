@@ -12,6 +12,7 @@
 #include "host_design.h"
 #include "kernels.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -31,8 +32,8 @@ const char *const kKernelNames[KK_COUNT] = {"k_front", "k_nlms_notch", "k_agc", 
 
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
 
-constexpr int kStages = 8;
-constexpr int kMaxChunks = 8;
+constexpr int kMaxGroups = 8;
+constexpr int kStreams = 3 * kMaxGroups + 1;   // per channel group: main chain, spectrum branch, side branch; + the front end
 
 }  // namespace
 
@@ -41,9 +42,9 @@ struct rdsp_gpu {
     int C = 0, maxT = 1;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     // one stream per stage of the graph + one event per (stage, chunk): the wavefront of process_blocks
-    cudaStream_t stage_stream[kStages] = {nullptr};
-    cudaEvent_t ev_stage[kStages][kMaxChunks] = {{nullptr}};
-    cudaEvent_t ev_fork = nullptr;
+    cudaStream_t stage_stream[kStreams] = {nullptr};
+    cudaEvent_t ev_group[kMaxGroups][3] = {{nullptr}};
+    cudaEvent_t ev_fork = nullptr, ev_front = nullptr;
     // IO_HOST: copies run on their own streams over double-buffered staging, so that the H2D of call n+1 and the
     // D2H of call n-1 overlap the kernels of call n (async handles)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -60,6 +61,7 @@ struct rdsp_gpu {
     RdspChanParams *d_par = nullptr;
     int *d_list_notch = nullptr, *d_list_plain = nullptr, *d_list_dnr = nullptr;
     int n_notch = 0, n_plain = 0, n_dnr = 0;
+    std::vector<int> l_notch, l_plain, l_dnr;   // host copies (ascending): channel groups launch sub-ranges
 
     // coefficient tables
     int16_t taps[15][RDSP_FIR_TAPS];
@@ -104,6 +106,7 @@ struct rdsp_gpu {
     // instrumentation
     uint64_t launches = 0;
     bool profiling = false;
+    bool timeline = false;                     // RDSP_TIMELINE=1: event-bracket every launch IN the wavefront and print when each ran
     std::vector<ProfRec> prof_pending;
     double prof_ms[KK_COUNT] = {0};
     uint64_t prof_n[KK_COUNT] = {0};
@@ -284,13 +287,14 @@ int sync_tables(rdsp_gpu *h)
     if (h->n_notch) CK(cudaMemcpyAsync(h->d_list_notch, l_notch.data(), l_notch.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (h->n_dnr) CK(cudaMemcpyAsync(h->d_list_dnr, l_dnr.data(), l_dnr.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));      // the host staging vectors go out of scope
+    h->l_notch.swap(l_notch); h->l_plain.swap(l_plain); h->l_dnr.swap(l_dnr);
     h->par_dirty = false;
     return RDSP_OK;
 }
 
 struct Prof {
     rdsp_gpu *h; int kind; ProfRec r; bool on; cudaStream_t st;
-    Prof(rdsp_gpu *h_, int kind_, cudaStream_t st_ = nullptr) : h(h_), kind(kind_), on(h_->profiling), st(st_ ? st_ : h_->stream) {
+    Prof(rdsp_gpu *h_, int kind_, cudaStream_t st_ = nullptr) : h(h_), kind(kind_), on(h_->profiling || h_->timeline), st(st_ ? st_ : h_->stream) {
         if (on) {
             r.kind = kind;
             cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
@@ -305,6 +309,18 @@ struct Prof {
 
 void prof_collect(rdsp_gpu *h)
 {
+    if (h->timeline && !h->prof_pending.empty()) {
+        // development aid: start / end of every launch of the last call relative to its fork event, in launch order
+        cudaStreamSynchronize(h->stream);
+        fprintf(stderr, "[rdsp timeline] kernel            start us   end us\n");
+        for (auto &r : h->prof_pending) {
+            float a = 0.f, b = 0.f;
+            cudaEventSynchronize(r.e1);
+            cudaEventElapsedTime(&a, h->ev_fork, r.e0);
+            cudaEventElapsedTime(&b, h->ev_fork, r.e1);
+            fprintf(stderr, "[rdsp timeline] %-14s %10.1f %8.1f\n", kKernelNames[r.kind], a * 1e3f, b * 1e3f);
+        }
+    }
     for (auto &r : h->prof_pending) {
         float ms = 0.f;
         cudaEventSynchronize(r.e1);
@@ -334,8 +350,10 @@ void free_all(rdsp_gpu *h)
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    for (int s = 0; s < kStages; s++) {
-        for (int k = 0; k < kMaxChunks; k++) if (h->ev_stage[s][k]) cudaEventDestroy(h->ev_stage[s][k]);
+    for (int g = 0; g < kMaxGroups; g++)
+        for (int k = 0; k < 3; k++) if (h->ev_group[g][k]) cudaEventDestroy(h->ev_group[g][k]);
+    if (h->ev_front) cudaEventDestroy(h->ev_front);
+    for (int s = 0; s < kStreams; s++) {
         if (h->stage_stream[s]) cudaStreamDestroy(h->stage_stream[s]);
     }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -400,7 +418,7 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     if ((sm & RDSP_STAGE_SPEC1024) && !(sm & (RDSP_STAGE_FRONTEND | RDSP_STAGE_FFTFILT))) { g_create_error = "SPEC1024 needs an audio path"; return RDSP_ERR_STATE; }
     if (cfg->spec256_naverage == 0 || cfg->spec256_naverage > 255) { g_create_error = "spec256_naverage must be 1..255"; return RDSP_ERR_RANGE; }
     if (cfg->io_location > RDSP_IO_HOST) { g_create_error = "io_location invalid"; return RDSP_ERR_RANGE; }
-    if (cfg->pipeline_chunks > (uint32_t)kMaxChunks) { g_create_error = "pipeline_chunks must be 0 (auto) .. 8"; return RDSP_ERR_RANGE; }
+    if (cfg->pipeline_chunks > (uint32_t)kMaxGroups) { g_create_error = "pipeline_chunks must be 0 (auto) .. 8"; return RDSP_ERR_RANGE; }
     if (!(cfg->agc_target > 0.f) || !(cfg->agc_max_gain > 0.f) || !(cfg->agc_attack_ms > 0.f)) { g_create_error = "AGC constants invalid"; return RDSP_ERR_RANGE; }
 
     int ndev = 0;
@@ -434,10 +452,12 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     CKC(cudaSetDevice(cfg->device));
     CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
-    CKC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    for (int s = 0; s < kStages; s++) {
+    CKC(cudaEventCreate(&h->ev_fork));                            // timing enabled: origin of the RDSP_TIMELINE printout
+    CKC(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
+    for (int g = 0; g < kMaxGroups; g++)
+        for (int k = 0; k < 3; k++) CKC(cudaEventCreateWithFlags(&h->ev_group[g][k], cudaEventDisableTiming));
+    for (int s = 0; s < kStreams; s++) {
         CKC(cudaStreamCreateWithFlags(&h->stage_stream[s], cudaStreamNonBlocking));
-        for (int k = 0; k < kMaxChunks; k++) CKC(cudaEventCreateWithFlags(&h->ev_stage[s][k], cudaEventDisableTiming));
     }
 
     // host-side tables
@@ -465,6 +485,7 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
         CKC(dalloc(&h->d_fe_hist2, C * 3 * RDSP_BLK));
         CKC(dalloc(&h->d_toep, front_tc_toeplitz_bytes()));
         if (const char *e = getenv("RDSP_FRONT_IMPL")) h->front_tc = !(e[0] == 'c' || e[0] == 'C');
+        if (const char *e = getenv("RDSP_TIMELINE")) h->timeline = e[0] == '1';
         CKC(dalloc(&h->d_mid_a, T * C * RDSP_BLK));
     }
     if (sm & RDSP_STAGE_NOTCH) {
@@ -647,172 +668,169 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
         audio = h->d_out_stage2[hb];
     }
 
-    // ---- wavefront over chunks of blocks ---------------------------------------------------------------
-    // Every stage of the graph has its own stream; the T blocks of the call are cut into chunks and stage s of
-    // chunk k waits (CUDA events) for its producers on chunk k, while stream order alone keeps a stage's own state
-    // in sequence.  So the front end of chunk k+1 runs beside the NLMS of chunk k and the spectrum path beside
-    // both: the issue-bound kernels fill the slots the latency-bound recurrences leave empty.  While per-kernel
-    // profiling is on, everything runs as one chunk on one stream so that each kernel's time is its own.
-    enum { ST_FRONT = 0, ST_NOTCH, ST_AGC, ST_FFT, ST_DNR, ST_S1024, ST_BIQ, ST_S256 };
+    // ---- channel groups -----------------------------------------------------------------------------------
+    // Channels are independent, and every kernel after the front end is bound by the latency of a per-channel
+    // recurrence rather than by throughput.  The call is therefore cut ACROSS channels: the front end takes all
+    // channels in one launch (tiles x time segments fill the SMs), then G channel groups walk the rest of the graph
+    // on streams of their own — notch -> AGC -> FFT filter -> DNR -> audio spectrum on one, high-pass -> IQ spectrum
+    // on another — with no dependency between groups, so the hardware overlaps G latency-bound chains.  Every launch
+    // still covers all T blocks of the call: state makes one round trip and the launch latency is paid once.
+    // (The first version cut the call along TIME instead; its timeline, tools/diag_timeline.py, showed every stage
+    // paying its launch + state latency per chunk and the DNR stage of 4 chunks taking twice its one-launch time.)
+    // While per-kernel profiling is on, everything runs as one group on one stream so that each kernel's time is its own.
     const bool piped = !h->profiling;
-    int nchunks = 1;
+    int G = 1;
     if (piped) {
-        nchunks = h->cfg.pipeline_chunks ? (int)h->cfg.pipeline_chunks : 4;
-        if (nchunks > T) nchunks = T;
-        if (nchunks > kMaxChunks) nchunks = kMaxChunks;
+        // measured (cfg5, 8192 channels, T = 8): 1 group 0.71 ms, 2 groups 0.90, 4 groups 0.83, 8 groups 1.11 — small
+        // concurrent launches of the same kernel slow each other more than they overlap, so the default is ONE group
+        // (main chain + spectrum branch + the AGC of the channels that bypass the notch on three streams)
+        G = h->cfg.pipeline_chunks ? (int)h->cfg.pipeline_chunks : 1;
+        if (G > kMaxGroups) G = kMaxGroups;
+        while (G > 1 && C / G < 256) G--;
         CK(cudaEventRecord(h->ev_fork, st));                             // the input (and earlier calls) are in place
-        for (int s = 0; s < kStages; s++) CK(cudaStreamWaitEvent(h->stage_stream[s], h->ev_fork, 0));
     }
-    auto sstream = [&](int stage) { return piped ? h->stage_stream[stage] : st; };
-    auto wait_for = [&](int stage, int dep, int chunk) -> cudaError_t {
-        return piped ? cudaStreamWaitEvent(h->stage_stream[stage], h->ev_stage[dep][chunk], 0) : cudaSuccess;
-    };
-    auto done = [&](int stage, int chunk) -> cudaError_t {
-        return piped ? cudaEventRecord(h->ev_stage[stage][chunk], h->stage_stream[stage]) : cudaSuccess;
-    };
+    cudaStream_t s_front = piped ? h->stage_stream[3 * kMaxGroups] : st;
     const int naverage = (int)h->cfg.spec256_naverage;
     int lgn = 0; while ((1u << lgn) < h->cfg.spec256_naverage) lgn++;
+    float *dbg = h->d_dbg;
 
-    for (int k = 0; k < nchunks; k++) {
-        const int t0 = (int)((long long)T * k / nchunks), t1 = (int)((long long)T * (k + 1) / nchunks), Tc = t1 - t0;
-        const size_t o2 = (size_t)t0 * C * 2 * RDSP_BLK, o1 = (size_t)t0 * C * RDSP_BLK;     // stereo / mono row offsets
-        const int16_t *iq_k = iq + o2;
-        int16_t *audio_k = audio ? audio + o2 : nullptr;
-        float *dbg_k = h->d_dbg ? h->d_dbg + o2 : nullptr;
+    // ---- K0+K1+K2, all channels
+    bool front_last = false;
+    if (fe) {
+        if (piped) CK(cudaStreamWaitEvent(s_front, h->ev_fork, 0));
+        front_last = !(notch || agc || ff);
+        FrontArgs a{};
+        a.iq = iq; a.out_mono = front_last ? nullptr : h->d_mid_a; a.out_stereo = front_last ? audio : nullptr;
+        a.dbg = front_last ? dbg : nullptr; a.par = h->d_par; a.taps = h->d_taps; a.C = C; a.T = T;
+        Prof pr(h, KK_FRONT, s_front);
+        if (h->front_tc) {
+            a.hist = h->fe_hist_cur ? h->d_fe_hist2 : h->d_fe_hist;
+            a.hist_out = h->fe_hist_cur ? h->d_fe_hist : h->d_fe_hist2;
+            h->fe_hist_cur ^= 1;
+            FrontTcTables tb{};
+            tb.tile_ch = h->d_tile_ch; tb.tile_rows = h->d_tile_rows; tb.toep = h->d_toep; tb.n_tiles = h->n_tiles;
+            launch_front_tc(a, tb, s_front);
+        } else {
+            a.hist = h->fe_hist_cur ? h->d_fe_hist2 : h->d_fe_hist;
+            launch_front(a, s_front);
+        }
+    }
+    if (piped && fe) CK(cudaEventRecord(h->ev_front, s_front));
+
+    // sub-range of a sorted channel list that falls into [c0, c1)
+    auto sub = [](const std::vector<int> &l, int c0, int c1, int &first, int &count) {
+        first = (int)(std::lower_bound(l.begin(), l.end(), c0) - l.begin());
+        count = (int)(std::lower_bound(l.begin(), l.end(), c1) - l.begin()) - first;
+    };
+    int n_fft_frames = 0;
+    for (int t = 0; t < T; t++) {
+        const unsigned long long tk = h->tick + t;
+        if (tk >= 7 && ((tk - 7) & 3) == 0) n_fft_frames++;
+    }
+
+    for (int g = 0; g < G; g++) {
+        const int c0 = (int)((long long)C * g / G), c1 = (int)((long long)C * (g + 1) / G), nc = c1 - c0;
+        cudaStream_t s_main = piped ? h->stage_stream[g] : st;
+        cudaStream_t s_spec = piped ? h->stage_stream[kMaxGroups + g] : st;
+        if (piped) {
+            CK(cudaStreamWaitEvent(s_main, fe ? h->ev_front : h->ev_fork, 0));
+            CK(cudaStreamWaitEvent(s_spec, h->ev_fork, 0));
+        }
 
         if (has(h, RDSP_STAGE_SPEC256)) {
             BiquadArgs b{};
-            b.iq = iq_k; b.out = h->d_hp_iq + o2; b.state = h->d_bq_state; b.C = C; b.T = Tc;
+            b.iq = iq; b.out = h->d_hp_iq; b.state = h->d_bq_state; b.C = C; b.T = T; b.ch0 = c0; b.n = nc;
             b.b0 = h->bq[0]; b.b1 = h->bq[1]; b.b2 = h->bq[2]; b.a1 = h->bq[3]; b.a2 = h->bq[4];
-            { Prof pr(h, KK_BIQUAD, sstream(ST_BIQ)); launch_biquad(b, sstream(ST_BIQ)); }
-            CK(done(ST_BIQ, k));
+            { Prof pr(h, KK_BIQUAD, s_spec); launch_biquad(b, s_spec); }
             Spec256Args a{};
-            a.iq = h->d_hp_iq + o2; a.prev = h->d_spec_prev; a.sum = h->d_spec_sum; a.output = h->d_spec_out;
-            a.C = C; a.T = Tc; a.have_prev = h->spec_have_prev; a.count = h->spec_count; a.naverage = naverage;
+            a.iq = h->d_hp_iq; a.prev = h->d_spec_prev; a.sum = h->d_spec_sum; a.output = h->d_spec_out;
+            a.C = C; a.T = T; a.ch0 = c0; a.n = nc; a.have_prev = h->spec_have_prev; a.count = h->spec_count; a.naverage = naverage;
             a.div_shift = 32 + lgn;
             a.div_magic = ((1ull << a.div_shift) + h->cfg.spec256_naverage - 1) / h->cfg.spec256_naverage;
             a.tw = h->d_tw; a.win = h->d_win256;
-            CK(wait_for(ST_S256, ST_BIQ, k));
-            { Prof pr(h, KK_SPEC256, sstream(ST_S256)); launch_spec256(a, sstream(ST_S256)); }
-            CK(done(ST_S256, k));
-            // host mirror of the uniform counters (analyze_fft256iq.cpp:73-77,99-113)
-            const int updates = Tc - (h->spec_have_prev ? 0 : 1);
-            h->spec_have_prev = 1;
-            const int total = h->spec_count + updates;
-            if (total / naverage > 0) std::fill(h->spec_ready.begin(), h->spec_ready.end(), (uint8_t)1);
-            h->spec_count = total % naverage;
+            { Prof pr(h, KK_SPEC256, s_spec); launch_spec256(a, s_spec); }
         }
 
         const int16_t *mono = nullptr;
-        int audio_src = -1;                                               // stage that completes `mono` / the audio so far
         if (fe) {
-            const bool last = !(notch || agc || ff);
-            FrontArgs a{};
-            a.iq = iq_k; a.out_mono = last ? nullptr : h->d_mid_a + o1; a.out_stereo = last ? audio_k : nullptr;
-            a.dbg = last ? dbg_k : nullptr; a.par = h->d_par; a.taps = h->d_taps; a.C = C; a.T = Tc;
-            if (h->front_tc) {
-                // the tensor-core front end takes the whole call in one launch (tiles x time segments fill the SMs);
-                // later chunks of the wavefront only see its completion event
-                if (k == 0) {
-                    a.T = T;
-                    a.hist = h->fe_hist_cur ? h->d_fe_hist2 : h->d_fe_hist;
-                    a.hist_out = h->fe_hist_cur ? h->d_fe_hist : h->d_fe_hist2;
-                    h->fe_hist_cur ^= 1;
-                    FrontTcTables tb{};
-                    tb.tile_ch = h->d_tile_ch; tb.tile_rows = h->d_tile_rows; tb.toep = h->d_toep; tb.n_tiles = h->n_tiles;
-                    Prof pr(h, KK_FRONT, sstream(ST_FRONT));
-                    launch_front_tc(a, tb, sstream(ST_FRONT));
-                }
-            } else {
-                a.hist = h->fe_hist_cur ? h->d_fe_hist2 : h->d_fe_hist;
-                Prof pr(h, KK_FRONT, sstream(ST_FRONT));
-                launch_front(a, sstream(ST_FRONT));
-            }
-            CK(done(ST_FRONT, k));
-            mono = h->d_mid_a + o1;
-            audio_src = ST_FRONT;
-            if (notch) {
-                CK(wait_for(ST_NOTCH, ST_FRONT, k));
-                if (h->n_notch > 0) {
+            mono = h->d_mid_a;
+            int f_notch = 0, n_notch = 0, f_plain = 0, n_plain = 0;
+            if (notch) { sub(h->l_notch, c0, c1, f_notch, n_notch); sub(h->l_plain, c0, c1, f_plain, n_plain); }
+            if (notch || agc) {
+                AgcArgs ag{};
+                ag.out_mono = ff ? h->d_mid_b : nullptr; ag.out_stereo = ff ? nullptr : audio;
+                ag.dbg = ff ? nullptr : dbg; ag.env = h->d_agc_env; ag.par = h->d_par; ag.C = C; ag.T = T;
+                ag.agc_stage = agc ? 1 : 0;
+                ag.target = h->cfg.agc_target; ag.max_gain = h->cfg.agc_max_gain; ag.alpha_a = h->agc_alpha_a;
+                // channels that bypass the notch read the front end's q15 rows ...
+                ag.list = notch ? h->d_list_plain + f_plain : nullptr; ag.n_list = notch ? n_plain : nc; ag.ch0 = c0;
+                ag.in_q15 = h->d_mid_a; ag.in_f32 = nullptr;
+                // (on a side stream when the notch runs next to it: the two touch disjoint channels)
+                const bool side = piped && notch && n_notch > 0 && ag.n_list > 0;
+                cudaStream_t s_side = side ? h->stage_stream[2 * kMaxGroups + g] : s_main;
+                if (side) CK(cudaStreamWaitEvent(s_side, h->ev_front, 0));
+                if (ag.n_list > 0) { Prof pr(h, KK_AGC, s_side); launch_agc(ag, s_side); }
+                if (side) CK(cudaEventRecord(h->ev_group[g][2], s_side));
+                if (notch && n_notch > 0) {
                     NlmsArgs n{};
-                    n.list = h->d_list_notch; n.n_list = h->n_notch; n.C = C; n.T = Tc;
-                    n.in_q15 = h->d_mid_a + o1; n.out_f32 = h->d_scr + o1;
+                    n.list = h->d_list_notch + f_notch; n.n_list = n_notch; n.C = C; n.T = T;
+                    n.in_q15 = h->d_mid_a; n.out_f32 = h->d_scr;
                     n.coeff = h->d_nc_coeff; n.prev = h->d_nc_prev; n.energy = h->d_nc_energy; n.first = h->d_nc_first;
                     n.par = h->d_par; n.mode = 0;
-                    { Prof pr(h, KK_NOTCH, sstream(ST_NOTCH)); launch_nlms(n, sstream(ST_NOTCH)); }
+                    { Prof pr(h, KK_NOTCH, s_main); launch_nlms(n, s_main); }
+                    // ... the others read the notch's f32 error signal
+                    ag.list = h->d_list_notch + f_notch; ag.n_list = n_notch; ag.in_q15 = nullptr; ag.in_f32 = h->d_scr;
+                    { Prof pr(h, KK_AGC, s_main); launch_agc(ag, s_main); }
                 }
-                CK(done(ST_NOTCH, k));
-            }
-            if (notch || agc) {
-                CK(wait_for(ST_AGC, ST_FRONT, k));
-                if (notch) CK(wait_for(ST_AGC, ST_NOTCH, k));
-                AgcArgs g{};
-                g.out_mono = ff ? h->d_mid_b + o1 : nullptr; g.out_stereo = ff ? nullptr : audio_k;
-                g.dbg = ff ? nullptr : dbg_k; g.env = h->d_agc_env; g.par = h->d_par; g.C = C; g.T = Tc;
-                g.agc_stage = agc ? 1 : 0;
-                g.target = h->cfg.agc_target; g.max_gain = h->cfg.agc_max_gain; g.alpha_a = h->agc_alpha_a;
-                // channels that bypassed the notch read the front end's q15 rows ...
-                g.list = notch ? h->d_list_plain : nullptr; g.n_list = notch ? h->n_plain : C;
-                g.in_q15 = h->d_mid_a + o1; g.in_f32 = nullptr;
-                if (g.n_list > 0) { Prof pr(h, KK_AGC, sstream(ST_AGC)); launch_agc(g, sstream(ST_AGC)); }
-                // ... the others read the notch's f32 error signal
-                if (notch && h->n_notch > 0) {
-                    g.list = h->d_list_notch; g.n_list = h->n_notch; g.in_q15 = nullptr; g.in_f32 = h->d_scr + o1;
-                    { Prof pr(h, KK_AGC, sstream(ST_AGC)); launch_agc(g, sstream(ST_AGC)); }
-                }
-                CK(done(ST_AGC, k));
-                mono = h->d_mid_b + o1;
-                audio_src = ST_AGC;
+                if (side) CK(cudaStreamWaitEvent(s_main, h->ev_group[g][2], 0));
+                mono = h->d_mid_b;
             }
         }
         if (ff) {
-            if (audio_src >= 0) CK(wait_for(ST_FFT, audio_src, k));
             FftFiltArgs f{};
-            f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq_k; f.out_stereo = audio_k; f.out_f32_L = h->d_scr + o1;
-            f.dbg = dbg_k; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256;
-            f.par = h->d_par; f.C = C; f.T = Tc; f.nr_stage = nr ? 1 : 0;
-            { Prof pr(h, KK_FFTFILT, sstream(ST_FFT)); launch_fftfilt(f, sstream(ST_FFT)); }
-            CK(done(ST_FFT, k));
-            audio_src = ST_FFT;
+            f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq; f.out_stereo = audio; f.out_f32_L = h->d_scr;
+            f.dbg = dbg; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256;
+            f.par = h->d_par; f.C = C; f.T = T; f.ch0 = c0; f.n = nc; f.nr_stage = nr ? 1 : 0;
+            { Prof pr(h, KK_FFTFILT, s_main); launch_fftfilt(f, s_main); }
             if (nr) {
-                CK(wait_for(ST_DNR, ST_FFT, k));
-                if (h->n_dnr > 0) {
+                int f_dnr = 0, n_dnr = 0;
+                sub(h->l_dnr, c0, c1, f_dnr, n_dnr);
+                if (n_dnr > 0) {
                     NlmsArgs n{};
-                    n.list = h->d_list_dnr; n.n_list = h->n_dnr; n.C = C; n.T = Tc;
-                    n.in_f32 = h->d_scr + o1; n.out_stereo = audio_k; n.dbg = dbg_k;
+                    n.list = h->d_list_dnr + f_dnr; n.n_list = n_dnr; n.C = C; n.T = T;
+                    n.in_f32 = h->d_scr; n.out_stereo = audio; n.dbg = dbg;
                     n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
                     n.par = h->d_par; n.mode = 1;
-                    { Prof pr(h, KK_DNR, sstream(ST_DNR)); launch_nlms(n, sstream(ST_DNR)); }
+                    { Prof pr(h, KK_DNR, s_main); launch_nlms(n, s_main); }
                 }
-                CK(done(ST_DNR, k));
-                audio_src = ST_DNR;
             }
         }
         if (has(h, RDSP_STAGE_SPEC1024)) {
-            CK(wait_for(ST_S1024, audio_src, k));
             Spec1024Args s1{};
-            s1.audio = audio_k; s1.ring = h->d_ring; s1.output = h->d_spec1024_out; s1.C = C; s1.T = Tc; s1.tick0 = h->tick;
-            s1.tw = h->d_tw; s1.win = h->d_win1024;
-            int n_fft = 0;
-            for (int t = 0; t < Tc; t++) {
-                const unsigned long long tk = h->tick + t;
-                if (tk >= 7 && ((tk - 7) & 3) == 0) n_fft++;
-            }
-            s1.any_fft = n_fft > 0;
-            { Prof pr(h, KK_SPEC1024, sstream(ST_S1024)); launch_spec1024(s1, sstream(ST_S1024)); }
-            CK(done(ST_S1024, k));
-            if (n_fft) std::fill(h->spec1024_ready.begin(), h->spec1024_ready.end(), (uint8_t)1);
+            s1.audio = audio; s1.ring = h->d_ring; s1.output = h->d_spec1024_out; s1.C = C; s1.T = T; s1.ch0 = c0; s1.n = nc;
+            s1.tick0 = h->tick; s1.tw = h->d_tw; s1.win = h->d_win1024;
+            s1.any_fft = n_fft_frames > 0;
+            { Prof pr(h, KK_SPEC1024, s_main); launch_spec1024(s1, s_main); }
         }
-        h->tick += Tc;
+        if (piped) {
+            // join: the call is complete on the handle's stream when every group has finished both of its streams
+            CK(cudaEventRecord(h->ev_group[g][0], s_main));
+            CK(cudaEventRecord(h->ev_group[g][1], s_spec));
+            CK(cudaStreamWaitEvent(st, h->ev_group[g][0], 0));
+            CK(cudaStreamWaitEvent(st, h->ev_group[g][1], 0));
+        }
     }
-    if (piped) {
-        // join: the call is complete on the handle's stream when every stage has finished its last chunk
-        const int used[] = {fe ? ST_FRONT : -1, (fe && notch) ? ST_NOTCH : -1, (fe && (notch || agc)) ? ST_AGC : -1, ff ? ST_FFT : -1,
-                            (ff && nr) ? ST_DNR : -1, has(h, RDSP_STAGE_SPEC1024) ? ST_S1024 : -1,
-                            has(h, RDSP_STAGE_SPEC256) ? ST_BIQ : -1, has(h, RDSP_STAGE_SPEC256) ? ST_S256 : -1};
-        for (int s : used)
-            if (s >= 0) CK(cudaStreamWaitEvent(st, h->ev_stage[s][nchunks - 1], 0));
+    // host mirror of the uniform counters (analyze_fft256iq.cpp:73-77,99-113; AudioAnalyzeFFT1024 frame cadence)
+    if (has(h, RDSP_STAGE_SPEC256)) {
+        const int updates = T - (h->spec_have_prev ? 0 : 1);
+        h->spec_have_prev = 1;
+        const int total = h->spec_count + updates;
+        if (total / naverage > 0) std::fill(h->spec_ready.begin(), h->spec_ready.end(), (uint8_t)1);
+        h->spec_count = total % naverage;
     }
+    if (has(h, RDSP_STAGE_SPEC1024) && n_fft_frames) std::fill(h->spec1024_ready.begin(), h->spec1024_ready.end(), (uint8_t)1);
+    h->tick += T;
+    if (piped && fe && front_last) CK(cudaStreamWaitEvent(st, h->ev_front, 0));
     CK(cudaGetLastError());
 
     if (host_io) {
@@ -828,6 +846,7 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
         CK(cudaStreamSynchronize(h->stream));
         if (host_io) CK(cudaStreamSynchronize(h->d2h_stream));
     }
+    if (h->timeline) prof_collect(h);
     return RDSP_OK;
 }
 
