@@ -94,6 +94,54 @@ def test_taps_are_data(rd, po):
     assert np.array_equal(g, o)
 
 
+@pytest.mark.parametrize("nc,nblocks", [(300, 5), (1200, 12)])
+def test_frontend_tensor_core_wraps_like_the_cuda_core_kernel(rd, po, nc, nblocks, monkeypatch):
+    """k_front_tc (tcgen05, byte-split q15 products) against k_front (IMAD) and the oracle with FULL-RANGE taps and
+    inputs, where the 32-bit fast-FIR accumulator wraps: bit-exact outputs over several calls (state carry),
+    ragged tiles (channel classes that do not fill 128 rows) and calls long enough to be cut into time segments."""
+    rng = np.random.default_rng(11)
+    taps = {(k, i): rng.integers(-32768, 32768, 129).astype(np.int16) for k in range(3) for i in range(5)}
+    taps[(0, 1)] = taps[(0, 0)].copy(); taps[(1, 1)] = taps[(1, 0)].copy()       # LSB / USB share their Hilbert rows
+    for i in range(5):
+        taps[(2, i)] = (taps[(2, i)] // (1 << i)).astype(np.int16)                # a spread of band-pass magnitudes
+    demod = rng.integers(0, 5, nc)
+    filt = rng.integers(0, 5, nc)
+    gains = rng.choice([1.0, 0.37, 2.5, 1.02], nc)
+    iq = rng.integers(-32768, 32768, (nblocks, nc, 128, 2)).astype(np.int16)
+    iq[:, ::7] = np.where(rng.random((nblocks, (nc + 6) // 7, 128, 2)) < 0.5, 32767, -32768).astype(np.int16)
+
+    def run(impl):
+        if impl:
+            monkeypatch.setenv("RDSP_FRONT_IMPL", impl)
+        else:
+            monkeypatch.delenv("RDSP_FRONT_IMPL", raising=False)
+        bank = make_bank(rd, nc, rd.STAGE_FRONTEND, max_blocks=nblocks)
+        for (k, i), t in taps.items():
+            bank.set_taps(k, i, t)
+        for c in range(nc):
+            bank.set_mode(c, 1, rd.default_params(demod=int(demod[c]), audio_filter=int(filt[c]), in_gain=float(gains[c])))
+        outs = [bank.process_host(iq)]
+        outs.append(bank.process_host(iq[: max(1, nblocks // 2)]))              # second call: delay lines carried over
+        outs.append(bank.process_host(iq[:1]))
+        return np.concatenate(outs)
+
+    g_tc = run(None)
+    g_cc = run("cuda-core")
+    assert np.array_equal(g_tc, g_cc)
+    saved = {(k, i): po.get_taps(k, i) for (k, i) in taps}
+    try:
+        for (k, i), t in taps.items():
+            po.lib().rdsp_oracle_set_taps(k, i, t.ctypes.data)
+        sub = np.arange(0, nc, max(1, nc // 40))                                  # the oracle on a sample of the channels
+        params = [po.default_params(demod=int(demod[c]), audio_filter=int(filt[c]), in_gain=float(gains[c])) for c in sub]
+        seq = np.concatenate([iq[:, sub], iq[: max(1, nblocks // 2), sub], iq[:1, sub]])
+        o, _ = po.process_bank(po.default_config(stage_mask=po.STAGE_FRONTEND), params, np.ascontiguousarray(seq))
+    finally:
+        for (k, i), t in saved.items():
+            po.lib().rdsp_oracle_set_taps(k, i, t.ctypes.data)
+    assert np.array_equal(g_tc[:, sub], o)
+
+
 # ------------------------------------------------------------------------------------------ K3, K4
 
 def test_notch_and_agc_f32_parity(rd, po):
