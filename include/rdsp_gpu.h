@@ -59,14 +59,17 @@ enum {
     RDSP_ERR_STATE     = -5    /* call not valid for this handle's stage mask */
 };
 
-/* demodulation modes, RDSP_controls.h:330-423 (SAMmode: not built yet) */
+/* demodulation modes, RDSP_controls.h:330-423 */
 enum {
     RDSP_DEMOD_LSB    = 0,     /* LSBmode     */
     RDSP_DEMOD_USB    = 1,     /* USBmode     */
     RDSP_DEMOD_CW_LSB = 2,     /* CW_LSBmode  */
     RDSP_DEMOD_CW_USB = 3,     /* CW_USBmode  */
     RDSP_DEMOD_AM     = 4,     /* AMmode      */
-    RDSP_DEMOD_COUNT  = 5
+    RDSP_DEMOD_COUNT  = 5,     /* rows of the Hilbert tap tables (rdsp_gpu_set_taps index) */
+    RDSP_DEMOD_SAM    = 5,     /* SAMmode, RDSP_controls.h:384-391: synchronous AM — the AM tap rows, carrier PLL
+                                  + coherent detection instead of the envelope (DESIGN.md "SAM") */
+    RDSP_DEMOD_MODES  = 6
 };
 
 /* audio filter presets, RDSP_controls.h:149-191 */
@@ -143,11 +146,18 @@ typedef struct {
     float   in_gain;             /* default 1.0   RadioDSP_SDR_RX.ino:133 */
     float   out_gain;            /* default 0.5   RadioDSP_SDR_RX.ino:134 */
     float   iq_balance;          /* default 1.020 RadioDSP_SDR_RX.ino:135 */
+    int32_t als_peak;            /* 0: SDR.setALSfilterNotch() (RDSP_controls.h:258, the notch emits the NLMS error),
+                                    1: ALS "peak" (backup sketch: the notch stage emits the NLMS estimate); default 0 */
 } rdsp_chan_params_t;
 
 /* fill *cfg / *p with the reference's setup() defaults */
 void rdsp_gpu_default_config(rdsp_gpu_config_t *cfg);
 void rdsp_gpu_default_params(rdsp_chan_params_t *p);
+
+/* The band-pass designer of the default tap bank for an arbitrary audio band (Hz): 129 q15 taps for
+ * rdsp_gpu_set_taps(RDSP_TAPS_BANDPASS, ...).  audioWSPR (RDSP_controls.h:392-402: 200 Hz around 1500 Hz) is
+ * rdsp_gpu_design_bandpass(1400, 1600, taps) loaded into a preset row.  No handle, no device. */
+int  rdsp_gpu_design_bandpass(float lo_hz, float hi_hz, int16_t *taps, uint32_t n_taps);
 
 int  rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out);
 void rdsp_gpu_destroy(rdsp_gpu_t *h);

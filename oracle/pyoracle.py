@@ -24,7 +24,7 @@ REF_PATH = os.path.join(HERE, "_ref", "librdsp_ref.so")
 BLK = 128
 
 # ---- mirrors of include/rdsp_gpu.h ---------------------------------------------------------
-DEMOD_LSB, DEMOD_USB, DEMOD_CW_LSB, DEMOD_CW_USB, DEMOD_AM = range(5)
+DEMOD_LSB, DEMOD_USB, DEMOD_CW_LSB, DEMOD_CW_USB, DEMOD_AM, DEMOD_SAM = range(6)
 FILTER_CW, FILTER_2100, FILTER_2700, FILTER_3100, FILTER_AM = range(5)
 AGC_OFF, AGC_FAST, AGC_MEDIUM, AGC_SLOW = range(4)
 NR_OFF, NR_LMS, NR_SPECTRAL = range(3)
@@ -49,6 +49,7 @@ class Params(C.Structure):
         ("notch_on", C.c_int32), ("notch_level", C.c_int32), ("nr_kind", C.c_int32),
         ("nr_level", C.c_int32), ("pbt_lo_hz", C.c_float), ("pbt_hi_hz", C.c_float),
         ("in_gain", C.c_float), ("out_gain", C.c_float), ("iq_balance", C.c_float),
+        ("als_peak", C.c_int32),
     ]
 
     def copy(self, **kw):

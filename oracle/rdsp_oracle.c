@@ -82,6 +82,14 @@ static int16_t q15_round(double v)
  *   AM: A = B = real low-pass (lo = -hi), envelope of (A(I), B(Q)).
  *   Band-pass bank: real taps 2*cI.
  *   Every designed pair is first scaled to unity gain at the centre of its pass-band. */
+/* SAM loop (shim-defined; the same constants in radiodsp_sdr_rx_b200/csrc/rdsp_common.cuh): natural frequency 100 Hz,
+ * damping 0.707 at 44.1 kHz; pull-in limited to +-1 kHz; carrier-level tracker 100 ms */
+#define RDSP_SAM_K1   0.020146f
+#define RDSP_SAM_K2   2.02995e-4f
+#define RDSP_SAM_WMAX 0.142476f
+#define RDSP_SAM_ADC  2.2673e-4f
+#define RDSP_SAM_PI   3.14159265358979f
+
 static const double k_hil_band[RDSP_DEMOD_COUNT][2] = {
     { 100.0, 3600.0 },   /* LSB    */
     { 100.0, 3600.0 },   /* USB    */
@@ -212,6 +220,8 @@ struct rdsp_oracle_chan {
     int32_t mult_i, mult_q;
     /* K1/K2 q15 delay lines: the 128 samples before the current block */
     int16_t hist_i[BLK], hist_q[BLK], hist_d[BLK];
+    /* SAM carrier PLL: phase, frequency (rad/sample), carrier level */
+    float sam_phi, sam_omega, sam_dc;
     /* K3 notch */
     nlms_t notch;
     int notch_old_level;
@@ -258,6 +268,7 @@ void rdsp_oracle_default_params(rdsp_chan_params_t *p)
     p->in_gain = 1.0f;
     p->out_gain = 0.5f;
     p->iq_balance = 1.020f;
+    p->als_peak = 0;
 }
 
 void rdsp_oracle_default_config(rdsp_gpu_config_t *cfg)
@@ -345,7 +356,8 @@ static inline int16_t mix_gain(int16_t in, int32_t mult)
 static void stage_frontend(rdsp_oracle_chan_t *c, const int16_t *iq, int16_t *audio)
 {
     int16_t xi[BLK], xq[BLK], a[BLK], b[BLK], d[BLK];
-    const int m = c->par.demod;
+    const int mode = c->par.demod;
+    const int m = mode == RDSP_DEMOD_SAM ? RDSP_DEMOD_AM : mode;         /* SAM filters its arms with the AM rows */
     for (int n = 0; n < BLK; n++) {
         xi[n] = mix_gain(iq[2 * n], c->mult_i);
         xq[n] = mix_gain(iq[2 * n + 1], c->mult_q);
@@ -355,7 +367,25 @@ static void stage_frontend(rdsp_oracle_chan_t *c, const int16_t *iq, int16_t *au
     memcpy(c->hist_i, xi, sizeof(xi));
     memcpy(c->hist_q, xq, sizeof(xq));
     for (int n = 0; n < BLK; n++) {
-        switch (m) {
+        switch (mode) {
+        case RDSP_DEMOD_SAM: {
+            /* SAMmode (RDSP_controls.h:384-391; AudioSDR absent, shim-defined): second-order PLL on the carrier of
+             * the low-passed pair, coherent detection, carrier level removed by a slow tracker.  f32. */
+            float sn = sinf(c->sam_phi), cs = cosf(c->sam_phi);
+            float re = (float)a[n] * cs + (float)b[n] * sn;
+            float im = (float)b[n] * cs - (float)a[n] * sn;
+            float err = (re == 0.0f && im == 0.0f) ? 0.0f : atan2f(im, re);
+            c->sam_omega += RDSP_SAM_K2 * err;
+            c->sam_omega = fminf(fmaxf(c->sam_omega, -RDSP_SAM_WMAX), RDSP_SAM_WMAX);
+            c->sam_phi += c->sam_omega + RDSP_SAM_K1 * err;
+            if (c->sam_phi >= RDSP_SAM_PI) c->sam_phi -= 2.0f * RDSP_SAM_PI;
+            if (c->sam_phi < -RDSP_SAM_PI) c->sam_phi += 2.0f * RDSP_SAM_PI;
+            c->sam_dc += (re - c->sam_dc) * RDSP_SAM_ADC;
+            float o = re - c->sam_dc;
+            o = fminf(fmaxf(o, -32768.0f), 32767.0f);
+            d[n] = (int16_t)(int32_t)o;                                           /* truncation toward zero */
+            break;
+        }
         case RDSP_DEMOD_USB: case RDSP_DEMOD_CW_USB:
             d[n] = (int16_t)sat16((int32_t)a[n] - (int32_t)b[n]); break;          /* QSUB16 */
         case RDSP_DEMOD_LSB: case RDSP_DEMOD_CW_LSB:
@@ -376,8 +406,8 @@ static void stage_notch(rdsp_oracle_chan_t *c, float *x)
         nlms_init(&c->notch, c->par.notch_level);
         c->notch_old_level = c->par.notch_level;
     }
-    nlms_run(&c->notch, BLK, x);
-    memcpy(x, c->notch.errsig, BLK * sizeof(float));
+    nlms_run(&c->notch, BLK, x);                       /* leaves the estimate in x, the error in errsig */
+    if (!c->par.als_peak) memcpy(x, c->notch.errsig, BLK * sizeof(float));   /* notch: error; peak: estimate */
 }
 
 /* K4: AGC (peak follower, shim-defined) then SDR.setOutputGain, RadioDSP_SDR_RX.ino:134 */

@@ -7,7 +7,7 @@ creating a bank without an sm_100-class GPU, raises.
 """
 from .native import (  # noqa: F401
     RdspError, Config, Params, ReceiverBank, default_config, default_params, lib, version,
-    DEMOD_LSB, DEMOD_USB, DEMOD_CW_LSB, DEMOD_CW_USB, DEMOD_AM,
+    DEMOD_LSB, DEMOD_USB, DEMOD_CW_LSB, DEMOD_CW_USB, DEMOD_AM, DEMOD_SAM,
     FILTER_CW, FILTER_2100, FILTER_2700, FILTER_3100, FILTER_AM,
     AGC_OFF, AGC_FAST, AGC_MEDIUM, AGC_SLOW, NR_OFF, NR_LMS, NR_SPECTRAL,
     STAGE_FRONTEND, STAGE_NOTCH, STAGE_AGC, STAGE_FFTFILT, STAGE_NR, STAGE_SPEC256, STAGE_SPEC1024, STAGE_ALL,

@@ -105,12 +105,17 @@ void design_hilbert_pair(int demod, int16_t *ti, int16_t *tq)
     }
 }
 
-void design_bandpass(int filter, int16_t *t)
+void design_bandpass_hz(double lo, double hi, int16_t *t)
 {
     double cI[RDSP_FIR_TAPS], cQ[RDSP_FIR_TAPS];
-    design_cplx_fir(cI, cQ, RDSP_FIR_TAPS, kBpBand[filter][0], kBpBand[filter][1], kFs);
-    normalise_centre_gain(cI, cQ, RDSP_FIR_TAPS, kBpBand[filter][0], kBpBand[filter][1], kFs);
+    design_cplx_fir(cI, cQ, RDSP_FIR_TAPS, lo, hi, kFs);
+    normalise_centre_gain(cI, cQ, RDSP_FIR_TAPS, lo, hi, kFs);
     for (int k = 0; k < RDSP_FIR_TAPS; k++) t[k] = q15_round(2.0 * cI[k]);
+}
+
+void design_bandpass(int filter, int16_t *t)
+{
+    design_bandpass_hz(kBpBand[filter][0], kBpBand[filter][1], t);
 }
 
 float lms_mu(int strength)

@@ -92,8 +92,9 @@ __global__ void __launch_bounds__(MAXWARPS * 32, 2) k_front(FrontArgs a)
     const int ch = active ? chq : a.C - 1;                   // idle half-warps shadow the last channel, stores masked
 
     const RdspChanParams p = a.par[ch];
-    const int16_t *tapA = s_taps + (0 + p.demod) * TROW;
-    const int16_t *tapB = s_taps + (RDSP_N_DEMOD + p.demod) * TROW;
+    const int td = p.demod >= RDSP_N_DEMOD ? RDSP_DEMOD_AM_ : p.demod;     // (SAM is only built in k_front_tc; the host rejects it here)
+    const int16_t *tapA = s_taps + (0 + td) * TROW;
+    const int16_t *tapB = s_taps + (RDSP_N_DEMOD + td) * TROW;
     const int16_t *tapM = s_taps + (2 * RDSP_N_DEMOD + p.filter) * TROW;
     int16_t *bI = s_buf[slot][0], *bQ = s_buf[slot][1], *bD = s_buf[slot][2];
     int4 *bI4 = reinterpret_cast<int4 *>(bI), *bQ4 = reinterpret_cast<int4 *>(bQ), *bD4 = reinterpret_cast<int4 *>(bD);

@@ -245,9 +245,13 @@ __device__ __forceinline__ void issue_fir(uint32_t ring_lo, uint32_t ring_hi, ui
 }
 
 // ---- epilogues ----------------------------------------------------------------------------------------------------
-// epilogue 1: I' and Q' accumulators -> q15 -> sideband sum / envelope -> D slice (byte planes), 8 outputs per round
-template <bool AM>
-__device__ __forceinline__ void epilogue1(const TcSmem &s, uint32_t tmem_row, int row, int slice, bool usb)
+// epilogue 1: I' and Q' accumulators -> q15 -> sideband sum / envelope / synchronous detection -> D slice (byte planes),
+// 8 outputs per round.  MODE 0: QADD16 / QSUB16, 1: AM envelope, 2: SAM (carrier PLL, sequential in time: the thread
+// of a row walks its samples in order, chunk after chunk, with the loop state in registers).
+struct SamState { float phi, omega, dc; };
+
+template <int MODE>
+__device__ __forceinline__ void epilogue1(const TcSmem &s, uint32_t tmem_row, int row, int slice, bool usb, SamState &sam)
 {
 #pragma unroll 1
     for (int it = 0; it < 4; it++) {
@@ -260,9 +264,24 @@ __device__ __forceinline__ void epilogue1(const TcSmem &s, uint32_t tmem_row, in
         for (int j = 0; j < 8; j++) {
             const int32_t ya = recombine(v[0][j], v[1][j], v[2][j]);
             const int32_t yb = recombine(v[3][j], v[4][j], v[5][j]);
-            if (AM) {
+            if (MODE == 1) {
                 const uint32_t e = sqrt_u32_approx_fast((uint32_t)(ya * ya) + (uint32_t)(yb * yb), s.sqrt_guess());
                 d[j] = (int32_t)min(e, 32767u);
+            } else if (MODE == 2) {
+                // oracle/rdsp_oracle.c:stage_frontend, RDSP_DEMOD_SAM
+                float sn, cs;
+                sincosf(sam.phi, &sn, &cs);
+                const float fa = (float)ya, fb = (float)yb;
+                const float re = fa * cs + fb * sn, im = fb * cs - fa * sn;
+                const float err = (re == 0.0f && im == 0.0f) ? 0.0f : atan2f(im, re);
+                sam.omega += RDSP_SAM_K2 * err;
+                sam.omega = fminf(fmaxf(sam.omega, -RDSP_SAM_WMAX), RDSP_SAM_WMAX);
+                sam.phi += sam.omega + RDSP_SAM_K1 * err;
+                if (sam.phi >= RDSP_SAM_PI) sam.phi -= 2.0f * RDSP_SAM_PI;
+                if (sam.phi < -RDSP_SAM_PI) sam.phi += 2.0f * RDSP_SAM_PI;
+                sam.dc += (re - sam.dc) * RDSP_SAM_ADC;
+                const float o = fminf(fmaxf(re - sam.dc, -32768.0f), 32767.0f);
+                d[j] = (int32_t)o;                                           // truncation toward zero
             } else {
                 d[j] = sat16(usb ? ya - yb : ya + yb);
             }
@@ -336,7 +355,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x, seg = blockIdx.y;
     const int4 rows = tb.tile_rows[tile];                                 // x, y, z = Toeplitz images; w = AM flag
-    const bool am = rows.w != 0;
+    const int dmode = rows.w;                                             // 0 sideband sum, 1 AM envelope, 2 SAM
 #ifdef RDSP_TC_PROF
     unsigned long long gt0_;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0_));
@@ -474,6 +493,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
         const int row = threadIdx.x;
         const bool usb = s.row_usb()[row] != 0;
         const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+        const int ch1 = s.row_ch()[row];
+        SamState sam{0.f, 0.f, 0.f};
+        if (dmode == 2 && ch1 >= 0) {
+            const float4 st = *reinterpret_cast<const float4 *>(a.sam_state + (size_t)ch1 * 4);
+            sam.phi = st.x; sam.omega = st.y; sam.dc = st.z;
+        }
         TCP_BEGIN;
 #pragma unroll 1
         for (int c = 0; c < nch; c++) {
@@ -483,13 +508,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
             if (c >= 2) mbar_wait(bar(B_M2_DONE + (c & 1)), ((c - 2) >> 1) & 1);
             if (warp == 0) TCP(9);
             tc_fence_after();
-            if (am) epilogue1<true>(s, tmem_row + (c & 1) * TM_ACC1B, row, (c + 4) % SLICES, usb);
-            else epilogue1<false>(s, tmem_row + (c & 1) * TM_ACC1B, row, (c + 4) % SLICES, usb);
+            if (dmode == 1) epilogue1<1>(s, tmem_row + (c & 1) * TM_ACC1B, row, (c + 4) % SLICES, usb, sam);
+            else if (dmode == 2) epilogue1<2>(s, tmem_row + (c & 1) * TM_ACC1B, row, (c + 4) % SLICES, usb, sam);
+            else epilogue1<0>(s, tmem_row + (c & 1) * TM_ACC1B, row, (c + 4) % SLICES, usb, sam);
             tc_fence_before();
             fence_async_smem();
             mbar_arrive(bar(B_E1_DONE + (c & 1)));
             if (warp == 0) TCP(10);
         }
+        if (dmode == 2 && ch1 >= 0) *reinterpret_cast<float4 *>(a.sam_state + (size_t)ch1 * 4) = make_float4(sam.phi, sam.omega, sam.dc, 0.f);
     } else {
         // ===== epilogue 2 =====
         const int row = threadIdx.x - W_E2 * 32;
@@ -550,7 +577,8 @@ void front_tc_build_toeplitz(const int16_t *taps /*[15][stride]*/, int stride, u
                     }
 }
 
-// Channels that share their three tap rows (by content) and the AM flag form a class; classes are cut into tiles of 128.
+// Channels that share their three tap rows (by content) and the detector (sideband sum / envelope / SAM) form a class;
+// classes are cut into tiles of 128.
 int front_tc_build_tiles(const RdspChanParams *par, int C, const int16_t *taps, int stride,
                          std::vector<int> &tile_ch, std::vector<int4> &tile_rows)
 {
@@ -563,7 +591,9 @@ int front_tc_build_tiles(const RdspChanParams *par, int C, const int16_t *taps, 
     std::map<std::array<int, 4>, std::vector<int>> classes;
     for (int ch = 0; ch < C; ch++) {
         const RdspChanParams &p = par[ch];
-        const std::array<int, 4> key = {canon[p.demod], canon[RDSP_N_DEMOD + p.demod], canon[2 * RDSP_N_DEMOD + p.filter], p.demod == 4 ? 1 : 0};
+        const int td = p.demod == RDSP_DEMOD_SAM_ ? RDSP_DEMOD_AM_ : p.demod;      // SAM filters its arms with the AM rows
+        const int kind = p.demod == RDSP_DEMOD_AM_ ? 1 : (p.demod == RDSP_DEMOD_SAM_ ? 2 : 0);
+        const std::array<int, 4> key = {canon[td], canon[RDSP_N_DEMOD + td], canon[2 * RDSP_N_DEMOD + p.filter], kind};
         classes[key].push_back(ch);
     }
     tile_ch.clear();
@@ -631,6 +661,6 @@ void launch_front_tc(const FrontArgs &a_in, const FrontTcTables &tb_in, cudaStre
     if (!a.hist_out) a.hist_out = a.hist;
     int S = 1;
     front_tc_plan_segments(tb.n_tiles, a.T, n_sm, tb.seg_bounds, &S);
-    if (S > 1 && a.hist_out == a.hist) { S = 1; tb.seg_bounds[0] = 0; tb.seg_bounds[1] = a.T; }   // in-place state: one segment
+    if (S > 1 && (a.hist_out == a.hist || tb.any_sam)) { S = 1; tb.seg_bounds[0] = 0; tb.seg_bounds[1] = a.T; }   // in-place state / SAM loop: one segment
     k_front_tc<<<dim3(tb.n_tiles, S), NTHREADS, SMEM_B, st>>>(a, tb);
 }

@@ -63,10 +63,11 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
 
     float c[W], u[S];
     float energy = 0.0f, mu = 0.0f;
-    bool first = false;
+    bool first = false, peak = false;
     if (active) {
         const RdspChanParams p = a.par[ch];
         mu = a.mode ? p.mu_dnr : p.mu_notch;
+        peak = !a.mode && p.als_peak != 0;                               // ALS "peak": the notch stage emits the estimate
         const float *cf = a.coeff + (size_t)ch * RDSP_LMS_NTAPS;
 #pragma unroll
         for (int i = 0; i < W; i++) c[i] = cf[95 - W * g - i];        // register i <-> delay W*g + i
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
                     e[3] = dd[3] - y[3]; gj[3] = e[3] * qn[3];
 
                     if (g == 0)
-                        st4(xb + n, a.mode ? make_float4(y[0], y[1], y[2], y[3]) : make_float4(e[0], e[1], e[2], e[3]));
+                        st4(xb + n, (a.mode || peak) ? make_float4(y[0], y[1], y[2], y[3]) : make_float4(e[0], e[1], e[2], e[3]));
 
                     // ---- coefficient update c += sum_j g[j] x[n+j]
 #pragma unroll

@@ -46,10 +46,11 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms_direct(NlmsArgs a)
 
     float c[W], xw[W];
     float energy = 0.0f, mu = 0.0f;
-    bool first = false;
+    bool first = false, peak = false;
     if (active) {
         const RdspChanParams p = a.par[ch];
         mu = a.mode ? p.mu_dnr : p.mu_notch;
+        peak = !a.mode && p.als_peak != 0;
         const float *cf = a.coeff + (size_t)ch * RDSP_LMS_NTAPS;
 #pragma unroll
         for (int i = 0; i < W; i++) c[i] = cf[95 - W * g - i];        // register i <-> delay W*g + i
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms_direct(NlmsArgs a)
                     const float w = (e * mu) * inv;
 #pragma unroll
                     for (int i = 0; i < W; i++) c[i] = fmaf(w, xw[(u - i + W) % W], c[i]);
-                    if (g == 0) xb[n] = a.mode ? sum : e;    // slot n of the previous block is dead after d was read
+                    if (g == 0) xb[n] = (a.mode || peak) ? sum : e;    // slot n of the previous block is dead after d was read
                 }
             }
         }

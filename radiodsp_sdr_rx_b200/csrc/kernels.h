@@ -14,6 +14,7 @@ struct FrontArgs {
     int16_t *hist;              // [C][3][128] delay lines: I', Q', demodulated
     int16_t *hist_out;          // k_front_tc only: where the new delay lines go (nullptr = in place; a second buffer lets
                                 // the blocks of a call be cut into concurrent time segments)
+    float *sam_state;           // [C][4] SAM carrier loop: phase, frequency, carrier level, pad (k_front_tc only)
     const RdspChanParams *par;  // [C]
     const int32_t *taps;        // [15][132]: hilbert_i[5], hilbert_q[5], bandpass[5]
     int C, T;
@@ -23,10 +24,11 @@ void launch_front(const FrontArgs &a, cudaStream_t st);
 // K0+K1+K2 on tcgen05 (k_front_tc.cu): channels grouped into tiles of 128 that share their tap rows
 struct FrontTcTables {
     const int *tile_ch;         // [n_tiles][128] channel of every MMA row, -1 = padding
-    const int4 *tile_rows;      // [n_tiles] Toeplitz image index of the I', Q' and band-pass taps; w = AM envelope
+    const int4 *tile_rows;      // [n_tiles] Toeplitz image index of the I', Q' and band-pass taps; w = 0 sideband sum, 1 AM envelope, 2 SAM
     const uint8_t *toep;        // [15][2][5120] banded Toeplitz byte planes of the tap rows (front_tc_build_toeplitz)
     int n_tiles;
     int seg_bounds[9];          // filled by launch_front_tc: block range of every time segment
+    int any_sam;                // a SAM tile exists: its carrier loop is sequential over the whole call, one segment
 };
 void launch_front_tc(const FrontArgs &a, const FrontTcTables &tb, cudaStream_t st);
 size_t front_tc_toeplitz_bytes();

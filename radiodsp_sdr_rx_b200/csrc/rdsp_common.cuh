@@ -16,6 +16,16 @@
 #define RDSP_LMS_NTAPS  96
 #define RDSP_N_DEMOD    5
 #define RDSP_N_FILTER   5
+#define RDSP_DEMOD_AM_  4            // AM envelope; RDSP_DEMOD_SAM_ shares its tap rows
+#define RDSP_DEMOD_SAM_ 5
+
+// SAM carrier loop (shim-defined, the same constants in oracle/rdsp_oracle.c): natural frequency 100 Hz, damping 0.707
+// at 44.1 kHz; pull-in limited to +-1 kHz; carrier-level tracker 100 ms
+#define RDSP_SAM_K1   0.020146f
+#define RDSP_SAM_K2   2.02995e-4f
+#define RDSP_SAM_WMAX 0.142476f
+#define RDSP_SAM_ADC  2.2673e-4f
+#define RDSP_SAM_PI   3.14159265358979f
 
 // per-channel parameters as the kernels see them (written by rdsp_gpu_set_mode)
 struct __align__(16) RdspChanParams {
@@ -32,7 +42,8 @@ struct __align__(16) RdspChanParams {
     uint8_t agc_mode;      // RDSP_AGC_*
     uint8_t notch_on;
     uint8_t nr_kind;       // RDSP_NR_* (0 when level == 0)
-    uint8_t pad[11];
+    uint8_t als_peak;      // K3 emits the NLMS estimate instead of the error
+    uint8_t pad[10];
 };
 static_assert(sizeof(RdspChanParams) == 48, "RdspChanParams layout");
 

@@ -83,6 +83,8 @@ struct rdsp_gpu {
     int fe_hist_cur = 0;
     bool front_tc = true;                      // RDSP_FRONT_IMPL=cuda-core selects k_front.cu (cross-check)
     uint8_t *d_toep = nullptr;                 // Toeplitz byte planes of the 15 tap rows
+    float *d_sam_state = nullptr;              // [C][4] SAM carrier loop
+    int any_sam = 0;
     int *d_tile_ch = nullptr; int4 *d_tile_rows = nullptr; int n_tiles = 0, tile_cap = 0;
     float *d_nc_coeff = nullptr, *d_nc_prev = nullptr, *d_nc_energy = nullptr; uint8_t *d_nc_first = nullptr;
     float *d_dn_coeff = nullptr, *d_dn_prev = nullptr, *d_dn_energy = nullptr; uint8_t *d_dn_first = nullptr;
@@ -137,7 +139,8 @@ bool has(const rdsp_gpu *h, uint32_t st) { return (h->cfg.stage_mask & st) != 0;
 
 int validate_params(const rdsp_chan_params_t *p, std::string &why)
 {
-    if (p->demod < 0 || p->demod >= RDSP_DEMOD_COUNT) { why = "demod out of range"; return RDSP_ERR_RANGE; }
+    if (p->demod < 0 || p->demod >= RDSP_DEMOD_MODES) { why = "demod out of range"; return RDSP_ERR_RANGE; }
+    if (p->als_peak < 0 || p->als_peak > 1) { why = "als_peak must be 0 or 1"; return RDSP_ERR_RANGE; }
     if (p->audio_filter < 0 || p->audio_filter >= RDSP_FILTER_COUNT) { why = "audio_filter out of range"; return RDSP_ERR_RANGE; }
     if (p->agc_mode < 0 || p->agc_mode >= RDSP_AGC_COUNT) { why = "agc_mode out of range"; return RDSP_ERR_RANGE; }
     if (p->notch_on < 0 || p->notch_on > 1) { why = "notch_on must be 0 or 1"; return RDSP_ERR_RANGE; }
@@ -179,6 +182,7 @@ void derive_params(rdsp_gpu *h, int ch)
     d.filter = (uint8_t)p.audio_filter;
     d.agc_mode = (uint8_t)p.agc_mode;
     d.notch_on = (uint8_t)p.notch_on;
+    d.als_peak = (uint8_t)p.als_peak;
     d.nr_kind = (uint8_t)(p.nr_level > 0 ? p.nr_kind : RDSP_NR_OFF);
 }
 
@@ -269,6 +273,8 @@ int sync_tables(rdsp_gpu *h)
     if (has(h, RDSP_STAGE_FRONTEND)) {
         // k_front_tc: channels that share their tap rows, in tiles of 128 MMA rows
         h->n_tiles = front_tc_build_tiles(h->dpar.data(), h->C, &h->taps[0][0], RDSP_FIR_TAPS, tile_ch, tile_rows);
+        h->any_sam = 0;
+        for (const int4 &r : tile_rows) if (r.w == 2) h->any_sam = 1;
         if (h->n_tiles > h->tile_cap) {
             if (h->d_tile_ch) cudaFree(h->d_tile_ch);
             if (h->d_tile_rows) cudaFree(h->d_tile_rows);
@@ -332,7 +338,7 @@ void prof_collect(rdsp_gpu *h)
 
 void free_all(rdsp_gpu *h)
 {
-    void *ptrs[] = {h->d_fe_hist2, h->d_toep, h->d_tile_ch, h->d_tile_rows,
+    void *ptrs[] = {h->d_fe_hist2, h->d_toep, h->d_tile_ch, h->d_tile_rows, h->d_sam_state,
                     h->d_par, h->d_list_notch, h->d_list_plain, h->d_list_dnr, h->d_taps, h->d_masks, h->d_tw, h->d_win256, h->d_win1024,
                     h->d_tw256, h->d_fe_hist, h->d_nc_coeff, h->d_nc_prev, h->d_nc_energy, h->d_nc_first, h->d_dn_coeff,
                     h->d_dn_prev, h->d_dn_energy, h->d_dn_first, h->d_agc_env, h->d_conv_last, h->d_nfloor, h->d_bq_state,
@@ -400,6 +406,7 @@ void rdsp_gpu_default_params(rdsp_chan_params_t *p)
     p->in_gain = 1.0f;                           // :133
     p->out_gain = 0.5f;                          // :134
     p->iq_balance = 1.020f;                      // :135
+    p->als_peak = 0;                             // SDR.setALSfilterNotch(), RDSP_controls.h:258
 }
 
 const char *rdsp_gpu_last_error(const rdsp_gpu_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -484,6 +491,7 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
         CKC(dalloc(&h->d_fe_hist, C * 3 * RDSP_BLK));
         CKC(dalloc(&h->d_fe_hist2, C * 3 * RDSP_BLK));
         CKC(dalloc(&h->d_toep, front_tc_toeplitz_bytes()));
+        CKC(dalloc(&h->d_sam_state, C * 4));
         if (const char *e = getenv("RDSP_FRONT_IMPL")) h->front_tc = !(e[0] == 'c' || e[0] == 'C');
         if (const char *e = getenv("RDSP_TIMELINE")) h->timeline = e[0] == '1';
         CKC(dalloc(&h->d_mid_a, T * C * RDSP_BLK));
@@ -709,8 +717,11 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
             h->fe_hist_cur ^= 1;
             FrontTcTables tb{};
             tb.tile_ch = h->d_tile_ch; tb.tile_rows = h->d_tile_rows; tb.toep = h->d_toep; tb.n_tiles = h->n_tiles;
+            tb.any_sam = h->any_sam;
+            a.sam_state = h->d_sam_state;
             launch_front_tc(a, tb, s_front);
         } else {
+            if (h->any_sam) { h->err = "SAM is only built in the tensor-core front end (unset RDSP_FRONT_IMPL)"; return RDSP_ERR_STATE; }
             a.hist = h->fe_hist_cur ? h->d_fe_hist2 : h->d_fe_hist;
             launch_front(a, s_front);
         }
@@ -946,6 +957,14 @@ int rdsp_gpu_set_taps(rdsp_gpu_t *h, int kind, int index, const int16_t *taps, u
     if (!row || n_taps != RDSP_FIR_TAPS) { h->err = "tap table kind/index/length invalid"; return RDSP_ERR_RANGE; }
     memcpy(row, taps, RDSP_FIR_TAPS * sizeof(int16_t));
     h->taps_dirty = true;
+    return RDSP_OK;
+}
+
+int rdsp_gpu_design_bandpass(float lo_hz, float hi_hz, int16_t *taps, uint32_t n_taps)
+{
+    if (!taps || n_taps != RDSP_FIR_TAPS) return RDSP_ERR_INVALID;
+    if (!(lo_hz >= 0.0f && hi_hz > lo_hz && hi_hz <= 22050.0f)) return RDSP_ERR_RANGE;
+    rdsp_host::design_bandpass_hz((double)lo_hz, (double)hi_hz, taps);
     return RDSP_OK;
 }
 

@@ -74,7 +74,7 @@ public:
         case 2: newMode = "USB";  radio.setAudioFilter(RDSP_FILTER_2700); TuningOffset = radio.setDemodMode(RDSP_DEMOD_USB); newFilter = "2.7 kHz"; fndx = 2; break;
         case 3: newMode = "LSB";  radio.setAudioFilter(RDSP_FILTER_2700); TuningOffset = radio.setDemodMode(RDSP_DEMOD_LSB); newFilter = "2.7 kHz"; fndx = 2; break;
         case 4: newMode = "AM";   radio.setAudioFilter(RDSP_FILTER_AM);   TuningOffset = radio.setDemodMode(RDSP_DEMOD_AM); newFilter = "3.9 kHz"; fndx = 4; break;
-        case 5: newMode = "SAM";  radio.setAudioFilter(RDSP_FILTER_AM);   TuningOffset = radio.setDemodMode(RDSP_DEMOD_AM); newFilter = "3.9 kHz"; fndx = 4; break;   // SAM not built: plain AM
+        case 5: newMode = "SAM";  radio.setAudioFilter(RDSP_FILTER_AM);   TuningOffset = radio.setDemodMode(RDSP_DEMOD_SAM); newFilter = "3.9 kHz"; fndx = 4; break;
         case 6: newMode = "RTTY"; radio.setAudioFilter(RDSP_FILTER_2100); TuningOffset = radio.setDemodMode(RDSP_DEMOD_USB); newFilter = "2.1 kHz"; fndx = 1; break;
         }
         mndx = (mndx == 6) ? 0 : mndx + 1;

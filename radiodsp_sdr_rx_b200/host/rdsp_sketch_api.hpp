@@ -26,7 +26,7 @@ namespace rdsp {
 
 // the reference's enumerators
 enum DemodMode { LSBmode = RDSP_DEMOD_LSB, USBmode = RDSP_DEMOD_USB, CW_LSBmode = RDSP_DEMOD_CW_LSB,
-                 CW_USBmode = RDSP_DEMOD_CW_USB, AMmode = RDSP_DEMOD_AM };
+                 CW_USBmode = RDSP_DEMOD_CW_USB, AMmode = RDSP_DEMOD_AM, SAMmode = RDSP_DEMOD_SAM };
 enum AudioFilter { audioCW = RDSP_FILTER_CW, audio2100 = RDSP_FILTER_2100, audio2700 = RDSP_FILTER_2700,
                    audio3100 = RDSP_FILTER_3100, audioAM = RDSP_FILTER_AM };
 enum AGCMode { AGCoff = RDSP_AGC_OFF, AGCfast = RDSP_AGC_FAST, AGCmedium = RDSP_AGC_MEDIUM, AGCslow = RDSP_AGC_SLOW };
@@ -85,7 +85,8 @@ public:
     void setAGCmode(AGCMode m) { agc_mode_ = m; apply_agc(); }
     void enableALSfilter() { auto p = b_.get(ch_); p.notch_on = 1; b_.set(ch_, p); }
     void disableALSfilter() { auto p = b_.get(ch_); p.notch_on = 0; b_.set(ch_, p); }
-    void setALSfilterNotch() {}
+    void setALSfilterNotch() { auto p = b_.get(ch_); p.als_peak = 0; b_.set(ch_, p); }
+    void setALSfilterPeak() { auto p = b_.get(ch_); p.als_peak = 1; b_.set(ch_, p); }
     void setALSfilterAdaptive() {}
     void disableNoiseBlanker() {}
     void setInputGain(float g) { auto p = b_.get(ch_); p.in_gain = g; b_.set(ch_, p); }

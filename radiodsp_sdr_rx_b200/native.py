@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "librdsp_gpu.so")
 
 BLK = 128
 
-DEMOD_LSB, DEMOD_USB, DEMOD_CW_LSB, DEMOD_CW_USB, DEMOD_AM = range(5)
+DEMOD_LSB, DEMOD_USB, DEMOD_CW_LSB, DEMOD_CW_USB, DEMOD_AM, DEMOD_SAM = range(6)
 FILTER_CW, FILTER_2100, FILTER_2700, FILTER_3100, FILTER_AM = range(5)
 AGC_OFF, AGC_FAST, AGC_MEDIUM, AGC_SLOW = range(4)
 NR_OFF, NR_LMS, NR_SPECTRAL = range(3)
@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "rdsp_gpu_default_config", "rdsp_gpu_default_params", "rdsp_gpu_create", "rdsp_gpu_destroy",
     "rdsp_gpu_set_mode", "rdsp_gpu_get_mode", "rdsp_gpu_process_block", "rdsp_gpu_process_blocks",
     "rdsp_gpu_synchronize", "rdsp_gpu_stream_join", "rdsp_gpu_set_stream", "rdsp_gpu_read_spectrum", "rdsp_gpu_read_audio_spectrum",
-    "rdsp_gpu_read_panadapter", "rdsp_gpu_read_waterfall", "rdsp_gpu_set_taps", "rdsp_gpu_get_taps", "rdsp_gpu_set_mask", "rdsp_gpu_get_mask",
+    "rdsp_gpu_read_panadapter", "rdsp_gpu_read_waterfall", "rdsp_gpu_set_taps", "rdsp_gpu_get_taps", "rdsp_gpu_design_bandpass", "rdsp_gpu_set_mask", "rdsp_gpu_get_mask",
     "rdsp_gpu_read_debug_f32", "rdsp_gpu_kernel_launches", "rdsp_gpu_profile", "rdsp_gpu_profile_read",
     "rdsp_gpu_last_error", "rdsp_gpu_version",
 ]
@@ -53,6 +53,7 @@ class Params(C.Structure):
         ("notch_on", C.c_int32), ("notch_level", C.c_int32), ("nr_kind", C.c_int32),
         ("nr_level", C.c_int32), ("pbt_lo_hz", C.c_float), ("pbt_hi_hz", C.c_float),
         ("in_gain", C.c_float), ("out_gain", C.c_float), ("iq_balance", C.c_float),
+        ("als_peak", C.c_int32),
     ]
 
     def copy(self, **kw):
@@ -91,6 +92,7 @@ def lib():
         L.rdsp_gpu_read_waterfall.argtypes = [vp, u32, u32, vp, vp]
         L.rdsp_gpu_set_taps.argtypes = [vp, i32, i32, vp, u32]
         L.rdsp_gpu_get_taps.argtypes = [vp, i32, i32, vp, u32]
+        L.rdsp_gpu_design_bandpass.argtypes = [C.c_float, C.c_float, vp, u32]
         L.rdsp_gpu_set_mask.argtypes = [vp, u32, u32, vp]
         L.rdsp_gpu_get_mask.argtypes = [vp, u32, vp]
         L.rdsp_gpu_read_debug_f32.argtypes = [vp, u32, u32, u32, vp]
@@ -123,6 +125,15 @@ def default_params(**kw) -> Params:
     for k, v in kw.items():
         setattr(p, k, v)
     return p
+
+
+def design_bandpass(lo_hz: float, hi_hz: float) -> np.ndarray:
+    """129 q15 band-pass taps for an arbitrary audio band (audioWSPR: 1400 .. 1600 Hz); no device needed"""
+    t = np.zeros(129, np.int16)
+    rc = lib().rdsp_gpu_design_bandpass(lo_hz, hi_hz, t.ctypes.data, 129)
+    if rc != 0:
+        raise ValueError(f"rdsp_gpu_design_bandpass({lo_hz}, {hi_hz}) failed: {rc}")
+    return t
 
 
 def _addr(x):

@@ -59,8 +59,11 @@ class SDRChannel:
     def disableALSfilter(self):
         self._update(notch_on=0)
 
-    def setALSfilterNotch(self):      # the only ALS flavour this build has
-        pass
+    def setALSfilterNotch(self):
+        self._update(als_peak=0)
+
+    def setALSfilterPeak(self):
+        self._update(als_peak=1)
 
     def setALSfilterAdaptive(self):
         pass

@@ -48,7 +48,7 @@ def synth_iq(channels, n_blocks: int, demod, first_block: int = 0, interferer=Fa
              snr_db: float = 10.0, seed: int = SEED) -> np.ndarray:
     """int16 [n_blocks, len(channels), 128, 2] for the given absolute channel ids.
 
-    demod: int or per-channel sequence of RDSP_DEMOD_* (0 LSB, 1 USB, 2 CW_LSB, 3 CW_USB, 4 AM)
+    demod: int or per-channel sequence of RDSP_DEMOD_* (0 LSB, 1 USB, 2 CW_LSB, 3 CW_USB, 4 AM, 5 SAM)
     interferer: bool or per-channel sequence
     """
     channels = np.asarray(channels, dtype=np.int64).reshape(-1)
@@ -67,7 +67,7 @@ def synth_iq(channels, n_blocks: int, demod, first_block: int = 0, interferer=Fa
     side = np.where((demod == 0) | (demod == 2), -1.0, 1.0)[:, None]  # lower side for LSB / CW_LSB
     ssb = (demod == 0) | (demod == 1)
     cw = (demod == 2) | (demod == 3)
-    am = demod == 4
+    am = (demod == 4) | (demod == 5)                                  # AM and SAM share the AM scene
     if ssb.any():
         tones = ((400.0, 1.0), (700.0, 0.8), (1100.0, 0.6), (1700.0, 0.5), (2300.0, 0.4))
         acc = np.zeros((nc, ns), np.complex128)

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(rd):
 
 def test_struct_layouts_match_header(rd):
     from radiodsp_sdr_rx_b200 import native
-    assert C.sizeof(native.Config) == 68 and C.sizeof(native.Params) == 48
+    assert C.sizeof(native.Config) == 68 and C.sizeof(native.Params) == 52
     cfg = rd.default_config()
     assert cfg.struct_size == C.sizeof(native.Config)
     assert (cfg.n_channels, cfg.stage_mask, cfg.spec256_naverage) == (1, rd.STAGE_ALL, 30)
@@ -37,7 +37,7 @@ def test_struct_layouts_match_header(rd):
     assert (p.demod, p.audio_filter, p.agc_mode, p.notch_on, p.nr_kind, p.nr_level) == (
         rd.DEMOD_LSB, rd.FILTER_2700, rd.AGC_MEDIUM, 0, rd.NR_OFF, 0)
     assert (p.pbt_lo_hz, p.pbt_hi_hz, p.in_gain, p.out_gain) == (300.0, 4000.0, 1.0, 0.5)
-    assert abs(p.iq_balance - 1.02) < 1e-6
+    assert abs(p.iq_balance - 1.02) < 1e-6 and p.als_peak == 0
 
 
 def test_oracle_and_product_defaults_agree(rd, po):
@@ -107,3 +107,21 @@ def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(tmp_path, rd):
         assert r.returncode == 0, r.stderr
     else:
         assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+def test_design_bandpass_needs_no_device():
+    """rdsp_gpu_design_bandpass: the designer of the default band-pass bank for any band (audioWSPR = 1400..1600 Hz,
+    RDSP_controls.h:392-402); runs on the host, reproduces the preset rows of the oracle's tap bank"""
+    import numpy as np
+    import radiodsp_sdr_rx_b200 as rd
+    from radiodsp_sdr_rx_b200 import native
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import pyoracle as po
+    assert np.array_equal(native.design_bandpass(150.0, 2700.0), po.get_taps(po.TAPS_BANDPASS, po.FILTER_2700))
+    w = native.design_bandpass(1400.0, 1600.0).astype(np.float64) / 32768.0
+    f = np.fft.rfft(w, 8192)
+    gain = lambda hz: abs(f[int(round(hz * 8192 / 44100.0))])
+    assert abs(gain(1500.0) - 1.0) < 0.02 and gain(200.0) < 0.01 and gain(3000.0) < 0.01   # 129 taps: a 1.4 kHz transition band
+    with __import__("pytest").raises(ValueError):
+        native.design_bandpass(3000.0, 1000.0)

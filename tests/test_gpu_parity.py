@@ -142,6 +142,57 @@ def test_frontend_tensor_core_wraps_like_the_cuda_core_kernel(rd, po, nc, nblock
     assert np.array_equal(g_tc[:, sub], o)
 
 
+def test_sam_matches_the_oracle(rd, po):
+    """SAMmode: carrier PLL + coherent detection inside k_front_tc's epilogue (sequential over the samples of a row),
+    f32 loop against the oracle's libm loop: demodulated q15 within 2 LSB, relative RMS <= 1e-4 of full scale signal"""
+    nc, nb = 140, 40                                        # 140 SAM channels: one full tile and a ragged one
+    n = np.arange(nb * 128)
+    rng = np.random.default_rng(5)
+    iq = np.zeros((nb, nc, 128, 2), np.int16)
+    for c in range(nc):
+        off, ph, mod = rng.uniform(-300, 300), rng.uniform(0, 6.28), rng.uniform(300, 2500)
+        env = 5000 * (1 + 0.6 * np.cos(2 * np.pi * mod * n / 44100.0))
+        z = env * np.exp(1j * (2 * np.pi * off * n / 44100.0 + ph)) + rng.normal(0, 200, n.size) + 1j * rng.normal(0, 200, n.size)
+        iq[:, c, :, 0] = np.rint(z.real).reshape(nb, 128); iq[:, c, :, 1] = np.rint(z.imag).reshape(nb, 128)
+    params = [po.default_params(demod=po.DEMOD_SAM, audio_filter=po.FILTER_AM) for _ in range(nc)]
+    params[3] = po.default_params(demod=po.DEMOD_AM, audio_filter=po.FILTER_AM)          # a neighbour in another class
+    g_out, _, o_out, _, _, _ = run_both(rd, po, rd.STAGE_FRONTEND, params, iq, blocks_per_call=8)
+    assert np.array_equal(g_out[:, 3], o_out[:, 3])                                         # the AM channel stays bit-exact
+    d = g_out.astype(np.int32) - o_out
+    assert np.abs(d).max() <= 2, np.abs(d).max()
+    assert rel_rms(g_out, o_out) <= REL_RMS_TOL
+    assert abs(synth.snr_db(o_out, g_out)) > 60.0
+
+
+def test_als_peak_matches_the_oracle(rd, po):
+    nc = 12
+    iq = synth.synth_iq(np.arange(nc), 30, 3, interferer=True)
+    params = [po.default_params(demod=po.DEMOD_CW_USB, audio_filter=po.FILTER_CW, notch_on=1, als_peak=c % 2) for c in range(nc)]
+    g_out, g_f32, o_out, o_f32, _, _ = run_both(rd, po, rd.STAGE_FRONTEND | rd.STAGE_NOTCH | rd.STAGE_AGC, params, iq, blocks_per_call=6)
+    assert rel_rms(g_f32, o_f32) <= REL_RMS_TOL
+    assert np.abs(g_out.astype(np.int32) - o_out).max() <= 1
+    assert not np.array_equal(g_out[:, 0], g_out[:, 1])      # notch and peak differ
+
+
+def test_wspr_band_through_set_taps(rd, po):
+    """audioWSPR (RDSP_controls.h:392-402): rdsp_gpu_design_bandpass(1400, 1600) loaded into a preset row"""
+    from radiodsp_sdr_rx_b200 import native
+    t = native.design_bandpass(1400.0, 1600.0)
+    iq = synth.synth_iq([1, 2, 3], 12, [1, 1, 1])
+    bank = make_bank(rd, 3, rd.STAGE_FRONTEND)
+    bank.set_mode(0, 3, rd.default_params(demod=rd.DEMOD_USB, audio_filter=rd.FILTER_CW))
+    bank.set_taps(rd.TAPS_BANDPASS, rd.FILTER_CW, t)
+    g = bank.process_host(iq)
+    saved = po.get_taps(2, 0)
+    try:
+        po.lib().rdsp_oracle_set_taps(2, 0, t.ctypes.data)
+        o, _ = po.process_bank(po.default_config(stage_mask=po.STAGE_FRONTEND),
+                               po.default_params(demod=po.DEMOD_USB, audio_filter=po.FILTER_CW), iq)
+    finally:
+        po.lib().rdsp_oracle_set_taps(2, 0, saved.ctypes.data)
+    assert np.array_equal(g, o)
+
+
 # ------------------------------------------------------------------------------------------ K3, K4
 
 def test_notch_and_agc_f32_parity(rd, po):

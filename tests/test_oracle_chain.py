@@ -49,6 +49,37 @@ def test_am_envelope_and_cw_filter(po):
     assert p700 > 5000 and p2500 < 1e-3 * p700
 
 
+def test_sam_locks_to_an_offset_carrier_where_the_envelope_detector_cannot_help(po):
+    """SAMmode (RDSP_controls.h:384-391): the carrier loop pulls in a carrier that is 40 Hz off tune and detects
+    coherently; the 1 kHz modulation comes out clean, and the loop frequency settles at the offset."""
+    cfg = po.default_config(stage_mask=po.STAGE_FRONTEND)
+    nb = 400                                                 # the carrier-level tracker (100 ms) needs ~1 s to settle
+    n = np.arange(nb * 128)
+    env = 6000 * (1 + 0.5 * np.cos(2 * np.pi * 1000 * n / FS))
+    car = np.exp(1j * (2 * np.pi * 40.0 * n / FS + 0.7))
+    iq = np.stack([np.rint(env * car.real), np.rint(env * car.imag)], -1).astype(np.int16).reshape(nb, 128, 2)
+    ch = po.OracleChan(cfg, po.default_params(demod=po.DEMOD_SAM, audio_filter=po.FILTER_AM, iq_balance=1.0))
+    out = ch.process(iq)
+    a = out[340:, :, 0].reshape(-1).astype(float)
+    assert synth.tone_snr_db(a - a.mean(), [1000.0]) > 40
+    assert abs(a.std() - 0.5 * 6000 / np.sqrt(2)) < 60        # the modulation through unity-gain filters
+    # a carrier-only input detects to (almost) nothing once the level tracker has settled
+    iq0 = np.stack([np.rint(6000 * car.real), np.rint(6000 * car.imag)], -1).astype(np.int16).reshape(nb, 128, 2)
+    quiet = po.OracleChan(cfg, po.default_params(demod=po.DEMOD_SAM, audio_filter=po.FILTER_AM, iq_balance=1.0)).process(iq0)
+    assert _rms(quiet[340:, :, 0]) < 30
+
+
+def test_als_peak_emits_the_estimate(po):
+    """ALS "peak": the notch stage emits what the NLMS predicts (the steady heterodyne) instead of the residue"""
+    cfg = po.default_config(stage_mask=po.STAGE_FRONTEND | po.STAGE_NOTCH)
+    sig = _tone_iq(-1500.0, 60, amp=6000)
+    off = po.OracleChan(cfg, po.default_params(notch_on=0, iq_balance=1.0)).process(sig)
+    notch = po.OracleChan(cfg, po.default_params(notch_on=1, iq_balance=1.0)).process(sig)
+    peak = po.OracleChan(cfg, po.default_params(notch_on=1, als_peak=1, iq_balance=1.0)).process(sig)
+    assert _rms(notch[40:, :, 0]) < 0.05 * _rms(off[40:, :, 0])
+    assert abs(_rms(peak[40:, :, 0]) / _rms(off[40:, :, 0]) - 1.0) < 0.05
+
+
 def test_q15_fir_wraps_and_saturates(po):
     """arm_fir_fast_q15 convention: 32-bit wrap-around accumulator, then SSAT(acc >> 15)"""
     L = po.lib()
