@@ -141,9 +141,11 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.rows, self.proc = [], None
+        if os.environ.get("RDSP_BENCH_NO_CLOCKS"):     # experiments only: rule the sampler out as a disturbance
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -345,12 +347,12 @@ def run_b200(args):
     barrier()
     t_wall1 = time.time()
     launches = bank.kernel_launches - launches0
-    # the timed region of a short run can fall between two nvidia-smi samples (20 ms period): keep the SAME load up,
+    # the timed region of a short run can fall between two nvidia-smi samples (200 ms period; faster polling measurably slows kernel launches): keep the SAME load up,
     # untimed, until at least three samples were taken under it, and report over [start of the timed region, end of load]
     t_load1 = t_wall1
     extended = 0
     if sampler.proc is not None:
-        deadline = time.time() + 2.0
+        deadline = time.time() + 3.0
         i = 0
         while time.time() < deadline:
             n_in = sum(1 for t, _ in sampler.rows if t_wall0 <= t <= time.time())
@@ -431,6 +433,8 @@ def run_b200(args):
             "value": value, "unit": "MS/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "q15+f32", "data": "synthetic",
+            "ms_step_min_median_max": [float(np.min(ms_steps)), float(np.median(ms_steps)), float(np.max(ms_steps))],
+            **({"ms_steps": [round(float(x), 3) for x in ms_steps]} if os.environ.get("RDSP_BENCH_STEPS") else {}),
             "config": {"workload": f"{wl}: {desc}", "channels_per_gpu": C_, "channels_total": world * C_, "blocks_per_call": T, "pipeline_chunks": args.pipeline_chunks or "auto",
                        "block_samples": BLK, "sample_rate_hz": FS, "sharding": "contiguous channel ranges, no collective on the hot path",
                        "l2": "256 MiB memset between timed steps; per-step CUDA events summed",

@@ -148,6 +148,9 @@ typedef struct {
     float   iq_balance;          /* default 1.020 RadioDSP_SDR_RX.ino:135 */
     int32_t als_peak;            /* 0: SDR.setALSfilterNotch() (RDSP_controls.h:258, the notch emits the NLMS error),
                                     1: ALS "peak" (backup sketch: the notch stage emits the NLMS estimate); default 0 */
+    int32_t nb_on;               /* SDR.enableNoiseBlanker / disableNoiseBlanker, RadioDSP_SDR_RX.ino:129-131; default 0 */
+    float   nb_threshold_db;     /* SDR.setNoiseBlankerThresholdDb(20.0), RadioDSP_SDR_RX.ino:130; 0 .. 40 dB over the
+                                    running IQ magnitude (DESIGN.md "Noise blanker"); default 20 */
 } rdsp_chan_params_t;
 
 /* fill *cfg / *p with the reference's setup() defaults */

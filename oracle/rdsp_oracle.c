@@ -222,6 +222,8 @@ struct rdsp_oracle_chan {
     int16_t hist_i[BLK], hist_q[BLK], hist_d[BLK];
     /* SAM carrier PLL: phase, frequency (rad/sample), carrier level */
     float sam_phi, sam_omega, sam_dc;
+    /* noise blanker: running IQ magnitude (|I| + |Q| averaged over 32-sample chunks) */
+    int32_t nb_ref;
     /* K3 notch */
     nlms_t notch;
     int notch_old_level;
@@ -269,6 +271,8 @@ void rdsp_oracle_default_params(rdsp_chan_params_t *p)
     p->out_gain = 0.5f;
     p->iq_balance = 1.020f;
     p->als_peak = 0;
+    p->nb_on = 0;
+    p->nb_threshold_db = 20.0f;
 }
 
 void rdsp_oracle_default_config(rdsp_gpu_config_t *cfg)
@@ -361,6 +365,23 @@ static void stage_frontend(rdsp_oracle_chan_t *c, const int16_t *iq, int16_t *au
     for (int n = 0; n < BLK; n++) {
         xi[n] = mix_gain(iq[2 * n], c->mult_i);
         xq[n] = mix_gain(iq[2 * n + 1], c->mult_q);
+    }
+    if (c->par.nb_on) {
+        /* Noise blanker (SDR.enableNoiseBlanker, RadioDSP_SDR_RX.ino:129-131; AudioSDR absent, shim-defined, integer):
+         * a frame whose |I| + |Q| exceeds threshold x the running magnitude is zeroed; the running magnitude is the mean
+         * of the (clipped) magnitudes of a 32-sample chunk, smoothed over 8 chunks; the first chunk only seeds it. */
+        const uint32_t mult_q8 = (uint32_t)(pow(10.0, (double)c->par.nb_threshold_db / 20.0) * 256.0 + 0.5);
+        for (int k = 0; k < BLK; k += 32) {
+            const int armed = c->nb_ref > 0;
+            const uint32_t thr = armed ? (uint32_t)(((uint32_t)c->nb_ref * mult_q8) >> 8) : 0xFFFFFFFFu;
+            uint32_t sum = 0;
+            for (int n = k; n < k + 32; n++) {
+                const uint32_t mag = (uint32_t)abs((int)xi[n]) + (uint32_t)abs((int)xq[n]);
+                if (mag > thr) { xi[n] = 0; xq[n] = 0; sum += thr; } else sum += mag;
+            }
+            const int32_t cm = (int32_t)(sum >> 5);
+            c->nb_ref = armed ? c->nb_ref + ((cm - c->nb_ref) >> 3) : cm;
+        }
     }
     oracle_fir_q15(g_hil_i[m], NTAPS, c->hist_i, xi, a, BLK);
     oracle_fir_q15(g_hil_q[m], NTAPS, c->hist_q, xq, b, BLK);

@@ -49,7 +49,7 @@ constexpr int OFF_TAPS = 6 * PLANE_B;                         // [set 0..2][plan
 constexpr int OFF_STAGE = OFF_TAPS + 3 * TOEP_SET_B;          // loader staging [2][4 warps][8 items][32 lanes][16 B]
 constexpr int STAGE_B = 4 * 8 * 32 * 16;                      // 16384 per buffer
 constexpr int OFF_META = OFF_STAGE + 2 * STAGE_B;             // per-row parameters, barriers, sqrt seed table
-constexpr int META_B = ROWS * 16 + 128 + 80;
+constexpr int META_B = ROWS * 16 + 128 + 80 + ROWS * 16;
 constexpr int SMEM_B = OFF_META + META_B;
 static_assert(SMEM_B <= 227 * 1024, "shared memory budget");
 
@@ -152,6 +152,11 @@ struct TcSmem {
     __device__ __forceinline__ uint64_t *bars() const { return reinterpret_cast<uint64_t *>(base + OFF_META + ROWS * 16); }
     __device__ __forceinline__ uint32_t *tmem_ptr() const { return reinterpret_cast<uint32_t *>(base + OFF_META + ROWS * 16 + 96); }
     __device__ __forceinline__ uint16_t *sqrt_guess() const { return reinterpret_cast<uint16_t *>(base + OFF_META + ROWS * 16 + 128); }
+    // noise blanker, per row: Q8 threshold factor (0 = off), running magnitude, threshold of the current chunk, chunk sum
+    __device__ __forceinline__ uint32_t *nb_mult() const { return reinterpret_cast<uint32_t *>(base + OFF_META + ROWS * 16 + 208); }
+    __device__ __forceinline__ int32_t *nb_ref() const { return reinterpret_cast<int32_t *>(base + OFF_META + ROWS * 20 + 208); }
+    __device__ __forceinline__ uint32_t *nb_thr() const { return reinterpret_cast<uint32_t *>(base + OFF_META + ROWS * 24 + 208); }
+    __device__ __forceinline__ uint32_t *nb_sum() const { return reinterpret_cast<uint32_t *>(base + OFF_META + ROWS * 28 + 208); }
 };
 
 // ---- loader -------------------------------------------------------------------------------------------------------
@@ -173,6 +178,7 @@ __device__ __forceinline__ void fetch_chunk(const TcSmem &s, const FrontArgs &a,
     cp_async_commit();
 }
 
+template <bool NB>
 __device__ __forceinline__ void split_chunk(const TcSmem &s, int buf, int slice, int lw, int lane)
 {
     const int rr = lane >> 2, q = lane & 3;
@@ -184,8 +190,24 @@ __device__ __forceinline__ void split_chunk(const TcSmem &s, int buf, int slice,
         uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
         const int mi = s.row_mi()[row], mq = s.row_mq()[row];
         const int mih = mi >> 16, mil = mi & 0xFFFF, mqh = mq >> 16, mql = mq & 0xFFFF;
+        if (NB) {
+            // noise blanker (oracle/rdsp_oracle.c:stage_frontend): zero the frames above the chunk's threshold, feed
+            // the clipped magnitudes into the row's chunk sum
+            const uint32_t thr = s.nb_thr()[row];
+            uint32_t sum = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) w[j] = mk16(mix_gain_tc(lo16(w[j]), mih, mil), mix_gain_tc(hi16(w[j]), mqh, mql));
+            for (int j = 0; j < 4; j++) {
+                const int32_t xi = mix_gain_tc(lo16(w[j]), mih, mil), xq = mix_gain_tc(hi16(w[j]), mqh, mql);
+                const uint32_t mag = (uint32_t)abs(xi) + (uint32_t)abs(xq);
+                const bool hit = mag > thr;
+                sum += hit ? thr : mag;
+                w[j] = hit ? 0u : mk16(xi, xq);
+            }
+            if (s.nb_mult()[row]) atomicAdd(&s.nb_sum()[row], sum);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) w[j] = mk16(mix_gain_tc(lo16(w[j]), mih, mil), mix_gain_tc(hi16(w[j]), mqh, mql));
+        }
         // word = [I lo, I hi, Q lo, Q hi]; 4 x 4 byte transpose
         const uint32_t i01 = prmt(w[0], w[1], 0x5140), q01 = prmt(w[0], w[1], 0x7362);
         const uint32_t i23 = prmt(w[2], w[3], 0x5140), q23 = prmt(w[2], w[3], 0x7362);
@@ -195,6 +217,23 @@ __device__ __forceinline__ void split_chunk(const TcSmem &s, int buf, int slice,
         *reinterpret_cast<uint32_t *>(s.ring(1, 0) + off) = prmt(q01, q23, 0x5410);
         *reinterpret_cast<uint32_t *>(s.ring(1, 1) + off) = prmt(q01, q23, 0x7632);
     }
+}
+
+// after every loader thread has added its frames of a chunk: thread r closes the chunk of row r (running magnitude,
+// next threshold); two named barriers among the 128 loader threads fence the exchange
+__device__ __forceinline__ void nb_close_chunk(const TcSmem &s, int r)
+{
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const uint32_t mult = s.nb_mult()[r];
+    if (mult) {
+        int32_t ref = s.nb_ref()[r];
+        const int32_t cm = (int32_t)(s.nb_sum()[r] >> 5);
+        ref = ref > 0 ? ref + ((cm - ref) >> 3) : cm;
+        s.nb_ref()[r] = ref;
+        s.nb_thr()[r] = ref > 0 ? (uint32_t)(((uint32_t)ref * mult) >> 8) : 0xFFFFFFFFu;
+        s.nb_sum()[r] = 0u;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
 // ---- delay-line state <-> ring, all warps -------------------------------------------------------------------------
@@ -270,7 +309,7 @@ __device__ __forceinline__ void epilogue1(const TcSmem &s, uint32_t tmem_row, in
             } else if (MODE == 2) {
                 // oracle/rdsp_oracle.c:stage_frontend, RDSP_DEMOD_SAM
                 float sn, cs;
-                sincosf(sam.phi, &sn, &cs);
+                __sincosf(sam.phi, &sn, &cs);                               // |phi| <= pi: 2^-21 absolute, no slow path / stack
                 const float fa = (float)ya, fb = (float)yb;
                 const float re = fa * cs + fb * sn, im = fb * cs - fa * sn;
                 const float err = (re == 0.0f && im == 0.0f) ? 0.0f : atan2f(im, re);
@@ -348,6 +387,9 @@ __device__ unsigned long long g_tc_cta[4096][2];
 //   m2_done[2]   MMA -> E2, E1      band-pass MMAs of chunk c retired: acc2 valid, D slice c%6 free     (commit)
 //   e2_done      E2 -> MMA          acc2 drained                                                    (128 arrivals)
 // The band-pass MMAs of chunk c-1 are issued after the Hilbert MMAs of chunk c, so epilogue 1 overlaps tensor work.
+// WITH_SAM: the instantiation that carries the SAM detector (atan2f and the loop state cost 15 registers and a stack
+// frame; with them in the common kernel every step of cfg5 was 17 % slower although no channel used SAM).
+template <bool WITH_SAM>
 __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTables tb)
 {
     extern __shared__ __align__(128) uint8_t s_raw[];
@@ -379,6 +421,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
         s.row_mq()[row] = ch >= 0 ? p.mult_q : 65536;
         s.row_usb()[row] = (p.demod == 1 || p.demod == 3) ? 1 : 0;
         if (row < 33) s.sqrt_guess()[row] = c_sqrt_guess[row];
+        const uint32_t nbm = ch >= 0 ? p.nb_mult_q8 : 0u;
+        const int32_t nbr = nbm ? a.nb_ref[ch] : 0;
+        s.nb_mult()[row] = nbm;
+        s.nb_ref()[row] = nbr;
+        s.nb_thr()[row] = (nbm && nbr > 0) ? (uint32_t)(((uint32_t)nbr * nbm) >> 8) : 0xFFFFFFFFu;
+        s.nb_sum()[row] = 0u;
     }
 #pragma unroll 1
     for (int k = 0; k < 3; k++) {
@@ -406,7 +454,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
             for (int cq = 0; cq < 4; cq++) {
                 fetch_chunk(s, a, t0 - 1, cq, cq & 1, warp - W_LD, lane);
                 cp_async_wait<0>();
-                split_chunk(s, cq & 1, cq, warp - W_LD, lane);
+                split_chunk<false>(s, cq & 1, cq, warp - W_LD, lane);      // (a call with blanked channels is one segment)
             }
         } else if (threadIdx.x < ROWS) {
             // demodulated line: zero history (its warm-up block only has to flush the band-pass through)
@@ -434,6 +482,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
     if (warp >= W_LD && warp < W_LD + 4) {
         // ===== loader =====
         const int lw = warp - W_LD;
+        bool tile_nb = false;                                              // any blanked row in this tile (CTA-uniform)
+        for (int r = 0; r < ROWS; r++) tile_nb |= s.nb_mult()[r] != 0u;
         fetch_chunk(s, a, t0, 0, 0, lw, lane);
         TCP_BEGIN;
 #pragma unroll 1
@@ -447,10 +497,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
             // slice (c+4)%6 was the oldest slice of chunk c-2
             if (c >= 2) mbar_wait(bar(B_M1_DONE + (c & 1)), ((c - 2) >> 1) & 1);
             if (lw == 0) TCP(0);
-            split_chunk(s, c & 1, (c + 4) % SLICES, lw, lane);
+            if (tile_nb) {
+                split_chunk<true>(s, c & 1, (c + 4) % SLICES, lw, lane);
+                nb_close_chunk(s, lw * 32 + lane);
+            } else {
+                split_chunk<false>(s, c & 1, (c + 4) % SLICES, lw, lane);
+            }
             fence_async_smem();
             mbar_arrive(bar(B_IN_FULL + (c & 1)));
             if (lw == 0) TCP(1);
+        }
+        if (tile_nb) {
+            const int r = lw * 32 + lane, ch = s.row_ch()[r];
+            if (ch >= 0 && s.nb_mult()[r]) a.nb_ref[ch] = s.nb_ref()[r];
         }
     } else if (warp == W_MMA) {
         // ===== MMA issue =====
@@ -495,7 +554,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
         const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
         const int ch1 = s.row_ch()[row];
         SamState sam{0.f, 0.f, 0.f};
-        if (dmode == 2 && ch1 >= 0) {
+        if (WITH_SAM && dmode == 2 && ch1 >= 0) {
             const float4 st = *reinterpret_cast<const float4 *>(a.sam_state + (size_t)ch1 * 4);
             sam.phi = st.x; sam.omega = st.y; sam.dc = st.z;
         }
@@ -509,14 +568,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
             if (warp == 0) TCP(9);
             tc_fence_after();
             if (dmode == 1) epilogue1<1>(s, tmem_row + (c & 1) * TM_ACC1B, row, (c + 4) % SLICES, usb, sam);
-            else if (dmode == 2) epilogue1<2>(s, tmem_row + (c & 1) * TM_ACC1B, row, (c + 4) % SLICES, usb, sam);
+            else if (WITH_SAM && dmode == 2) epilogue1<2>(s, tmem_row + (c & 1) * TM_ACC1B, row, (c + 4) % SLICES, usb, sam);
             else epilogue1<0>(s, tmem_row + (c & 1) * TM_ACC1B, row, (c + 4) % SLICES, usb, sam);
             tc_fence_before();
             fence_async_smem();
             mbar_arrive(bar(B_E1_DONE + (c & 1)));
             if (warp == 0) TCP(10);
         }
-        if (dmode == 2 && ch1 >= 0) *reinterpret_cast<float4 *>(a.sam_state + (size_t)ch1 * 4) = make_float4(sam.phi, sam.omega, sam.dc, 0.f);
+        if (WITH_SAM && dmode == 2 && ch1 >= 0) *reinterpret_cast<float4 *>(a.sam_state + (size_t)ch1 * 4) = make_float4(sam.phi, sam.omega, sam.dc, 0.f);
     } else {
         // ===== epilogue 2 =====
         const int row = threadIdx.x - W_E2 * 32;
@@ -654,7 +713,8 @@ void launch_front_tc(const FrontArgs &a_in, const FrontTcTables &tb_in, cudaStre
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_front_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B);
+        cudaFuncSetAttribute(k_front_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B);
+        cudaFuncSetAttribute(k_front_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B);
     }
     FrontArgs a = a_in;
     FrontTcTables tb = tb_in;
@@ -662,5 +722,6 @@ void launch_front_tc(const FrontArgs &a_in, const FrontTcTables &tb_in, cudaStre
     int S = 1;
     front_tc_plan_segments(tb.n_tiles, a.T, n_sm, tb.seg_bounds, &S);
     if (S > 1 && (a.hist_out == a.hist || tb.any_sam)) { S = 1; tb.seg_bounds[0] = 0; tb.seg_bounds[1] = a.T; }   // in-place state / SAM loop: one segment
-    k_front_tc<<<dim3(tb.n_tiles, S), NTHREADS, SMEM_B, st>>>(a, tb);
+    if (tb.sam_tiles) k_front_tc<true><<<dim3(tb.n_tiles, S), NTHREADS, SMEM_B, st>>>(a, tb);
+    else k_front_tc<false><<<dim3(tb.n_tiles, S), NTHREADS, SMEM_B, st>>>(a, tb);
 }

@@ -15,6 +15,7 @@ struct FrontArgs {
     int16_t *hist_out;          // k_front_tc only: where the new delay lines go (nullptr = in place; a second buffer lets
                                 // the blocks of a call be cut into concurrent time segments)
     float *sam_state;           // [C][4] SAM carrier loop: phase, frequency, carrier level, pad (k_front_tc only)
+    int32_t *nb_ref;            // [C] noise blanker: running IQ magnitude (k_front_tc only)
     const RdspChanParams *par;  // [C]
     const int32_t *taps;        // [15][132]: hilbert_i[5], hilbert_q[5], bandpass[5]
     int C, T;
@@ -28,7 +29,8 @@ struct FrontTcTables {
     const uint8_t *toep;        // [15][2][5120] banded Toeplitz byte planes of the tap rows (front_tc_build_toeplitz)
     int n_tiles;
     int seg_bounds[9];          // filled by launch_front_tc: block range of every time segment
-    int any_sam;                // a SAM tile exists: its carrier loop is sequential over the whole call, one segment
+    int sam_tiles;              // a SAM tile exists: launch the instantiation that carries the SAM detector
+    int any_sam;                // a SAM tile or a noise-blanked channel exists: their state is sequential over the whole call, one segment
 };
 void launch_front_tc(const FrontArgs &a, const FrontTcTables &tb, cudaStream_t st);
 size_t front_tc_toeplitz_bytes();

@@ -37,13 +37,14 @@ struct __align__(16) RdspChanParams {
     float   agc_alpha_d;   // K4 decay coefficient of the selected AGC mode
     float   nr_spec_level; // K8 iNRLevel
     int32_t mask_id;       // K5 row of the mask table
+    uint32_t nb_mult_q8;   // noise blanker threshold as a Q8 factor on the running IQ magnitude (0: blanker off)
     uint8_t demod;         // RDSP_DEMOD_*
     uint8_t filter;        // RDSP_FILTER_*
     uint8_t agc_mode;      // RDSP_AGC_*
     uint8_t notch_on;
     uint8_t nr_kind;       // RDSP_NR_* (0 when level == 0)
     uint8_t als_peak;      // K3 emits the NLMS estimate instead of the error
-    uint8_t pad[10];
+    uint8_t pad[6];
 };
 static_assert(sizeof(RdspChanParams) == 48, "RdspChanParams layout");
 

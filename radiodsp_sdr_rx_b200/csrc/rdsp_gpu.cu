@@ -84,7 +84,8 @@ struct rdsp_gpu {
     bool front_tc = true;                      // RDSP_FRONT_IMPL=cuda-core selects k_front.cu (cross-check)
     uint8_t *d_toep = nullptr;                 // Toeplitz byte planes of the 15 tap rows
     float *d_sam_state = nullptr;              // [C][4] SAM carrier loop
-    int any_sam = 0;
+    int32_t *d_nb_ref = nullptr;               // [C] noise blanker running magnitude
+    int any_sam = 0, sam_tiles = 0;
     int *d_tile_ch = nullptr; int4 *d_tile_rows = nullptr; int n_tiles = 0, tile_cap = 0;
     float *d_nc_coeff = nullptr, *d_nc_prev = nullptr, *d_nc_energy = nullptr; uint8_t *d_nc_first = nullptr;
     float *d_dn_coeff = nullptr, *d_dn_prev = nullptr, *d_dn_energy = nullptr; uint8_t *d_dn_first = nullptr;
@@ -141,6 +142,8 @@ int validate_params(const rdsp_chan_params_t *p, std::string &why)
 {
     if (p->demod < 0 || p->demod >= RDSP_DEMOD_MODES) { why = "demod out of range"; return RDSP_ERR_RANGE; }
     if (p->als_peak < 0 || p->als_peak > 1) { why = "als_peak must be 0 or 1"; return RDSP_ERR_RANGE; }
+    if (p->nb_on < 0 || p->nb_on > 1) { why = "nb_on must be 0 or 1"; return RDSP_ERR_RANGE; }
+    if (!(p->nb_threshold_db >= 0.0f && p->nb_threshold_db <= 40.0f)) { why = "nb_threshold_db out of range (0 .. 40)"; return RDSP_ERR_RANGE; }
     if (p->audio_filter < 0 || p->audio_filter >= RDSP_FILTER_COUNT) { why = "audio_filter out of range"; return RDSP_ERR_RANGE; }
     if (p->agc_mode < 0 || p->agc_mode >= RDSP_AGC_COUNT) { why = "agc_mode out of range"; return RDSP_ERR_RANGE; }
     if (p->notch_on < 0 || p->notch_on > 1) { why = "notch_on must be 0 or 1"; return RDSP_ERR_RANGE; }
@@ -183,6 +186,7 @@ void derive_params(rdsp_gpu *h, int ch)
     d.agc_mode = (uint8_t)p.agc_mode;
     d.notch_on = (uint8_t)p.notch_on;
     d.als_peak = (uint8_t)p.als_peak;
+    d.nb_mult_q8 = p.nb_on ? (uint32_t)(pow(10.0, (double)p.nb_threshold_db / 20.0) * 256.0 + 0.5) : 0u;
     d.nr_kind = (uint8_t)(p.nr_level > 0 ? p.nr_kind : RDSP_NR_OFF);
 }
 
@@ -273,8 +277,9 @@ int sync_tables(rdsp_gpu *h)
     if (has(h, RDSP_STAGE_FRONTEND)) {
         // k_front_tc: channels that share their tap rows, in tiles of 128 MMA rows
         h->n_tiles = front_tc_build_tiles(h->dpar.data(), h->C, &h->taps[0][0], RDSP_FIR_TAPS, tile_ch, tile_rows);
-        h->any_sam = 0;
-        for (const int4 &r : tile_rows) if (r.w == 2) h->any_sam = 1;
+        h->any_sam = 0; h->sam_tiles = 0;
+        for (const int4 &r : tile_rows) if (r.w == 2) { h->any_sam = 1; h->sam_tiles = 1; }
+        for (int ch = 0; ch < h->C; ch++) if (h->dpar[ch].nb_mult_q8) h->any_sam = 1;   // blanker state is sequential too
         if (h->n_tiles > h->tile_cap) {
             if (h->d_tile_ch) cudaFree(h->d_tile_ch);
             if (h->d_tile_rows) cudaFree(h->d_tile_rows);
@@ -338,7 +343,7 @@ void prof_collect(rdsp_gpu *h)
 
 void free_all(rdsp_gpu *h)
 {
-    void *ptrs[] = {h->d_fe_hist2, h->d_toep, h->d_tile_ch, h->d_tile_rows, h->d_sam_state,
+    void *ptrs[] = {h->d_fe_hist2, h->d_toep, h->d_tile_ch, h->d_tile_rows, h->d_sam_state, h->d_nb_ref,
                     h->d_par, h->d_list_notch, h->d_list_plain, h->d_list_dnr, h->d_taps, h->d_masks, h->d_tw, h->d_win256, h->d_win1024,
                     h->d_tw256, h->d_fe_hist, h->d_nc_coeff, h->d_nc_prev, h->d_nc_energy, h->d_nc_first, h->d_dn_coeff,
                     h->d_dn_prev, h->d_dn_energy, h->d_dn_first, h->d_agc_env, h->d_conv_last, h->d_nfloor, h->d_bq_state,
@@ -407,6 +412,8 @@ void rdsp_gpu_default_params(rdsp_chan_params_t *p)
     p->out_gain = 0.5f;                          // :134
     p->iq_balance = 1.020f;                      // :135
     p->als_peak = 0;                             // SDR.setALSfilterNotch(), RDSP_controls.h:258
+    p->nb_on = 0;                                // SDR.disableNoiseBlanker(), :131
+    p->nb_threshold_db = 20.0f;                  // :130
 }
 
 const char *rdsp_gpu_last_error(const rdsp_gpu_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -463,8 +470,15 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     CKC(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
     for (int g = 0; g < kMaxGroups; g++)
         for (int k = 0; k < 3; k++) CKC(cudaEventCreateWithFlags(&h->ev_group[g][k], cudaEventDisableTiming));
-    for (int s = 0; s < kStreams; s++) {
-        CKC(cudaStreamCreateWithFlags(&h->stage_stream[s], cudaStreamNonBlocking));
+    {
+        // the main chain (and the front end it waits for) outranks the spectrum and side branches: when an SM slot frees
+        // up, a block of the latency-critical notch / DNR launch goes first, the wide FFT grids fill what is left
+        int prio_lo = 0, prio_hi = 0;
+        CKC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        for (int s = 0; s < kStreams; s++) {
+            const bool critical = s < kMaxGroups || s == 3 * kMaxGroups;
+            CKC(cudaStreamCreateWithPriority(&h->stage_stream[s], cudaStreamNonBlocking, critical ? prio_hi : prio_lo));
+        }
     }
 
     // host-side tables
@@ -492,6 +506,7 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
         CKC(dalloc(&h->d_fe_hist2, C * 3 * RDSP_BLK));
         CKC(dalloc(&h->d_toep, front_tc_toeplitz_bytes()));
         CKC(dalloc(&h->d_sam_state, C * 4));
+        CKC(dalloc(&h->d_nb_ref, C));
         if (const char *e = getenv("RDSP_FRONT_IMPL")) h->front_tc = !(e[0] == 'c' || e[0] == 'C');
         if (const char *e = getenv("RDSP_TIMELINE")) h->timeline = e[0] == '1';
         CKC(dalloc(&h->d_mid_a, T * C * RDSP_BLK));
@@ -717,11 +732,11 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
             h->fe_hist_cur ^= 1;
             FrontTcTables tb{};
             tb.tile_ch = h->d_tile_ch; tb.tile_rows = h->d_tile_rows; tb.toep = h->d_toep; tb.n_tiles = h->n_tiles;
-            tb.any_sam = h->any_sam;
-            a.sam_state = h->d_sam_state;
+            tb.any_sam = h->any_sam; tb.sam_tiles = h->sam_tiles;
+            a.sam_state = h->d_sam_state; a.nb_ref = h->d_nb_ref;
             launch_front_tc(a, tb, s_front);
         } else {
-            if (h->any_sam) { h->err = "SAM is only built in the tensor-core front end (unset RDSP_FRONT_IMPL)"; return RDSP_ERR_STATE; }
+            if (h->any_sam) { h->err = "SAM and the noise blanker are only built in the tensor-core front end (unset RDSP_FRONT_IMPL)"; return RDSP_ERR_STATE; }
             a.hist = h->fe_hist_cur ? h->d_fe_hist2 : h->d_fe_hist;
             launch_front(a, s_front);
         }

@@ -88,7 +88,9 @@ public:
     void setALSfilterNotch() { auto p = b_.get(ch_); p.als_peak = 0; b_.set(ch_, p); }
     void setALSfilterPeak() { auto p = b_.get(ch_); p.als_peak = 1; b_.set(ch_, p); }
     void setALSfilterAdaptive() {}
-    void disableNoiseBlanker() {}
+    void enableNoiseBlanker() { auto p = b_.get(ch_); p.nb_on = 1; b_.set(ch_, p); }
+    void disableNoiseBlanker() { auto p = b_.get(ch_); p.nb_on = 0; b_.set(ch_, p); }
+    void setNoiseBlankerThresholdDb(float db) { auto p = b_.get(ch_); p.nb_threshold_db = db; b_.set(ch_, p); }
     void setInputGain(float g) { auto p = b_.get(ch_); p.in_gain = g; b_.set(ch_, p); }
     void setOutputGain(float g) { auto p = b_.get(ch_); p.out_gain = g; b_.set(ch_, p); }
     void setIQgainBalance(float v) { auto p = b_.get(ch_); p.iq_balance = v; b_.set(ch_, p); }

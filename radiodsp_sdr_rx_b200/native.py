@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librdsp_gpu.so")
+LIB_PATH = os.environ.get("RDSP_GPU_LIB") or os.path.join(HERE, "librdsp_gpu.so")      # override: A/B builds of the same ABI
 
 BLK = 128
 
@@ -53,7 +53,7 @@ class Params(C.Structure):
         ("notch_on", C.c_int32), ("notch_level", C.c_int32), ("nr_kind", C.c_int32),
         ("nr_level", C.c_int32), ("pbt_lo_hz", C.c_float), ("pbt_hi_hz", C.c_float),
         ("in_gain", C.c_float), ("out_gain", C.c_float), ("iq_balance", C.c_float),
-        ("als_peak", C.c_int32),
+        ("als_peak", C.c_int32), ("nb_on", C.c_int32), ("nb_threshold_db", C.c_float),
     ]
 
     def copy(self, **kw):

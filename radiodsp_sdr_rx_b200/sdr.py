@@ -65,6 +65,15 @@ class SDRChannel:
     def setALSfilterPeak(self):
         self._update(als_peak=1)
 
+    def enableNoiseBlanker(self):            # RadioDSP_SDR_RX.ino:129
+        self._update(nb_on=1)
+
+    def disableNoiseBlanker(self):           # :131
+        self._update(nb_on=0)
+
+    def setNoiseBlankerThresholdDb(self, db: float):   # :130
+        self._update(nb_threshold_db=db)
+
     def setALSfilterAdaptive(self):
         pass
 

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(rd):
 
 def test_struct_layouts_match_header(rd):
     from radiodsp_sdr_rx_b200 import native
-    assert C.sizeof(native.Config) == 68 and C.sizeof(native.Params) == 52
+    assert C.sizeof(native.Config) == 68 and C.sizeof(native.Params) == 60
     cfg = rd.default_config()
     assert cfg.struct_size == C.sizeof(native.Config)
     assert (cfg.n_channels, cfg.stage_mask, cfg.spec256_naverage) == (1, rd.STAGE_ALL, 30)
@@ -37,7 +37,7 @@ def test_struct_layouts_match_header(rd):
     assert (p.demod, p.audio_filter, p.agc_mode, p.notch_on, p.nr_kind, p.nr_level) == (
         rd.DEMOD_LSB, rd.FILTER_2700, rd.AGC_MEDIUM, 0, rd.NR_OFF, 0)
     assert (p.pbt_lo_hz, p.pbt_hi_hz, p.in_gain, p.out_gain) == (300.0, 4000.0, 1.0, 0.5)
-    assert abs(p.iq_balance - 1.02) < 1e-6 and p.als_peak == 0
+    assert abs(p.iq_balance - 1.02) < 1e-6 and p.als_peak == 0 and p.nb_on == 0 and p.nb_threshold_db == 20.0
 
 
 def test_oracle_and_product_defaults_agree(rd, po):

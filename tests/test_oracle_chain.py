@@ -80,6 +80,23 @@ def test_als_peak_emits_the_estimate(po):
     assert abs(_rms(peak[40:, :, 0]) / _rms(off[40:, :, 0]) - 1.0) < 0.05
 
 
+def test_noise_blanker_zeroes_impulses_and_leaves_the_signal(po):
+    """SDR.enableNoiseBlanker + setNoiseBlankerThresholdDb (RadioDSP_SDR_RX.ino:129-130): frames far above the running
+    IQ magnitude are zeroed before the filters; a clean signal passes untouched"""
+    cfg = po.default_config(stage_mask=po.STAGE_FRONTEND)
+    clean = _tone_iq(-1000.0, 40, amp=2000)
+    dirty = clean.copy()
+    dirty.reshape(-1, 2)[777::1500] = 30000                     # ignition-noise style impulses, ~24 dB above the tone
+    off = po.default_params(iq_balance=1.0)
+    on = po.default_params(iq_balance=1.0, nb_on=1, nb_threshold_db=12.0)
+    ref = po.OracleChan(cfg, off).process(clean)
+    assert np.array_equal(po.OracleChan(cfg, on).process(clean), ref)          # nothing to blank
+    hurt = po.OracleChan(cfg, off).process(dirty)
+    healed = po.OracleChan(cfg, on).process(dirty)
+    e_hurt = _rms((hurt - ref.astype(np.int32))[4:, :, 0]); e_healed = _rms((healed - ref.astype(np.int32))[4:, :, 0])
+    assert e_healed < 0.12 * e_hurt
+
+
 def test_q15_fir_wraps_and_saturates(po):
     """arm_fir_fast_q15 convention: 32-bit wrap-around accumulator, then SSAT(acc >> 15)"""
     L = po.lib()

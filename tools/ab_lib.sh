@@ -1,0 +1,5 @@
+#!/bin/bash
+one() { RDSP_BENCH_NO_CLOCKS=1 python bench.py --steps 100 --warmup 10 --no-cpu "${@:2}" 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$1', round(d['value']), round(d['ms_per_step'],4), [round(x,3) for x in d['ms_step_min_median_max']])"; }
+one current
+one current
+one "no side streams (profiling-like serial)" --pipeline-chunks 1
