@@ -147,5 +147,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_fftfilt(FftFiltArgs a)
 
 void launch_fftfilt(const FftFiltArgs &a, cudaStream_t st)
 {
+    RDSP_CARVEOUT_ONCE(k_fftfilt);
     if (a.n > 0) k_fftfilt<<<(a.n + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(a);
 }

@@ -53,8 +53,19 @@ constexpr int META_B = ROWS * 16 + 128 + 80 + ROWS * 16;
 constexpr int SMEM_B = OFF_META + META_B;
 static_assert(SMEM_B <= 227 * 1024, "shared memory budget");
 
-constexpr int TM_COLS = 512;                  // TMEM columns: two x [I ll|mid|hh][Q ll|mid|hh] x 32, one x [ll|mid|hh] x 32
-constexpr int TM_ACC1B = 192, TM_ACC2P = 384; // acc1[0] @0, acc1[1] @192, acc2 @384 (480 of 512 columns)
+// TMEM columns (480 of 512): two Hilbert accumulator sets [I ll|mid|hh][Q ll|mid|hh] x 32 @0 / @192, band-pass
+// [ll|mid|hh] x 32 @384.  With -DRDSP_TC_A_TMEM=1 the I' / Q' byte planes are ALSO kept in TMEM ([0,192): plane p at
+// 48 p, slice s at + 8 s, lane = row) and are the A operand of the Hilbert MMAs (.ts form), with one accumulator set
+// @192.  Built, bit-exact, and NOT faster (93 vs 80 us): tools/ubench_umma.cu shows that a tcgen05.mma of M = 128,
+// K = 32 costs ~52 clk for every N <= 64 whether A comes from shared memory or TMEM (64 clk at N = 128, 128 at
+// N = 256; ~40 clk with several issuing warps) — the N = 32 MMAs of this kernel pay a fixed per-instruction cost, not
+// operand fetch, and the .ts form only loses the second accumulator set.  Kept as an option for the record.
+#ifndef RDSP_TC_A_TMEM
+#define RDSP_TC_A_TMEM 0
+#endif
+constexpr int TM_COLS = 512;
+constexpr int TM_RING = 0, TM_PLANE = 48;
+constexpr int TM_ACC1B = 192, TM_ACC2P = 384;
 
 // mbarriers (index = chunk parity unless single):
 constexpr int B_IN_FULL = 0, B_M1_DONE = 2, B_E1_DONE = 4, B_M2_DONE = 6, B_E2_DONE = 8;
@@ -112,6 +123,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8])
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const int4 a, const int4 b)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g, uint32_t src_bytes)
 {
@@ -280,6 +303,34 @@ __device__ __forceinline__ void issue_fir(uint32_t ring_lo, uint32_t ring_hi, ui
         mma_i8(tmem_d + 1 * NOUT, a_lo, b_hi, IDESC_US, 1);
         mma_i8(tmem_d + 2 * NOUT, a_hi, b_hi, IDESC_SS, ks > 0);
         sl = sl + 1 == SLICES ? 0 : sl + 1;
+    }
+}
+
+// the same FIR with the delay-line planes as TMEM A operand: ring_lo / ring_hi = TMEM column of slice 0 of the plane
+__device__ __forceinline__ void issue_fir_ts(uint32_t ring_lo, uint32_t ring_hi, uint32_t taps_lo, uint32_t taps_hi, uint32_t tmem_d, int c)
+{
+    int sl = c % SLICES;
+#pragma unroll 1
+    for (int ks = 0; ks < KSTEPS; ks++) {
+        const uint32_t a_lo = ring_lo + 8u * (uint32_t)sl, a_hi = ring_hi + 8u * (uint32_t)sl;
+        const uint64_t b_lo = make_desc(taps_lo + ks * 2 * NOUT * 16, NOUT * 16), b_hi = make_desc(taps_hi + ks * 2 * NOUT * 16, NOUT * 16);
+        mma_i8_ts(tmem_d + 0 * NOUT, a_lo, b_lo, IDESC_UU, ks > 0);
+        mma_i8_ts(tmem_d + 1 * NOUT, a_hi, b_lo, IDESC_SU, ks > 0);
+        mma_i8_ts(tmem_d + 1 * NOUT, a_lo, b_hi, IDESC_US, 1);
+        mma_i8_ts(tmem_d + 2 * NOUT, a_hi, b_hi, IDESC_SS, ks > 0);
+        sl = sl + 1 == SLICES ? 0 : sl + 1;
+    }
+}
+
+// one 32-sample slice of the four I' / Q' byte planes, shared memory -> TMEM; the thread of row r moves its row
+// (tmem_lane = TMEM base with the lane offset of this warp's quadrant)
+__device__ __forceinline__ void slice_to_tmem(const TcSmem &s, uint32_t tmem_lane, int slice, int r)
+{
+#pragma unroll
+    for (int pl = 0; pl < 4; pl++) {
+        const uint8_t *src = s.ring(pl >> 1, pl & 1) + slice * SLICE_B + r * 16;
+        tmem_st8(tmem_lane + TM_RING + pl * TM_PLANE + slice * 8, *reinterpret_cast<const int4 *>(src),
+                 *reinterpret_cast<const int4 *>(src + ROWS * 16));
     }
 }
 
@@ -477,6 +528,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s.tmem_ptr();
+#if RDSP_TC_A_TMEM
+    if (warp >= W_LD && warp < W_LD + 4) {
+        const int r = (warp - W_LD) * 32 + lane;
+        const uint32_t tl = tmem + ((uint32_t)((warp - W_LD) * 32) << 16);
+#pragma unroll 1
+        for (int sl = 0; sl < 4; sl++) slice_to_tmem(s, tl, sl, r);        // the history of the I' / Q' lines
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+#endif
     TCQ(13);
 
     if (warp >= W_LD && warp < W_LD + 4) {
@@ -503,7 +566,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
             } else {
                 split_chunk<false>(s, c & 1, (c + 4) % SLICES, lw, lane);
             }
+#if RDSP_TC_A_TMEM
+            asm volatile("bar.sync 2, 128;" ::: "memory");               // the rows of this slice were written by all four loader warps
+            slice_to_tmem(s, tmem + ((uint32_t)(lw * 32) << 16), (c + 4) % SLICES, lw * 32 + lane);
+            tmem_st_wait();
+            tc_fence_before();
+#else
             fence_async_smem();
+#endif
             mbar_arrive(bar(B_IN_FULL + (c & 1)));
             if (lw == 0) TCP(1);
         }
@@ -524,12 +594,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
                 if (c < nch) {
                     mbar_wait(bar(B_IN_FULL + (c & 1)), (c >> 1) & 1);
                     TCP(2);
+#if RDSP_TC_A_TMEM
+                    if (c >= 1) mbar_wait(bar(B_E1_DONE + ((c - 1) & 1)), ((c - 1) >> 1) & 1);   // the one accumulator set is drained
+                    TCP(3);
+                    tc_fence_after();
+                    const uint32_t acc1 = tmem + TM_ACC1B;
+                    issue_fir_ts(tmem + TM_RING + 0 * TM_PLANE, tmem + TM_RING + 1 * TM_PLANE, tA0, tA1, acc1, c);
+                    issue_fir_ts(tmem + TM_RING + 2 * TM_PLANE, tmem + TM_RING + 3 * TM_PLANE, tB0, tB1, acc1 + 3 * NOUT, c);
+#else
                     if (c >= 2) mbar_wait(bar(B_E1_DONE + (c & 1)), ((c - 2) >> 1) & 1);
                     TCP(3);
                     tc_fence_after();
                     const uint32_t acc1 = tmem + (c & 1) * TM_ACC1B;
                     issue_fir(rI0, rI1, tA0, tA1, acc1, c);
                     issue_fir(rQ0, rQ1, tB0, tB1, acc1 + 3 * NOUT, c);
+#endif
                     mma_commit(bar(B_M1_DONE + (c & 1)));
                     TCP(4);
                 }
@@ -567,9 +646,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
             if (c >= 2) mbar_wait(bar(B_M2_DONE + (c & 1)), ((c - 2) >> 1) & 1);
             if (warp == 0) TCP(9);
             tc_fence_after();
-            if (dmode == 1) epilogue1<1>(s, tmem_row + (c & 1) * TM_ACC1B, row, (c + 4) % SLICES, usb, sam);
-            else if (WITH_SAM && dmode == 2) epilogue1<2>(s, tmem_row + (c & 1) * TM_ACC1B, row, (c + 4) % SLICES, usb, sam);
-            else epilogue1<0>(s, tmem_row + (c & 1) * TM_ACC1B, row, (c + 4) % SLICES, usb, sam);
+            const uint32_t acc1 = tmem_row + (RDSP_TC_A_TMEM ? TM_ACC1B : (c & 1) * TM_ACC1B);
+            if (dmode == 1) epilogue1<1>(s, acc1, row, (c + 4) % SLICES, usb, sam);
+            else if (WITH_SAM && dmode == 2) epilogue1<2>(s, acc1, row, (c + 4) % SLICES, usb, sam);
+            else epilogue1<0>(s, acc1, row, (c + 4) % SLICES, usb, sam);
             tc_fence_before();
             fence_async_smem();
             mbar_arrive(bar(B_E1_DONE + (c & 1)));

@@ -299,6 +299,7 @@ void launch_nlms(const NlmsArgs &a, cudaStream_t st)
     if (const char *env = getenv("RDSP_NLMS_LANES")) G = atoi(env) == 4 ? 4 : 8;       // experiments only
     const int cpb = NWARPS * (32 / G);
     const int grid = (a.n_list + cpb - 1) / cpb;
+    RDSP_CARVEOUT_ONCE(k_nlms<4>); RDSP_CARVEOUT_ONCE(k_nlms<8>);
     if (G == 4) k_nlms<4><<<grid, NWARPS * 32, 0, st>>>(a);
     else k_nlms<8><<<grid, NWARPS * 32, 0, st>>>(a);
 }

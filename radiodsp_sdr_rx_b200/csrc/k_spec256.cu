@@ -17,7 +17,7 @@ namespace {
 
 constexpr int WARPS = 8;
 
-__global__ void __launch_bounds__(WARPS * 32) k_spec256(Spec256Args a)
+__global__ void __launch_bounds__(WARPS * 32, 3) k_spec256(Spec256Args a)
 {
     __shared__ __align__(8) int2 s_fft[WARPS][256 + 64];          // unpacked (re, im), skewed (fft_q15.cuh)
     __shared__ int16_t s_win[256];
@@ -106,5 +106,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_spec256(Spec256Args a)
 
 void launch_spec256(const Spec256Args &a, cudaStream_t st)
 {
+    RDSP_CARVEOUT_ONCE(k_spec256);
     if (a.n > 0) k_spec256<<<(a.n + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(a);
 }

@@ -5,6 +5,17 @@
 #include <vector>
 #include "rdsp_common.cuh"
 
+// Every kernel of the chain asks for the same L1 / shared-memory split (all shared): kernels of different stages run
+// next to each other on an SM, and an SM does not co-host kernels that want different carve-outs.
+#include <cstdlib>
+template <typename K>
+inline void rdsp_uniform_carveout(K kernel)
+{
+    static const int pct = [] { const char *e = getenv("RDSP_CARVEOUT"); return e ? atoi(e) : 50; }();
+    if (pct >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+#define RDSP_CARVEOUT_ONCE(kernel) do { static bool done_ = false; if (!done_) { rdsp_uniform_carveout(kernel); done_ = true; } } while (0)
+
 // K0+K1+K2 -----------------------------------------------------------------------------------
 struct FrontArgs {
     const int16_t *iq;          // [T][C][128][2]
