@@ -93,6 +93,38 @@ QHD void last(int2 *src, int b)
     w[3] = make_int2((Sx - Uy) >> 1, (Sy + Ux) >> 1);          // SHASX(S, U)
 }
 
+// ---- the same butterflies on registers (in place: x0..x3 = elements i, i+n2, i+2 n2, i+3 n2) ----------------------
+// A thread that holds 16 elements can run two consecutive stages between two shared-memory round trips.
+QHD void first_real_r(int2 &x0, int2 &x1, int2 &x2, int2 &x3, int2 t1, int2 t2, int2 t3)     // t1 = tw[ic], t2 = tw[2ic], t3 = tw[3ic]
+{
+    const int xa = x0.x >> 2, xb = x1.x >> 2, xc = x2.x >> 2, xd = x3.x >> 2;
+    const int Rx = xa + xc, Sx = xa - xc, Tx = xb + xd, Ux = xb - xd;
+    x0 = make_int2((Rx + Tx) >> 1, 0);
+    x1 = cmul(t2, make_int2(Rx - Tx, 0));
+    x2 = cmul(t1, make_int2(Sx, -Ux));
+    x3 = cmul(t3, make_int2(Sx, Ux));
+}
+QHD void middle_r(int2 &x0, int2 &x1, int2 &x2, int2 &x3, int2 t1, int2 t2, int2 t3)
+{
+    const int2 xa = x0, xb = x1, xc = x2, xd = x3;
+    const int Rx = s16(xa.x + xc.x), Ry = s16(xa.y + xc.y), Sx = s16(xa.x - xc.x), Sy = s16(xa.y - xc.y);
+    const int Tx = s16(xb.x + xd.x), Ty = s16(xb.y + xd.y), Ux = s16(xb.x - xd.x), Uy = s16(xb.y - xd.y);
+    x0 = make_int2(((Rx + Tx) >> 1) >> 1, ((Ry + Ty) >> 1) >> 1);
+    x1 = cmul(t2, make_int2((Rx - Tx) >> 1, (Ry - Ty) >> 1));
+    x2 = cmul(t1, make_int2((Sx + Uy) >> 1, (Sy - Ux) >> 1));
+    x3 = cmul(t3, make_int2((Sx - Uy) >> 1, (Sy + Ux) >> 1));
+}
+QHD void last_r(int2 &x0, int2 &x1, int2 &x2, int2 &x3)
+{
+    const int2 xa = x0, xb = x1, xc = x2, xd = x3;
+    const int Rx = s16(xa.x + xc.x), Ry = s16(xa.y + xc.y), Sx = s16(xa.x - xc.x), Sy = s16(xa.y - xc.y);
+    const int Tx = s16(xb.x + xd.x), Ty = s16(xb.y + xd.y), Ux = s16(xb.x - xd.x), Uy = s16(xb.y - xd.y);
+    x0 = make_int2((Rx + Tx) >> 1, (Ry + Ty) >> 1);
+    x1 = make_int2((Rx - Tx) >> 1, (Ry - Ty) >> 1);
+    x2 = make_int2((Sx + Uy) >> 1, (Sy - Ux) >> 1);
+    x3 = make_int2((Sx - Uy) >> 1, (Sy + Ux) >> 1);
+}
+
 QHD uint32_t bitrev(uint32_t i, int bits)
 {
     uint32_t r = 0;

@@ -6,10 +6,13 @@
 // i < 512, then keep the last 4 blocks (50 % overlap => a new spectrum every 4 ticks from tick 7 on).
 // All integer, bit-exact.
 //
-// Mapping: one 64-thread CTA per channel, 4 radix-4 butterflies per thread per stage on unpacked (re, im) pairs in
-// shared memory (fft_q15.cuh).  The 10 KB frame is the only per-channel shared memory, so ~20 channels are
-// resident per SM; twiddles and the window come through L1.  The last 8 blocks of L live in an HBM ring
-// [C][8][128] indexed by tick mod 8; ticks that do not complete a frame only append their block.
+// Mapping: one 64-thread CTA per channel.  The five radix-4 stages run as THREE passes: a thread holds 16 elements in
+// registers and runs two consecutive stages on them (stages 1+2 on the elements that differ in index digits 4,3 — read
+// straight from the HBM ring and windowed, the frame is never staged; stages 3+4 on digits 2,1), then the last stage and
+// the magnitudes.  Two shared-memory round trips and barriers instead of five (the per-butterfly arithmetic is the one of
+// fft_q15.cuh, so the result is bit-identical); element i sits at i + 4 (i >> 6), which keeps all three access patterns
+// conflict free.  Twiddles and the window come through L1.  The last 8 blocks of L live in an HBM ring [C][8][128]
+// indexed by tick mod 8; ticks that do not complete a frame only append their block.
 #include "rdsp_common.cuh"
 #include "fft_q15.cuh"
 #include "kernels.h"
@@ -17,10 +20,11 @@
 namespace {
 
 constexpr int NT = 64;
+__device__ __forceinline__ int PP(int i) { return i + 4 * (i >> 6); }
 
 __global__ void __launch_bounds__(NT) k_spec1024(Spec1024Args a)
 {
-    __shared__ __align__(16) int2 s_fft[1024 + 256];              // unpacked (re, im), skewed (fft_q15.cuh)
+    __shared__ __align__(16) int2 s_fft[1024 + 64];               // unpacked (re, im), element i at PP(i)
     __shared__ uint16_t s_guess[34];
     if (threadIdx.x < 33) s_guess[threadIdx.x] = c_sqrt_guess[threadIdx.x];
 
@@ -40,43 +44,79 @@ __global__ void __launch_bounds__(NT) k_spec1024(Spec1024Args a)
         if (!(tick >= 7ull && ((tick - 7ull) & 3ull) == 0ull)) continue;       // uniform over the CTA
         __syncthreads();                                            // the appended block is visible to the whole CTA
 
-        // frame = blocks tick-7 .. tick, windowed
-#pragma unroll 4
-        for (int j = 0; j < 16; j++) {
-            const int i = tid + NT * j;
-            const int b = i >> 7, n = i & 127;
-            const int32_t smp = ring[(int)((tick + 1 + b) & 7ull) * RDSP_BLK + n];
-            s_fft[q15fft::P(i)] = make_int2((int16_t)((smp * (int32_t)__ldg(a.win + i)) >> 15), 0);    // imaginary part 0
+        // ---- pass 1: stages 1 + 2 on x[d4][d3] = element 256 d4 + 64 d3 + tid, frame = blocks tick-7 .. tick, windowed
+        int2 x[4][4];
+#pragma unroll
+        for (int d4 = 0; d4 < 4; d4++)
+#pragma unroll
+            for (int d3 = 0; d3 < 4; d3++) {
+                const int i = 256 * d4 + 64 * d3 + tid;
+                const int b = i >> 7, n = i & 127;
+                const int32_t smp = ring[(int)((tick + 1 + b) & 7ull) * RDSP_BLK + n];
+                x[d4][d3] = make_int2((int16_t)((smp * (int32_t)__ldg(a.win + i)) >> 15), 0);      // imaginary part 0
+            }
+#pragma unroll
+        for (int d3 = 0; d3 < 4; d3++) {                            // stage 1: span 256, twiddle step 4, j = 64 d3 + tid
+            const int ic = 4 * (64 * d3 + tid);
+            q15fft::first_real_r(x[0][d3], x[1][d3], x[2][d3], x[3][d3], a.tw[ic], a.tw[2 * ic], a.tw[3 * ic]);
+        }
+        {
+            const int ic = 16 * tid;                                // stage 2: span 64, twiddle step 16, j = tid
+            const int2 t1 = a.tw[ic], t2 = a.tw[2 * ic], t3 = a.tw[3 * ic];
+#pragma unroll
+            for (int d4 = 0; d4 < 4; d4++) q15fft::middle_r(x[d4][0], x[d4][1], x[d4][2], x[d4][3], t1, t2, t3);
+        }
+#pragma unroll
+        for (int d4 = 0; d4 < 4; d4++)
+#pragma unroll
+            for (int d3 = 0; d3 < 4; d3++) s_fft[PP(256 * d4 + 64 * d3 + tid)] = x[d4][d3];
+        __syncthreads();
+        // ---- pass 2: stages 3 + 4 on y[d2][d1] = element base + 16 d2 + 4 d1, base = 64 (tid >> 2) + (tid & 3)
+        {
+            const int base = 64 * (tid >> 2) + (tid & 3), d0 = tid & 3;
+            int2 y[4][4];
+#pragma unroll
+            for (int d2 = 0; d2 < 4; d2++)
+#pragma unroll
+                for (int d1 = 0; d1 < 4; d1++) y[d2][d1] = s_fft[PP(base + 16 * d2 + 4 * d1)];
+#pragma unroll
+            for (int d1 = 0; d1 < 4; d1++) {                        // stage 3: span 16, twiddle step 64, j = 4 d1 + d0
+                const int ic = 64 * (4 * d1 + d0);
+                q15fft::middle_r(y[0][d1], y[1][d1], y[2][d1], y[3][d1], a.tw[ic], a.tw[2 * ic], a.tw[3 * ic]);
+            }
+            {
+                const int ic = 256 * d0;                            // stage 4: span 4, twiddle step 256, j = d0
+                const int2 t1 = a.tw[ic], t2 = a.tw[2 * ic], t3 = a.tw[3 * ic];
+#pragma unroll
+                for (int d2 = 0; d2 < 4; d2++) q15fft::middle_r(y[d2][0], y[d2][1], y[d2][2], y[d2][3], t1, t2, t3);
+            }
+#pragma unroll
+            for (int d2 = 0; d2 < 4; d2++)
+#pragma unroll
+                for (int d1 = 0; d1 < 4; d1++) s_fft[PP(base + 16 * d2 + 4 * d1)] = y[d2][d1];
         }
         __syncthreads();
-#pragma unroll
-        for (int r = 0; r < 4; r++) q15fft::first_real(s_fft, a.tw, 1024, 4, tid + NT * r);
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < 4; r++) q15fft::middle(s_fft, a.tw, 256, 64, 16, tid + NT * r);
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < 4; r++) q15fft::middle(s_fft, a.tw, 64, 16, 64, tid + NT * r);
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < 4; r++) q15fft::middle(s_fft, a.tw, 16, 4, 256, tid + NT * r);
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < 4; r++) q15fft::last(s_fft, tid + NT * r);
-        __syncthreads();
-
-        // bins 0..511 sit at the EVEN elements (bin = bitrev10(element)); walk the elements, stage the u16 results in
-        // natural order on top of the (now dead) frame, store them coalesced
+        // ---- pass 3: last stage on elements 4b .. 4b+3, b = tid + 64 r; bins 0..511 are the EVEN elements
+        // (bin = bitrev10(element)): magnitudes straight from the registers
         uint16_t v[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int2 w = s_fft[q15fft::P(2 * (tid + NT * j))];
-            v[j] = (uint16_t)sqrt_u32_approx_fast((uint32_t)(w.x * w.x) + (uint32_t)(w.y * w.y), s_guess);
+        for (int r = 0; r < 4; r++) {
+            const int e = 4 * (tid + NT * r);
+            const int4 lo = *reinterpret_cast<const int4 *>(&s_fft[PP(e)]), hi = *reinterpret_cast<const int4 *>(&s_fft[PP(e) + 2]);
+            int2 w0 = make_int2(lo.x, lo.y), w1 = make_int2(lo.z, lo.w), w2 = make_int2(hi.x, hi.y), w3 = make_int2(hi.z, hi.w);
+            q15fft::last_r(w0, w1, w2, w3);
+            v[2 * r] = (uint16_t)sqrt_u32_approx_fast((uint32_t)(w0.x * w0.x) + (uint32_t)(w0.y * w0.y), s_guess);
+            v[2 * r + 1] = (uint16_t)sqrt_u32_approx_fast((uint32_t)(w2.x * w2.x) + (uint32_t)(w2.y * w2.y), s_guess);
         }
         __syncthreads();
+        // stage the u16 results in natural order on top of the (now dead) frame, store them coalesced
         uint16_t *s_o = reinterpret_cast<uint16_t *>(s_fft);
 #pragma unroll
-        for (int j = 0; j < 8; j++) s_o[__brev((unsigned)(2 * (tid + NT * j))) >> 22] = v[j];
+        for (int r = 0; r < 4; r++) {
+            const unsigned e = 4u * (unsigned)(tid + NT * r);
+            s_o[__brev(e) >> 22] = v[2 * r];
+            s_o[__brev(e + 2u) >> 22] = v[2 * r + 1];
+        }
         __syncthreads();
         reinterpret_cast<uint4 *>(a.output + (size_t)ch * 512)[tid] = reinterpret_cast<const uint4 *>(s_o)[tid];
         __syncthreads();
