@@ -21,7 +21,7 @@ namespace {
 
 constexpr int WARPS = 8;
 
-__global__ void __launch_bounds__(WARPS * 32) k_fftfilt(FftFiltArgs a)
+__global__ void __launch_bounds__(WARPS * 32, 3) k_fftfilt(FftFiltArgs a)
 {
     __shared__ float2 s_tw[256];
     __shared__ __align__(16) float2 s_buf[WARPS][FFT256_BUF];
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_fftfilt(FftFiltArgs a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lc = blockIdx.x * WARPS + warp;
     if (lc >= a.n) return;
-    const int ch = a.ch0 + lc;
+    const int ch = a.list ? a.list[lc] : a.ch0 + lc;
     float2 *buf = s_buf[warp];
 
     const RdspChanParams p = a.par[ch];

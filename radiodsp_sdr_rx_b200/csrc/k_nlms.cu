@@ -291,8 +291,9 @@ void launch_nlms(const NlmsArgs &a, cudaStream_t st)
     static const bool direct = [] { const char *e = getenv("RDSP_NLMS_IMPL"); return e && e[0] == 'd'; }();
     if (direct) { launch_nlms_direct(a, st); return; }
     // 4 lanes per channel minimise instructions (the reductions are two shuffle stages, 30 % fewer instructions per
-    // sample); 8 lanes halve the dependent chain of a group.  Measured (8 blocks per launch, us, G = 4 / G = 8):
-    // 2048 channels 170 / 100, 6554 channels 167 / 165, 8192 channels 165 / 211, 16384 channels 324 / 336.
+    // sample); 8 lanes halve the dependent chain of a group.  Measured alone (8 blocks per launch, us, G = 4 / G = 8):
+    // 2048 channels 170 / 100, 6554 channels 167 / 165, 8192 channels 165 / 211, 16384 channels 324 / 336; inside the
+    // cfg5 step (6554 DNR channels beside the other kernels) G = 8 is 4 % ahead, inside cfg4a (8192) G = 4 by 11 %.
     // The two forms sum in different orders, so the switch sits above the per-GPU channel counts of the configs:
     // a handle and its channel-range shards then run the same form and agree bit for bit (tests/test_gpu_parity.py).
     int G = a.n_list >= 12288 ? 4 : 8;

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(NT) k_spec1024(Spec1024Args a)
     if (threadIdx.x < 33) s_guess[threadIdx.x] = c_sqrt_guess[threadIdx.x];
 
     const int tid = threadIdx.x;
-    const int ch = a.ch0 + blockIdx.x;
+    const int ch = a.list ? a.list[blockIdx.x] : a.ch0 + blockIdx.x;
     int16_t *ring = a.ring + (size_t)ch * 8 * RDSP_BLK;
     uint2 *gring = reinterpret_cast<uint2 *>(ring);               // 32 uint2 (4 samples each) per slot
 

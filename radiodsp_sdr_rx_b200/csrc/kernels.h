@@ -99,7 +99,8 @@ struct FftFiltArgs {
     const float2 *tw256;        // [256] (cos, sin)(2*pi*k/256)
     const RdspChanParams *par;
     int C, T;
-    int ch0, n;                 // channel range of this launch: [ch0, ch0 + n)
+    const int *list;            // channels of this launch (n entries), or nullptr: [ch0, ch0 + n)
+    int ch0, n;
     int nr_stage;               // RDSP_STAGE_NR present
 };
 void launch_fftfilt(const FftFiltArgs &a, cudaStream_t st);
@@ -139,7 +140,8 @@ struct Spec1024Args {
     int16_t *ring;              // [C][8][128] last blocks of L, slot = tick mod 8
     uint16_t *output;           // [C][512]
     int C, T;
-    int ch0, n;                 // channel range of this launch: [ch0, ch0 + n)
+    const int *list;            // channels of this launch (n entries), or nullptr: [ch0, ch0 + n)
+    int ch0, n;
     unsigned long long tick0;   // global tick index of block 0 of this call
     int any_fft;                // some tick of this call completes a 1024-sample frame
     const int2 *tw;             // [3072]

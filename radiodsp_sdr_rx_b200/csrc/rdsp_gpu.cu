@@ -60,8 +60,9 @@ struct rdsp_gpu {
     bool par_dirty = true;
     RdspChanParams *d_par = nullptr;
     int *d_list_notch = nullptr, *d_list_plain = nullptr, *d_list_dnr = nullptr;
+    int *d_list_dnr_p = nullptr, *d_list_dnr_n = nullptr;      // DNR channels that bypass / run the notch
     int n_notch = 0, n_plain = 0, n_dnr = 0;
-    std::vector<int> l_notch, l_plain, l_dnr;   // host copies (ascending): channel groups launch sub-ranges
+    std::vector<int> l_notch, l_plain, l_dnr, l_dnr_p, l_dnr_n;   // host copies (ascending): launches take sub-ranges
 
     // coefficient tables
     int16_t taps[15][RDSP_FIR_TAPS];
@@ -246,7 +247,7 @@ int sync_tables(rdsp_gpu *h)
     if (!h->par_dirty) return RDSP_OK;
 
     const bool notch_stage = has(h, RDSP_STAGE_NOTCH), nr_stage = has(h, RDSP_STAGE_NR);
-    std::vector<int> l_notch, l_plain, l_dnr, re_notch, re_dnr;
+    std::vector<int> l_notch, l_plain, l_dnr, l_dnr_p, l_dnr_n, re_notch, re_dnr;
     for (int ch = 0; ch < h->C; ch++) {
         const rdsp_chan_params_t &p = h->par[ch];
         // Init_LMS_NR on a level change: clears ring/state/energy, keeps the coefficients
@@ -259,6 +260,7 @@ int sync_tables(rdsp_gpu *h)
         }
         if (nr_stage && p.nr_kind == RDSP_NR_LMS && p.nr_level > 0) {
             l_dnr.push_back(ch);
+            if (notch_stage && p.notch_on) l_dnr_n.push_back(ch); else l_dnr_p.push_back(ch);
             if (p.nr_level != h->dnr_old_level[ch]) { re_dnr.push_back(ch); h->dnr_old_level[ch] = p.nr_level; }
         }
     }
@@ -297,8 +299,10 @@ int sync_tables(rdsp_gpu *h)
     if (h->n_plain) CK(cudaMemcpyAsync(h->d_list_plain, l_plain.data(), l_plain.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (h->n_notch) CK(cudaMemcpyAsync(h->d_list_notch, l_notch.data(), l_notch.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (h->n_dnr) CK(cudaMemcpyAsync(h->d_list_dnr, l_dnr.data(), l_dnr.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (!l_dnr_p.empty()) CK(cudaMemcpyAsync(h->d_list_dnr_p, l_dnr_p.data(), l_dnr_p.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (!l_dnr_n.empty()) CK(cudaMemcpyAsync(h->d_list_dnr_n, l_dnr_n.data(), l_dnr_n.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));      // the host staging vectors go out of scope
-    h->l_notch.swap(l_notch); h->l_plain.swap(l_plain); h->l_dnr.swap(l_dnr);
+    h->l_notch.swap(l_notch); h->l_plain.swap(l_plain); h->l_dnr.swap(l_dnr); h->l_dnr_p.swap(l_dnr_p); h->l_dnr_n.swap(l_dnr_n);
     h->par_dirty = false;
     return RDSP_OK;
 }
@@ -344,7 +348,7 @@ void prof_collect(rdsp_gpu *h)
 void free_all(rdsp_gpu *h)
 {
     void *ptrs[] = {h->d_fe_hist2, h->d_toep, h->d_tile_ch, h->d_tile_rows, h->d_sam_state, h->d_nb_ref,
-                    h->d_par, h->d_list_notch, h->d_list_plain, h->d_list_dnr, h->d_taps, h->d_masks, h->d_tw, h->d_win256, h->d_win1024,
+                    h->d_par, h->d_list_notch, h->d_list_plain, h->d_list_dnr, h->d_list_dnr_p, h->d_list_dnr_n, h->d_taps, h->d_masks, h->d_tw, h->d_win256, h->d_win1024,
                     h->d_tw256, h->d_fe_hist, h->d_nc_coeff, h->d_nc_prev, h->d_nc_energy, h->d_nc_first, h->d_dn_coeff,
                     h->d_dn_prev, h->d_dn_energy, h->d_dn_first, h->d_agc_env, h->d_conv_last, h->d_nfloor, h->d_bq_state,
                     h->d_spec_prev, h->d_spec_sum, h->d_spec_out, h->d_ring, h->d_spec1024_out, h->d_view, h->d_smeter,
@@ -476,7 +480,7 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
         int prio_lo = 0, prio_hi = 0;
         CKC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         for (int s = 0; s < kStreams; s++) {
-            const bool critical = s < kMaxGroups || s == 3 * kMaxGroups;
+            const bool critical = s < kMaxGroups || s >= 2 * kMaxGroups;      // main chains, notch-class chains, front end
             CKC(cudaStreamCreateWithPriority(&h->stage_stream[s], cudaStreamNonBlocking, critical ? prio_hi : prio_lo));
         }
     }
@@ -535,6 +539,8 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     }
     if (sm & RDSP_STAGE_NR) {
         CKC(dalloc(&h->d_list_dnr, C));
+        CKC(dalloc(&h->d_list_dnr_p, C));
+        CKC(dalloc(&h->d_list_dnr_n, C));
         CKC(dalloc(&h->d_dn_coeff, C * RDSP_LMS_NTAPS));
         CKC(dalloc(&h->d_dn_prev, C * RDSP_BLK));
         CKC(dalloc(&h->d_dn_energy, C));
@@ -754,10 +760,83 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
         if (tk >= 7 && ((tk - 7) & 3) == 0) n_fft_frames++;
     }
 
+    // one chain of the audio graph on stream `cs` for the channels [c0, c1) of class `cls`:
+    //   0 = every channel (no split), 1 = the channels that bypass the notch, 2 = the channels whose notch runs.
+    // With classes 1 and 2 on two streams the latency-bound notch -> AGC -> ... chain of the (few) notched channels runs
+    // beside the wide kernels of the others instead of in front of them.
+    auto run_chain = [&](cudaStream_t cs, int cls, int c0, int c1) -> int {
+        const int nc = c1 - c0;
+        int f_notch = 0, n_notch = 0, f_plain = 0, n_plain = 0;
+        if (notch) { sub(h->l_notch, c0, c1, f_notch, n_notch); sub(h->l_plain, c0, c1, f_plain, n_plain); }
+        const int *cls_list = cls == 1 ? h->d_list_plain + f_plain : (cls == 2 ? h->d_list_notch + f_notch : nullptr);
+        const int cls_n = cls == 1 ? n_plain : (cls == 2 ? n_notch : nc);
+        if (cls_n <= 0) return RDSP_OK;
+        const int16_t *mono = nullptr;
+        if (fe) {
+            mono = h->d_mid_a;
+            if (notch || agc) {
+                AgcArgs ag{};
+                ag.out_mono = ff ? h->d_mid_b : nullptr; ag.out_stereo = ff ? nullptr : audio;
+                ag.dbg = ff ? nullptr : dbg; ag.env = h->d_agc_env; ag.par = h->d_par; ag.C = C; ag.T = T;
+                ag.agc_stage = agc ? 1 : 0;
+                ag.target = h->cfg.agc_target; ag.max_gain = h->cfg.agc_max_gain; ag.alpha_a = h->agc_alpha_a;
+                if (cls != 2) {
+                    // channels that bypass the notch read the front end's q15 rows ...
+                    ag.list = notch ? h->d_list_plain + f_plain : nullptr; ag.n_list = notch ? n_plain : nc; ag.ch0 = c0;
+                    ag.in_q15 = h->d_mid_a; ag.in_f32 = nullptr;
+                    if (ag.n_list > 0) { Prof pr(h, KK_AGC, cs); launch_agc(ag, cs); }
+                }
+                if (cls != 1 && notch && n_notch > 0) {
+                    NlmsArgs n{};
+                    n.list = h->d_list_notch + f_notch; n.n_list = n_notch; n.C = C; n.T = T;
+                    n.in_q15 = h->d_mid_a; n.out_f32 = h->d_scr;
+                    n.coeff = h->d_nc_coeff; n.prev = h->d_nc_prev; n.energy = h->d_nc_energy; n.first = h->d_nc_first;
+                    n.par = h->d_par; n.mode = 0;
+                    { Prof pr(h, KK_NOTCH, cs); launch_nlms(n, cs); }
+                    // ... the others read the notch's f32 error signal
+                    ag.list = h->d_list_notch + f_notch; ag.n_list = n_notch; ag.in_q15 = nullptr; ag.in_f32 = h->d_scr;
+                    { Prof pr(h, KK_AGC, cs); launch_agc(ag, cs); }
+                }
+                mono = h->d_mid_b;
+            }
+        }
+        if (ff) {
+            FftFiltArgs f{};
+            f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq; f.out_stereo = audio; f.out_f32_L = h->d_scr;
+            f.dbg = dbg; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256;
+            f.par = h->d_par; f.C = C; f.T = T; f.list = cls_list; f.ch0 = c0; f.n = cls_n; f.nr_stage = nr ? 1 : 0;
+            { Prof pr(h, KK_FFTFILT, cs); launch_fftfilt(f, cs); }
+            if (nr) {
+                const std::vector<int> &ld = cls == 1 ? h->l_dnr_p : (cls == 2 ? h->l_dnr_n : h->l_dnr);
+                const int *dl = cls == 1 ? h->d_list_dnr_p : (cls == 2 ? h->d_list_dnr_n : h->d_list_dnr);
+                int f_dnr = 0, n_dnr = 0;
+                sub(ld, c0, c1, f_dnr, n_dnr);
+                if (n_dnr > 0) {
+                    NlmsArgs n{};
+                    n.list = dl + f_dnr; n.n_list = n_dnr; n.C = C; n.T = T;
+                    n.in_f32 = h->d_scr; n.out_stereo = audio; n.dbg = dbg;
+                    n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
+                    n.par = h->d_par; n.mode = 1;
+                    { Prof pr(h, KK_DNR, cs); launch_nlms(n, cs); }
+                }
+            }
+        }
+        if (has(h, RDSP_STAGE_SPEC1024)) {
+            Spec1024Args s1{};
+            s1.audio = audio; s1.ring = h->d_ring; s1.output = h->d_spec1024_out; s1.C = C; s1.T = T;
+            s1.list = cls_list; s1.ch0 = c0; s1.n = cls_n;
+            s1.tick0 = h->tick; s1.tw = h->d_tw; s1.win = h->d_win1024;
+            s1.any_fft = n_fft_frames > 0;
+            { Prof pr(h, KK_SPEC1024, cs); launch_spec1024(s1, cs); }
+        }
+        return RDSP_OK;
+    };
+
     for (int g = 0; g < G; g++) {
         const int c0 = (int)((long long)C * g / G), c1 = (int)((long long)C * (g + 1) / G), nc = c1 - c0;
         cudaStream_t s_main = piped ? h->stage_stream[g] : st;
         cudaStream_t s_spec = piped ? h->stage_stream[kMaxGroups + g] : st;
+        cudaStream_t s_side = piped ? h->stage_stream[2 * kMaxGroups + g] : st;
         if (piped) {
             CK(cudaStreamWaitEvent(s_main, fe ? h->ev_front : h->ev_fork, 0));
             CK(cudaStreamWaitEvent(s_spec, h->ev_fork, 0));
@@ -777,69 +856,24 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
             { Prof pr(h, KK_SPEC256, s_spec); launch_spec256(a, s_spec); }
         }
 
-        const int16_t *mono = nullptr;
-        if (fe) {
-            mono = h->d_mid_a;
-            int f_notch = 0, n_notch = 0, f_plain = 0, n_plain = 0;
-            if (notch) { sub(h->l_notch, c0, c1, f_notch, n_notch); sub(h->l_plain, c0, c1, f_plain, n_plain); }
-            if (notch || agc) {
-                AgcArgs ag{};
-                ag.out_mono = ff ? h->d_mid_b : nullptr; ag.out_stereo = ff ? nullptr : audio;
-                ag.dbg = ff ? nullptr : dbg; ag.env = h->d_agc_env; ag.par = h->d_par; ag.C = C; ag.T = T;
-                ag.agc_stage = agc ? 1 : 0;
-                ag.target = h->cfg.agc_target; ag.max_gain = h->cfg.agc_max_gain; ag.alpha_a = h->agc_alpha_a;
-                // channels that bypass the notch read the front end's q15 rows ...
-                ag.list = notch ? h->d_list_plain + f_plain : nullptr; ag.n_list = notch ? n_plain : nc; ag.ch0 = c0;
-                ag.in_q15 = h->d_mid_a; ag.in_f32 = nullptr;
-                // (on a side stream when the notch runs next to it: the two touch disjoint channels)
-                const bool side = piped && notch && n_notch > 0 && ag.n_list > 0;
-                cudaStream_t s_side = side ? h->stage_stream[2 * kMaxGroups + g] : s_main;
-                if (side) CK(cudaStreamWaitEvent(s_side, h->ev_front, 0));
-                if (ag.n_list > 0) { Prof pr(h, KK_AGC, s_side); launch_agc(ag, s_side); }
-                if (side) CK(cudaEventRecord(h->ev_group[g][2], s_side));
-                if (notch && n_notch > 0) {
-                    NlmsArgs n{};
-                    n.list = h->d_list_notch + f_notch; n.n_list = n_notch; n.C = C; n.T = T;
-                    n.in_q15 = h->d_mid_a; n.out_f32 = h->d_scr;
-                    n.coeff = h->d_nc_coeff; n.prev = h->d_nc_prev; n.energy = h->d_nc_energy; n.first = h->d_nc_first;
-                    n.par = h->d_par; n.mode = 0;
-                    { Prof pr(h, KK_NOTCH, s_main); launch_nlms(n, s_main); }
-                    // ... the others read the notch's f32 error signal
-                    ag.list = h->d_list_notch + f_notch; ag.n_list = n_notch; ag.in_q15 = nullptr; ag.in_f32 = h->d_scr;
-                    { Prof pr(h, KK_AGC, s_main); launch_agc(ag, s_main); }
-                }
-                if (side) CK(cudaStreamWaitEvent(s_main, h->ev_group[g][2], 0));
-                mono = h->d_mid_b;
-            }
-        }
-        if (ff) {
-            FftFiltArgs f{};
-            f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq; f.out_stereo = audio; f.out_f32_L = h->d_scr;
-            f.dbg = dbg; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256;
-            f.par = h->d_par; f.C = C; f.T = T; f.ch0 = c0; f.n = nc; f.nr_stage = nr ? 1 : 0;
-            { Prof pr(h, KK_FFTFILT, s_main); launch_fftfilt(f, s_main); }
-            if (nr) {
-                int f_dnr = 0, n_dnr = 0;
-                sub(h->l_dnr, c0, c1, f_dnr, n_dnr);
-                if (n_dnr > 0) {
-                    NlmsArgs n{};
-                    n.list = h->d_list_dnr + f_dnr; n.n_list = n_dnr; n.C = C; n.T = T;
-                    n.in_f32 = h->d_scr; n.out_stereo = audio; n.dbg = dbg;
-                    n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
-                    n.par = h->d_par; n.mode = 1;
-                    { Prof pr(h, KK_DNR, s_main); launch_nlms(n, s_main); }
-                }
-            }
-        }
-        if (has(h, RDSP_STAGE_SPEC1024)) {
-            Spec1024Args s1{};
-            s1.audio = audio; s1.ring = h->d_ring; s1.output = h->d_spec1024_out; s1.C = C; s1.T = T; s1.ch0 = c0; s1.n = nc;
-            s1.tick0 = h->tick; s1.tw = h->d_tw; s1.win = h->d_win1024;
-            s1.any_fft = n_fft_frames > 0;
-            { Prof pr(h, KK_SPEC1024, s_main); launch_spec1024(s1, s_main); }
+        // the channels whose notch runs form their own chain on the side stream (when both classes exist)
+        int fn = 0, nn = 0, fp = 0, np = 0;
+        if (fe && notch) { sub(h->l_notch, c0, c1, fn, nn); sub(h->l_plain, c0, c1, fp, np); }
+        const bool split = piped && fe && notch && nn > 0 && np > 0;
+        if (split) {
+            CK(cudaStreamWaitEvent(s_side, h->ev_front, 0));
+            int rc2 = run_chain(s_side, 2, c0, c1);
+            if (rc2 != RDSP_OK) return rc2;
+            rc2 = run_chain(s_main, 1, c0, c1);
+            if (rc2 != RDSP_OK) return rc2;
+            CK(cudaEventRecord(h->ev_group[g][2], s_side));
+            CK(cudaStreamWaitEvent(st, h->ev_group[g][2], 0));
+        } else {
+            const int rc2 = run_chain(s_main, 0, c0, c1);
+            if (rc2 != RDSP_OK) return rc2;
         }
         if (piped) {
-            // join: the call is complete on the handle's stream when every group has finished both of its streams
+            // join: the call is complete on the handle's stream when every group has finished all of its streams
             CK(cudaEventRecord(h->ev_group[g][0], s_main));
             CK(cudaEventRecord(h->ev_group[g][1], s_spec));
             CK(cudaStreamWaitEvent(st, h->ev_group[g][0], 0));
