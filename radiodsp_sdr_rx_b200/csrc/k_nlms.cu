@@ -37,7 +37,7 @@ constexpr int NWARPS = 2;
 constexpr int XS = 260;                      // floats per row: 16-byte aligned, rows 4 banks apart
 constexpr int D = 4;                         // samples per group
 #ifndef RDSP_NLMS_ANCHOR
-#define RDSP_NLMS_ANCHOR 2
+#define RDSP_NLMS_ANCHOR 4
 #endif
 constexpr int ANCHOR = RDSP_NLMS_ANCHOR;     // groups between exact re-anchorings of the lag sums (S/4 is a multiple)
 constexpr float LMS_EPS = 0.000000119209289f;
@@ -182,13 +182,12 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
                     for (int j = 0; j < 4; j++) {
                         energy = __fsub_rn(energy, __fmul_rn(xo[j], xo[j]));
                         energy = __fadd_rn(energy, __fmul_rn(xn[j], xn[j]));
-                        // energy is a running difference: never divide by <= 0.  MUFU.RCP + one Newton step (error below
-                        // 1 ulp; the reference divides, which this path never reproduced bit for bit anyway)
+                        // energy is a running difference: never divide by <= 0.  MUFU.RCP (relative error 2^-23; the
+                        // reference divides, which this path never reproduced bit for bit anyway)
                         {
                             const float den = fmaxf(energy + LMS_EPS, LMS_EPS);
                             float r;
                             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
-                            r = fmaf(r, fmaf(-den, r, 1.0f), r);
                             qn[j] = mu * r;
                         }
                         // s_l(b) = s_l(b-1) + x[b-l] x[b] - x[b-l-96] x[b-96],  b = n + j
