@@ -29,6 +29,20 @@ QHD int P(int i) { return i + ((i >> 4) << 2); }
 QHD int padded(int n) { return n + (n >> 2); }
 
 QHD int s16(int v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 : v); }
+// SAT = false: the caller has PROVED that no sum of this frame can leave int16 (see no_saturation_bound below), so
+// QADD16 / QSUB16 are plain adds.  The saturating min / max pairs are a quarter of a butterfly's ALU-pipe work.
+template <bool SAT> QHD int s16c(int v) { return SAT ? s16(v) : v; }
+
+// A frame whose windowed input components are all <= this bound in magnitude cannot saturate in any stage of the
+// 256- or 1024-point transform.  With input bound m0: stage 1 works on x >> 2 (<= a0 = m0/4 + 1), forms sums <= 4 a0 and
+// twiddle products <= 0.70711 * 4 a0 + 1, so its outputs are <= A1 = 0.7075 m0 + 4; a middle stage with input bound A
+// saturates only if 2 A > 32767 and leaves A' = 1.4143 A + 2 (its largest outputs are the twiddle products of
+// (R - T) >> 1 <= 2 A + 1 per component); the last stage saturates only if 2 A > 32767.  1024 points: A4 <= 16383 needs
+// A1 <= 5788; 256 points: A3 <= 16383 needs A1 <= 8188.  11000 (1024-point REAL input, A1 = m0/2 + 3) and
+// 11000 (256-point complex input) leave margin for the rounding terms.  (k_spec1024 uses it: 97 -> 92 us; in k_spec256 the
+// second code path cost more registers than the min / max pairs it saved: 81 -> 85 us, not used there.)
+constexpr int NO_SAT_BOUND_1024_REAL = 11000;
+constexpr int NO_SAT_BOUND_256 = 11000;
 // twiddle * sample: top 16 bits of the two wrap-around 32-bit sums
 QHD int2 cmul(int2 c, int2 r)
 {
@@ -67,13 +81,14 @@ QHD void first_real(int2 *src, const int2 *tw, int N, int mod, int i)
 }
 
 // middle stage with group span n1 and quarter span n2 = n1/4, twiddle step mod; butterfly b in [0, N/4)
+template <bool SAT = true>
 QHD void middle(int2 *src, const int2 *tw, int n1, int n2, int mod, int b)
 {
     const int j = b % n2, grp = b / n2, ic = j * mod, i0 = j + grp * n1;
     int2 *p0 = src + P(i0), *p1 = src + P(i0 + n2), *p2 = src + P(i0 + 2 * n2), *p3 = src + P(i0 + 3 * n2);
     const int2 xa = *p0, xb = *p1, xc = *p2, xd = *p3;
-    const int Rx = s16(xa.x + xc.x), Ry = s16(xa.y + xc.y), Sx = s16(xa.x - xc.x), Sy = s16(xa.y - xc.y);
-    const int Tx = s16(xb.x + xd.x), Ty = s16(xb.y + xd.y), Ux = s16(xb.x - xd.x), Uy = s16(xb.y - xd.y);
+    const int Rx = s16c<SAT>(xa.x + xc.x), Ry = s16c<SAT>(xa.y + xc.y), Sx = s16c<SAT>(xa.x - xc.x), Sy = s16c<SAT>(xa.y - xc.y);
+    const int Tx = s16c<SAT>(xb.x + xd.x), Ty = s16c<SAT>(xb.y + xd.y), Ux = s16c<SAT>(xb.x - xd.x), Uy = s16c<SAT>(xb.y - xd.y);
     *p0 = make_int2(((Rx + Tx) >> 1) >> 1, ((Ry + Ty) >> 1) >> 1);
     *p1 = cmul(tw[2 * ic], make_int2((Rx - Tx) >> 1, (Ry - Ty) >> 1));
     *p2 = cmul(tw[ic], make_int2((Sx + Uy) >> 1, (Sy - Ux) >> 1));        // SHSAX(S, T)
@@ -81,12 +96,13 @@ QHD void middle(int2 *src, const int2 *tw, int n1, int n2, int mod, int b)
 }
 
 // last stage, butterfly b in [0, N/4) on elements 4b..4b+3
+template <bool SAT = true>
 QHD void last(int2 *src, int b)
 {
     int2 *w = src + P(4 * b);                                  // 4b..4b+3 never straddle a skew boundary
     const int2 xa = w[0], xb = w[1], xc = w[2], xd = w[3];
-    const int Rx = s16(xa.x + xc.x), Ry = s16(xa.y + xc.y), Sx = s16(xa.x - xc.x), Sy = s16(xa.y - xc.y);
-    const int Tx = s16(xb.x + xd.x), Ty = s16(xb.y + xd.y), Ux = s16(xb.x - xd.x), Uy = s16(xb.y - xd.y);
+    const int Rx = s16c<SAT>(xa.x + xc.x), Ry = s16c<SAT>(xa.y + xc.y), Sx = s16c<SAT>(xa.x - xc.x), Sy = s16c<SAT>(xa.y - xc.y);
+    const int Tx = s16c<SAT>(xb.x + xd.x), Ty = s16c<SAT>(xb.y + xd.y), Ux = s16c<SAT>(xb.x - xd.x), Uy = s16c<SAT>(xb.y - xd.y);
     w[0] = make_int2((Rx + Tx) >> 1, (Ry + Ty) >> 1);
     w[1] = make_int2((Rx - Tx) >> 1, (Ry - Ty) >> 1);
     w[2] = make_int2((Sx + Uy) >> 1, (Sy - Ux) >> 1);          // SHSAX(S, U)
@@ -104,21 +120,23 @@ QHD void first_real_r(int2 &x0, int2 &x1, int2 &x2, int2 &x3, int2 t1, int2 t2, 
     x2 = cmul(t1, make_int2(Sx, -Ux));
     x3 = cmul(t3, make_int2(Sx, Ux));
 }
+template <bool SAT = true>
 QHD void middle_r(int2 &x0, int2 &x1, int2 &x2, int2 &x3, int2 t1, int2 t2, int2 t3)
 {
     const int2 xa = x0, xb = x1, xc = x2, xd = x3;
-    const int Rx = s16(xa.x + xc.x), Ry = s16(xa.y + xc.y), Sx = s16(xa.x - xc.x), Sy = s16(xa.y - xc.y);
-    const int Tx = s16(xb.x + xd.x), Ty = s16(xb.y + xd.y), Ux = s16(xb.x - xd.x), Uy = s16(xb.y - xd.y);
+    const int Rx = s16c<SAT>(xa.x + xc.x), Ry = s16c<SAT>(xa.y + xc.y), Sx = s16c<SAT>(xa.x - xc.x), Sy = s16c<SAT>(xa.y - xc.y);
+    const int Tx = s16c<SAT>(xb.x + xd.x), Ty = s16c<SAT>(xb.y + xd.y), Ux = s16c<SAT>(xb.x - xd.x), Uy = s16c<SAT>(xb.y - xd.y);
     x0 = make_int2(((Rx + Tx) >> 1) >> 1, ((Ry + Ty) >> 1) >> 1);
     x1 = cmul(t2, make_int2((Rx - Tx) >> 1, (Ry - Ty) >> 1));
     x2 = cmul(t1, make_int2((Sx + Uy) >> 1, (Sy - Ux) >> 1));
     x3 = cmul(t3, make_int2((Sx - Uy) >> 1, (Sy + Ux) >> 1));
 }
+template <bool SAT = true>
 QHD void last_r(int2 &x0, int2 &x1, int2 &x2, int2 &x3)
 {
     const int2 xa = x0, xb = x1, xc = x2, xd = x3;
-    const int Rx = s16(xa.x + xc.x), Ry = s16(xa.y + xc.y), Sx = s16(xa.x - xc.x), Sy = s16(xa.y - xc.y);
-    const int Tx = s16(xb.x + xd.x), Ty = s16(xb.y + xd.y), Ux = s16(xb.x - xd.x), Uy = s16(xb.y - xd.y);
+    const int Rx = s16c<SAT>(xa.x + xc.x), Ry = s16c<SAT>(xa.y + xc.y), Sx = s16c<SAT>(xa.x - xc.x), Sy = s16c<SAT>(xa.y - xc.y);
+    const int Tx = s16c<SAT>(xb.x + xd.x), Ty = s16c<SAT>(xb.y + xd.y), Ux = s16c<SAT>(xb.x - xd.x), Uy = s16c<SAT>(xb.y - xd.y);
     x0 = make_int2((Rx + Tx) >> 1, (Ry + Ty) >> 1);
     x1 = make_int2((Rx - Tx) >> 1, (Ry - Ty) >> 1);
     x2 = make_int2((Sx + Uy) >> 1, (Sy - Ux) >> 1);

@@ -22,10 +22,69 @@ namespace {
 constexpr int NT = 64;
 __device__ __forceinline__ int PP(int i) { return i + 4 * (i >> 6); }
 
+// stages 1..5 and the magnitudes of one frame whose windowed samples sit in x[d4][d3] = element 256 d4 + 64 d3 + tid
+template <bool SAT>
+__device__ __forceinline__ void fft1024_passes(int2 (&x)[4][4], int2 *s_fft, const Spec1024Args &a, const uint16_t *s_guess, int tid, uint16_t (&v)[8])
+{
+#pragma unroll
+    for (int d3 = 0; d3 < 4; d3++) {                            // stage 1: span 256, twiddle step 4, j = 64 d3 + tid
+        const int ic = 4 * (64 * d3 + tid);
+        q15fft::first_real_r(x[0][d3], x[1][d3], x[2][d3], x[3][d3], a.tw[ic], a.tw[2 * ic], a.tw[3 * ic]);
+    }
+    {
+        const int ic = 16 * tid;                                // stage 2: span 64, twiddle step 16, j = tid
+        const int2 t1 = a.tw[ic], t2 = a.tw[2 * ic], t3 = a.tw[3 * ic];
+#pragma unroll
+        for (int d4 = 0; d4 < 4; d4++) q15fft::middle_r<SAT>(x[d4][0], x[d4][1], x[d4][2], x[d4][3], t1, t2, t3);
+    }
+#pragma unroll
+    for (int d4 = 0; d4 < 4; d4++)
+#pragma unroll
+        for (int d3 = 0; d3 < 4; d3++) s_fft[PP(256 * d4 + 64 * d3 + tid)] = x[d4][d3];
+    __syncthreads();
+    // ---- pass 2: stages 3 + 4 on y[d2][d1] = element base + 16 d2 + 4 d1, base = 64 (tid >> 2) + (tid & 3)
+    {
+        const int base = 64 * (tid >> 2) + (tid & 3), d0 = tid & 3;
+        int2 y[4][4];
+#pragma unroll
+        for (int d2 = 0; d2 < 4; d2++)
+#pragma unroll
+            for (int d1 = 0; d1 < 4; d1++) y[d2][d1] = s_fft[PP(base + 16 * d2 + 4 * d1)];
+#pragma unroll
+        for (int d1 = 0; d1 < 4; d1++) {                        // stage 3: span 16, twiddle step 64, j = 4 d1 + d0
+            const int ic = 64 * (4 * d1 + d0);
+            q15fft::middle_r<SAT>(y[0][d1], y[1][d1], y[2][d1], y[3][d1], a.tw[ic], a.tw[2 * ic], a.tw[3 * ic]);
+        }
+        {
+            const int ic = 256 * d0;                            // stage 4: span 4, twiddle step 256, j = d0
+            const int2 t1 = a.tw[ic], t2 = a.tw[2 * ic], t3 = a.tw[3 * ic];
+#pragma unroll
+            for (int d2 = 0; d2 < 4; d2++) q15fft::middle_r<SAT>(y[d2][0], y[d2][1], y[d2][2], y[d2][3], t1, t2, t3);
+        }
+#pragma unroll
+        for (int d2 = 0; d2 < 4; d2++)
+#pragma unroll
+            for (int d1 = 0; d1 < 4; d1++) s_fft[PP(base + 16 * d2 + 4 * d1)] = y[d2][d1];
+    }
+    __syncthreads();
+    // ---- pass 3: last stage on elements 4b .. 4b+3, b = tid + 64 r; bins 0..511 are the EVEN elements
+    // (bin = bitrev10(element)): magnitudes straight from the registers
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int e = 4 * (tid + NT * r);
+        const int4 lo = *reinterpret_cast<const int4 *>(&s_fft[PP(e)]), hi = *reinterpret_cast<const int4 *>(&s_fft[PP(e) + 2]);
+        int2 w0 = make_int2(lo.x, lo.y), w1 = make_int2(lo.z, lo.w), w2 = make_int2(hi.x, hi.y), w3 = make_int2(hi.z, hi.w);
+        q15fft::last_r<SAT>(w0, w1, w2, w3);
+        v[2 * r] = (uint16_t)sqrt_u32_approx_fast((uint32_t)(w0.x * w0.x) + (uint32_t)(w0.y * w0.y), s_guess);
+        v[2 * r + 1] = (uint16_t)sqrt_u32_approx_fast((uint32_t)(w2.x * w2.x) + (uint32_t)(w2.y * w2.y), s_guess);
+    }
+}
+
 __global__ void __launch_bounds__(NT) k_spec1024(Spec1024Args a)
 {
     __shared__ __align__(16) int2 s_fft[1024 + 64];               // unpacked (re, im), element i at PP(i)
     __shared__ uint16_t s_guess[34];
+    __shared__ int s_amax[2];
     if (threadIdx.x < 33) s_guess[threadIdx.x] = c_sqrt_guess[threadIdx.x];
 
     const int tid = threadIdx.x;
@@ -55,59 +114,20 @@ __global__ void __launch_bounds__(NT) k_spec1024(Spec1024Args a)
                 const int32_t smp = ring[(int)((tick + 1 + b) & 7ull) * RDSP_BLK + n];
                 x[d4][d3] = make_int2((int16_t)((smp * (int32_t)__ldg(a.win + i)) >> 15), 0);      // imaginary part 0
             }
-#pragma unroll
-        for (int d3 = 0; d3 < 4; d3++) {                            // stage 1: span 256, twiddle step 4, j = 64 d3 + tid
-            const int ic = 4 * (64 * d3 + tid);
-            q15fft::first_real_r(x[0][d3], x[1][d3], x[2][d3], x[3][d3], a.tw[ic], a.tw[2 * ic], a.tw[3 * ic]);
-        }
-        {
-            const int ic = 16 * tid;                                // stage 2: span 64, twiddle step 16, j = tid
-            const int2 t1 = a.tw[ic], t2 = a.tw[2 * ic], t3 = a.tw[3 * ic];
-#pragma unroll
-            for (int d4 = 0; d4 < 4; d4++) q15fft::middle_r(x[d4][0], x[d4][1], x[d4][2], x[d4][3], t1, t2, t3);
-        }
+        // a frame that provably cannot saturate (fft_q15.cuh) takes the butterflies without the min / max pairs
+        int amax = 0;
 #pragma unroll
         for (int d4 = 0; d4 < 4; d4++)
 #pragma unroll
-            for (int d3 = 0; d3 < 4; d3++) s_fft[PP(256 * d4 + 64 * d3 + tid)] = x[d4][d3];
+            for (int d3 = 0; d3 < 4; d3++) amax = max(amax, abs(x[d4][d3].x));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if ((tid & 31) == 0) s_amax[tid >> 5] = amax;
         __syncthreads();
-        // ---- pass 2: stages 3 + 4 on y[d2][d1] = element base + 16 d2 + 4 d1, base = 64 (tid >> 2) + (tid & 3)
-        {
-            const int base = 64 * (tid >> 2) + (tid & 3), d0 = tid & 3;
-            int2 y[4][4];
-#pragma unroll
-            for (int d2 = 0; d2 < 4; d2++)
-#pragma unroll
-                for (int d1 = 0; d1 < 4; d1++) y[d2][d1] = s_fft[PP(base + 16 * d2 + 4 * d1)];
-#pragma unroll
-            for (int d1 = 0; d1 < 4; d1++) {                        // stage 3: span 16, twiddle step 64, j = 4 d1 + d0
-                const int ic = 64 * (4 * d1 + d0);
-                q15fft::middle_r(y[0][d1], y[1][d1], y[2][d1], y[3][d1], a.tw[ic], a.tw[2 * ic], a.tw[3 * ic]);
-            }
-            {
-                const int ic = 256 * d0;                            // stage 4: span 4, twiddle step 256, j = d0
-                const int2 t1 = a.tw[ic], t2 = a.tw[2 * ic], t3 = a.tw[3 * ic];
-#pragma unroll
-                for (int d2 = 0; d2 < 4; d2++) q15fft::middle_r(y[d2][0], y[d2][1], y[d2][2], y[d2][3], t1, t2, t3);
-            }
-#pragma unroll
-            for (int d2 = 0; d2 < 4; d2++)
-#pragma unroll
-                for (int d1 = 0; d1 < 4; d1++) s_fft[PP(base + 16 * d2 + 4 * d1)] = y[d2][d1];
-        }
-        __syncthreads();
-        // ---- pass 3: last stage on elements 4b .. 4b+3, b = tid + 64 r; bins 0..511 are the EVEN elements
-        // (bin = bitrev10(element)): magnitudes straight from the registers
+        const bool no_sat = max(s_amax[0], s_amax[1]) <= q15fft::NO_SAT_BOUND_1024_REAL;
         uint16_t v[8];
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int e = 4 * (tid + NT * r);
-            const int4 lo = *reinterpret_cast<const int4 *>(&s_fft[PP(e)]), hi = *reinterpret_cast<const int4 *>(&s_fft[PP(e) + 2]);
-            int2 w0 = make_int2(lo.x, lo.y), w1 = make_int2(lo.z, lo.w), w2 = make_int2(hi.x, hi.y), w3 = make_int2(hi.z, hi.w);
-            q15fft::last_r(w0, w1, w2, w3);
-            v[2 * r] = (uint16_t)sqrt_u32_approx_fast((uint32_t)(w0.x * w0.x) + (uint32_t)(w0.y * w0.y), s_guess);
-            v[2 * r + 1] = (uint16_t)sqrt_u32_approx_fast((uint32_t)(w2.x * w2.x) + (uint32_t)(w2.y * w2.y), s_guess);
-        }
+        if (no_sat) fft1024_passes<false>(x, s_fft, a, s_guess, tid, v);
+        else fft1024_passes<true>(x, s_fft, a, s_guess, tid, v);
         __syncthreads();
         // stage the u16 results in natural order on top of the (now dead) frame, store them coalesced
         uint16_t *s_o = reinterpret_cast<uint16_t *>(s_fft);

@@ -297,10 +297,14 @@ def test_explicit_mask_is_data(rd, po):
 
 @pytest.mark.parametrize("nav,blocks_per_call", [(30, 1), (30, 16), (4, 3), (1, 7)])
 def test_spec256_bit_exact(rd, po, nav, blocks_per_call):
-    nc, nb = 19, 66
+    nc, nb = 27, 66
     iq = synth.synth_iq(np.arange(nc), nb, [c % 5 for c in range(nc)])
     iq[:, 3] = np.where((np.arange(nb * 128) // 5) % 2 == 0, 32767, -32768).astype(np.int16).reshape(nb, 128, 1)   # saturation
     iq[:, 4] = 0
+    # random +-A frames from moderate levels up to hard clipping (the saturating butterflies at work)
+    rng = np.random.default_rng(21)
+    for c, amp in zip(range(19, 27), (9000, 10900, 11000, 11100, 11600, 13000, 20000, 32767)):
+        iq[:, c] = (rng.integers(0, 2, (nb, 128, 2)) * 2 - 1) * amp
     bank = make_bank(rd, nc, rd.STAGE_SPEC256, spec256_naverage=nav)
     chans = [po.OracleChan(po.default_config(stage_mask=po.STAGE_SPEC256, spec256_naverage=nav)) for _ in range(nc)]
     n_ready = 0
@@ -331,9 +335,13 @@ def test_spec256_bit_exact(rd, po, nav, blocks_per_call):
 
 @pytest.mark.parametrize("blocks_per_call", [1, 3, 8, 13])
 def test_spec1024_bit_exact(rd, po, blocks_per_call):
-    nc, nb = 7, 39
+    nc, nb = 12, 39
     iq = synth.synth_iq(np.arange(50, 50 + nc), nb, [c % 5 for c in range(nc)])
     params = [po.default_params(demod=c % 5) for c in range(nc)]
+    # loud audio on both sides of the bound below which the kernel takes its saturation-free butterflies
+    # (fft_q15.cuh: NO_SAT_BOUND_1024_REAL = 11000 on the windowed samples), up to hard clipping
+    for c, g in zip(range(7, 12), (1.6, 2.2, 3.0, 5.0, 12.0)):
+        params[c] = po.default_params(demod=c % 2, in_gain=g)
     sm = rd.STAGE_FRONTEND | rd.STAGE_SPEC1024           # bit-exact audio => the spectrum must be bit-exact too
     bank = make_bank(rd, nc, sm)
     chans = []
