@@ -341,8 +341,10 @@ def run_b200(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     launches0 = bank.kernel_launches
     t_wall0 = time.time()
+    no_flush = bool(os.environ.get("RDSP_BENCH_NO_FLUSH"))      # experiments only (the reported numbers always flush)
     for i in range(K):
-        flush.zero_()                                  # L2 flush between timed iterations (outside the per-step events)
+        if not no_flush:
+            flush.zero_()                              # L2 flush between timed iterations (outside the per-step events)
         ev[i][0].record(stream)
         step(W + i)
         ev[i][1].record(stream)
