@@ -862,7 +862,8 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
         // the channels whose notch runs form their own chain on the side stream (when both classes exist)
         int fn = 0, nn = 0, fp = 0, np = 0;
         if (fe && notch) { sub(h->l_notch, c0, c1, fn, nn); sub(h->l_plain, c0, c1, fp, np); }
-        const bool split = piped && fe && notch && nn > 0 && np > 0;
+        static const bool no_split = [] { const char *e = getenv("RDSP_NO_SPLIT"); return e && e[0] == '1'; }();   // experiments
+        const bool split = piped && fe && notch && nn > 0 && np > 0 && !no_split;
         if (split) {
             CK(cudaStreamWaitEvent(s_side, h->ev_front, 0));
             int rc2 = run_chain(s_side, 2, c0, c1);
