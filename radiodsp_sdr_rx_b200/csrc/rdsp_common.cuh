@@ -84,7 +84,7 @@ __device__ __forceinline__ uint32_t sqrt_u32_approx(uint32_t in)
 }
 
 // The same function with its two divisions done by a float estimate and an exact fix-up (the quotients stay below
-// 2^18, where the estimate is off by at most one; two correction rounds are applied).  The int <-> float
+// 2^18, where the estimate is off by at most one).  The int <-> float
 // conversions use the 2^23 magic number (FADD / LOP, full rate) instead of I2F / F2I (16 lanes/clk/SM), and the seed
 // table is read through `guess` (a shared-memory copy of c_sqrt_guess: lanes index it divergently, which constant
 // memory would serialise).  Bit-identical to sqrt_u32_approx for every input (tools/front_tc_check, test_gpu_parity).
@@ -94,13 +94,10 @@ __device__ __forceinline__ uint32_t rdsp_udiv_small_q(uint32_t n, float n_f, uin
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(rdsp_small_u2f(d)));
     uint32_t q = __float_as_uint(n_f * r + 8388608.0f) & 0x7FFFFFu;
-    int32_t rem = (int32_t)(n - q * d);
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const bool lo = rem < 0, hi = rem >= (int32_t)d;
-        q += hi ? 1u : (lo ? 0xFFFFFFFFu : 0u);
-        rem += hi ? -(int32_t)d : (lo ? (int32_t)d : 0);
-    }
+    // n_f, the reciprocal and the product carry 2^-24 + 2^-23 + 2^-24 of relative error: with q < 2^18 the rounded
+    // estimate is within 0.57 of n / d, i.e. off by at most one in either direction
+    const int32_t rem = (int32_t)(n - q * d);
+    q += rem >= (int32_t)d ? 1u : (rem < 0 ? 0xFFFFFFFFu : 0u);
     return q;
 }
 __device__ __forceinline__ uint32_t sqrt_u32_approx_fast(uint32_t in, const uint16_t *guess)
