@@ -41,7 +41,7 @@ constexpr int PLANE_B = SLICES * SLICE_B;     // 24576
 constexpr int TOEP_PLANE_B = 10 * NOUT * 16;  // 5120: [10 k-groups][32 outputs][16 bytes]
 constexpr int TOEP_SET_B = 2 * TOEP_PLANE_B;  // lo plane, hi plane
 
-constexpr int W_E2 = 4, W_LD = 8, W_MMA = 12, NWARPS = 13;    // warps 0-3 are epilogue 1
+constexpr int W_E2 = 4, W_LD = 8, W_MMA = 12, W_MMA2 = 13, NWARPS = 14;    // warps 0-3 are epilogue 1
 constexpr int NTHREADS = NWARPS * 32;
 
 constexpr int OFF_RING = 0;                                   // [line 0..2][plane 0..1][PLANE_B]
@@ -290,6 +290,10 @@ __device__ __forceinline__ void state_io(const TcSmem &s, int16_t *hist, int fir
 
 // ---- MMA issue ----------------------------------------------------------------------------------------------------
 // one 129-tap FIR over 128 rows x 32 outputs: 5 K steps x 4 byte-plane products into (ll, mid, hh) at tmem_d
+// PART 0: all three accumulators; 1: ll and hh; 2: mid — two issuing threads may share one FIR, each owning whole
+// accumulators (the order between MMAs of different threads is not defined, the first write of an accumulator must
+// clear it)
+template <int PART = 0>
 __device__ __forceinline__ void issue_fir(uint32_t ring_lo, uint32_t ring_hi, uint32_t taps_lo, uint32_t taps_hi, uint32_t tmem_d, int c)
 {
     int sl = c % SLICES;
@@ -298,10 +302,10 @@ __device__ __forceinline__ void issue_fir(uint32_t ring_lo, uint32_t ring_hi, ui
         const uint32_t so = (uint32_t)(sl * SLICE_B);
         const uint64_t a_lo = make_desc(ring_lo + so, ROWS * 16), a_hi = make_desc(ring_hi + so, ROWS * 16);
         const uint64_t b_lo = make_desc(taps_lo + ks * 2 * NOUT * 16, NOUT * 16), b_hi = make_desc(taps_hi + ks * 2 * NOUT * 16, NOUT * 16);
-        mma_i8(tmem_d + 0 * NOUT, a_lo, b_lo, IDESC_UU, ks > 0);
-        mma_i8(tmem_d + 1 * NOUT, a_hi, b_lo, IDESC_SU, ks > 0);
-        mma_i8(tmem_d + 1 * NOUT, a_lo, b_hi, IDESC_US, 1);
-        mma_i8(tmem_d + 2 * NOUT, a_hi, b_hi, IDESC_SS, ks > 0);
+        if (PART != 2) mma_i8(tmem_d + 0 * NOUT, a_lo, b_lo, IDESC_UU, ks > 0);
+        if (PART != 1) mma_i8(tmem_d + 1 * NOUT, a_hi, b_lo, IDESC_SU, ks > 0);
+        if (PART != 1) mma_i8(tmem_d + 1 * NOUT, a_lo, b_hi, IDESC_US, 1);
+        if (PART != 2) mma_i8(tmem_d + 2 * NOUT, a_hi, b_hi, IDESC_SS, ks > 0);
         sl = sl + 1 == SLICES ? 0 : sl + 1;
     }
 }
@@ -490,9 +494,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
     auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     if (threadIdx.x == 0) {
         mbar_init(bar(B_IN_FULL), ROWS); mbar_init(bar(B_IN_FULL + 1), ROWS);
-        mbar_init(bar(B_M1_DONE), 1); mbar_init(bar(B_M1_DONE + 1), 1);
+        mbar_init(bar(B_M1_DONE), RDSP_TC_A_TMEM ? 1 : 2); mbar_init(bar(B_M1_DONE + 1), RDSP_TC_A_TMEM ? 1 : 2);   // two issuing threads commit (I' FIR, Q' FIR)
         mbar_init(bar(B_E1_DONE), ROWS); mbar_init(bar(B_E1_DONE + 1), ROWS);
-        mbar_init(bar(B_M2_DONE), 1); mbar_init(bar(B_M2_DONE + 1), 1);
+        mbar_init(bar(B_M2_DONE), RDSP_TC_A_TMEM ? 1 : 2); mbar_init(bar(B_M2_DONE + 1), RDSP_TC_A_TMEM ? 1 : 2);
         mbar_init(bar(B_E2_DONE), ROWS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -606,8 +610,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
                     TCP(3);
                     tc_fence_after();
                     const uint32_t acc1 = tmem + (c & 1) * TM_ACC1B;
-                    issue_fir(rI0, rI1, tA0, tA1, acc1, c);
-                    issue_fir(rQ0, rQ1, tB0, tB1, acc1 + 3 * NOUT, c);
+                    issue_fir<0>(rI0, rI1, tA0, tA1, acc1, c);              // the Q' FIR is issued by the second issuer warp
 #endif
                     mma_commit(bar(B_M1_DONE + (c & 1)));
                     TCP(4);
@@ -619,9 +622,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
                     if (cc >= 1) mbar_wait(bar(B_E2_DONE), (cc - 1) & 1);
                     TCP(6);
                     tc_fence_after();
-                    issue_fir(rD0, rD1, tM0, tM1, tmem + TM_ACC2P, cc);
+#if RDSP_TC_A_TMEM
+                    issue_fir<0>(rD0, rD1, tM0, tM1, tmem + TM_ACC2P, cc);
+#else
+                    issue_fir<1>(rD0, rD1, tM0, tM1, tmem + TM_ACC2P, cc);         // ll, hh here; mid by the second issuer
+#endif
                     mma_commit(bar(B_M2_DONE + (cc & 1)));
                     TCP(7);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == W_MMA2) {
+        // ===== second MMA issuer: the Q' FIR of every chunk (two issuing threads keep the tensor pipe at ~40 clk per
+        // MMA instead of ~52, tools/ubench_umma.cu); same waits as the first issuer, own commit on m1_done =====
+        if (lane == 0 && !RDSP_TC_A_TMEM) {
+            const uint32_t rQ0 = smem_u32(s.ring(1, 0)), rQ1 = smem_u32(s.ring(1, 1));
+            const uint32_t tB0 = smem_u32(s.taps(1, 0)), tB1 = smem_u32(s.taps(1, 1));
+            const uint32_t rD0 = smem_u32(s.ring(2, 0)), rD1 = smem_u32(s.ring(2, 1));
+            const uint32_t tM0 = smem_u32(s.taps(2, 0)), tM1 = smem_u32(s.taps(2, 1));
+#pragma unroll 1
+            for (int c = 0; c <= nch; c++) {
+                if (c < nch) {
+                    mbar_wait(bar(B_IN_FULL + (c & 1)), (c >> 1) & 1);
+                    if (c >= 2) mbar_wait(bar(B_E1_DONE + (c & 1)), ((c - 2) >> 1) & 1);
+                    tc_fence_after();
+                    issue_fir<0>(rQ0, rQ1, tB0, tB1, tmem + (c & 1) * TM_ACC1B + 3 * NOUT, c);
+                    mma_commit(bar(B_M1_DONE + (c & 1)));
+                }
+                if (c >= 1) {
+                    const int cc = c - 1;                                  // the mid accumulator of the band-pass FIR
+                    mbar_wait(bar(B_E1_DONE + (cc & 1)), (cc >> 1) & 1);
+                    if (cc >= 1) mbar_wait(bar(B_E2_DONE), (cc - 1) & 1);
+                    tc_fence_after();
+                    issue_fir<2>(rD0, rD1, tM0, tM1, tmem + TM_ACC2P, cc);
+                    mma_commit(bar(B_M2_DONE + (cc & 1)));
                 }
             }
         }
