@@ -30,6 +30,11 @@
 #include <array>
 #include <cstring>
 
+#ifndef RDSP_TC_A_TMEM
+#define RDSP_TC_A_TMEM 0
+#endif
+#define RDSP_TC_A_TMEM_EARLY RDSP_TC_A_TMEM
+
 namespace {
 
 constexpr int ROWS = 128;                     // channels per tile = MMA M
@@ -41,7 +46,9 @@ constexpr int PLANE_B = SLICES * SLICE_B;     // 24576
 constexpr int TOEP_PLANE_B = 10 * NOUT * 16;  // 5120: [10 k-groups][32 outputs][16 bytes]
 constexpr int TOEP_SET_B = 2 * TOEP_PLANE_B;  // lo plane, hi plane
 
-constexpr int W_E2 = 4, W_LD = 8, W_MMA = 12, W_MMA2 = 13, NWARPS = 14;    // warps 0-3 are epilogue 1
+constexpr int NLD = RDSP_TC_A_TMEM_EARLY ? 4 : 8;             // loader warps (the TMEM-operand variant maps them on lane quadrants)
+constexpr int ITEMS = 32 / NLD;                               // (row group, k-group) items per loader warp and chunk
+constexpr int W_E2 = 4, W_LD = 8, W_MMA = W_LD + NLD, W_MMA2 = W_MMA + 1, NWARPS = W_MMA2 + 1;    // warps 0-3 are epilogue 1
 constexpr int NTHREADS = NWARPS * 32;
 
 constexpr int OFF_RING = 0;                                   // [line 0..2][plane 0..1][PLANE_B]
@@ -60,9 +67,6 @@ static_assert(SMEM_B <= 227 * 1024, "shared memory budget");
 // K = 32 costs ~52 clk for every N <= 64 whether A comes from shared memory or TMEM (64 clk at N = 128, 128 at
 // N = 256; ~40 clk with several issuing warps) — the N = 32 MMAs of this kernel pay a fixed per-instruction cost, not
 // operand fetch, and the .ts form only loses the second accumulator set.  Kept as an option for the record.
-#ifndef RDSP_TC_A_TMEM
-#define RDSP_TC_A_TMEM 0
-#endif
 constexpr int TM_COLS = 512;
 constexpr int TM_RING = 0, TM_PLANE = 48;
 constexpr int TM_ACC1B = 192, TM_ACC2P = 384;
@@ -167,7 +171,7 @@ struct TcSmem {
     uint8_t *base;
     __device__ __forceinline__ uint8_t *ring(int line, int plane) const { return base + OFF_RING + (line * 2 + plane) * PLANE_B; }
     __device__ __forceinline__ uint8_t *taps(int set, int plane) const { return base + OFF_TAPS + (set * 2 + plane) * TOEP_PLANE_B; }
-    __device__ __forceinline__ uint8_t *stage(int buf, int lw) const { return base + OFF_STAGE + buf * STAGE_B + lw * (STAGE_B / 4); }
+    __device__ __forceinline__ uint8_t *stage(int buf, int lw) const { return base + OFF_STAGE + buf * STAGE_B + lw * (STAGE_B / NLD); }
     __device__ __forceinline__ int *row_ch() const { return reinterpret_cast<int *>(base + OFF_META); }
     __device__ __forceinline__ int *row_mi() const { return reinterpret_cast<int *>(base + OFF_META + ROWS * 4); }
     __device__ __forceinline__ int *row_mq() const { return reinterpret_cast<int *>(base + OFF_META + ROWS * 8); }
@@ -192,8 +196,8 @@ __device__ __forceinline__ void fetch_chunk(const TcSmem &s, const FrontArgs &a,
     const int rr = lane >> 2, q = lane & 3;
     const uint32_t st = smem_u32(s.stage(buf, lw)) + lane * 16;
 #pragma unroll 1
-    for (int k = 0; k < 8; k++) {
-        const int i = lw + 4 * k, g = i & 1, row = (i >> 1) * 8 + rr;
+    for (int k = 0; k < ITEMS; k++) {
+        const int i = lw + NLD * k, g = i & 1, row = (i >> 1) * 8 + rr;
         const int ch = s.row_ch()[row];
         const int16_t *src = a.iq + (((size_t)t * a.C + (ch >= 0 ? ch : 0)) * RDSP_BLK + cq * NOUT + g * 16 + q * 4) * 2;
         cp_async16(st + k * 512, src, ch >= 0 ? 16u : 0u);               // padding rows: zero fill
@@ -207,8 +211,8 @@ __device__ __forceinline__ void split_chunk(const TcSmem &s, int buf, int slice,
     const int rr = lane >> 2, q = lane & 3;
     const uint8_t *st = s.stage(buf, lw) + lane * 16;
 #pragma unroll 1
-    for (int k = 0; k < 8; k++) {
-        const int i = lw + 4 * k, g = i & 1, row = (i >> 1) * 8 + rr;
+    for (int k = 0; k < ITEMS; k++) {
+        const int i = lw + NLD * k, g = i & 1, row = (i >> 1) * 8 + rr;
         const int4 v = *reinterpret_cast<const int4 *>(st + k * 512);
         uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
         const int mi = s.row_mi()[row], mq = s.row_mq()[row];
@@ -242,12 +246,12 @@ __device__ __forceinline__ void split_chunk(const TcSmem &s, int buf, int slice,
     }
 }
 
-// after every loader thread has added its frames of a chunk: thread r closes the chunk of row r (running magnitude,
-// next threshold); two named barriers among the 128 loader threads fence the exchange
+// after every loader thread has added its frames of a chunk: thread r < 128 closes the chunk of row r (running
+// magnitude, next threshold); two named barriers among the loader threads fence the exchange
 __device__ __forceinline__ void nb_close_chunk(const TcSmem &s, int r)
 {
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const uint32_t mult = s.nb_mult()[r];
+    asm volatile("bar.sync 1, %0;" :: "n"(NLD * 32) : "memory");
+    const uint32_t mult = r < ROWS ? s.nb_mult()[r] : 0u;
     if (mult) {
         int32_t ref = s.nb_ref()[r];
         const int32_t cm = (int32_t)(s.nb_sum()[r] >> 5);
@@ -256,7 +260,7 @@ __device__ __forceinline__ void nb_close_chunk(const TcSmem &s, int r)
         s.nb_thr()[r] = ref > 0 ? (uint32_t)(((uint32_t)ref * mult) >> 8) : 0xFFFFFFFFu;
         s.nb_sum()[r] = 0u;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" :: "n"(NLD * 32) : "memory");
 }
 
 // ---- delay-line state <-> ring, all warps -------------------------------------------------------------------------
@@ -434,8 +438,8 @@ __device__ unsigned long long g_tc_cta[4096][2];
 #endif
 
 // ---- the kernel: warp-specialised pipeline over the chunks of one tile -----------------------------------------------
-//   warps 0-3   epilogue 1 (TMEM lane quadrant = warp)         warps 8-11  loader (HBM -> gain -> byte planes)
-//   warps 4-7   epilogue 2 (quadrant = warp - 4)               warp 12     MMA issue (one lane)
+//   warps 0-3   epilogue 1 (TMEM lane quadrant = warp)         warps 8-15  loader (HBM -> gain -> byte planes)
+//   warps 4-7   epilogue 2 (quadrant = warp - 4)               warps 16,17 MMA issue (one lane each)
 //   in_full[2]   loader -> MMA      chunk c's I'/Q' slice is in shared memory                      (128 arrivals)
 //   m1_done[2]   MMA -> E1, loader  Hilbert-pair MMAs of chunk c retired: acc1[c&1] valid, slice c%6 free (commit)
 //   e1_done[2]   E1 -> MMA          acc1[c&1] drained and the D slice of chunk c written           (128 arrivals)
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
     const uint32_t bar0 = smem_u32(s.bars());
     auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     if (threadIdx.x == 0) {
-        mbar_init(bar(B_IN_FULL), ROWS); mbar_init(bar(B_IN_FULL + 1), ROWS);
+        mbar_init(bar(B_IN_FULL), NLD * 32); mbar_init(bar(B_IN_FULL + 1), NLD * 32);
         mbar_init(bar(B_M1_DONE), RDSP_TC_A_TMEM ? 1 : 2); mbar_init(bar(B_M1_DONE + 1), RDSP_TC_A_TMEM ? 1 : 2);   // two issuing threads commit (I' FIR, Q' FIR)
         mbar_init(bar(B_E1_DONE), ROWS); mbar_init(bar(B_E1_DONE + 1), ROWS);
         mbar_init(bar(B_M2_DONE), RDSP_TC_A_TMEM ? 1 : 2); mbar_init(bar(B_M2_DONE + 1), RDSP_TC_A_TMEM ? 1 : 2);
@@ -504,7 +508,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
     if (seg == 0) {
         state_io<false>(s, a.hist, 0, warp, lane);                         // delay lines of the previous call -> slices 0..3
     } else {
-        if (warp >= W_LD && warp < W_LD + 4) {
+        if (warp >= W_LD && warp < W_LD + NLD) {
 #pragma unroll 1
             for (int cq = 0; cq < 4; cq++) {
                 fetch_chunk(s, a, t0 - 1, cq, cq & 1, warp - W_LD, lane);
@@ -533,7 +537,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
     tc_fence_after();
     const uint32_t tmem = *s.tmem_ptr();
 #if RDSP_TC_A_TMEM
-    if (warp >= W_LD && warp < W_LD + 4) {
+    if (warp >= W_LD && warp < W_LD + NLD) {
         const int r = (warp - W_LD) * 32 + lane;
         const uint32_t tl = tmem + ((uint32_t)((warp - W_LD) * 32) << 16);
 #pragma unroll 1
@@ -546,7 +550,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
 #endif
     TCQ(13);
 
-    if (warp >= W_LD && warp < W_LD + 4) {
+    if (warp >= W_LD && warp < W_LD + NLD) {
         // ===== loader =====
         const int lw = warp - W_LD;
         bool tile_nb = false;                                              // any blanked row in this tile (CTA-uniform)
@@ -582,7 +586,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
             if (lw == 0) TCP(1);
         }
         if (tile_nb) {
-            const int r = lw * 32 + lane, ch = s.row_ch()[r];
+            const int r = lw * 32 + lane, ch = r < ROWS ? s.row_ch()[r] : -1;
             if (ch >= 0 && s.nb_mult()[r]) a.nb_ref[ch] = s.nb_ref()[r];
         }
     } else if (warp == W_MMA) {
