@@ -48,7 +48,9 @@ constexpr int TOEP_SET_B = 2 * TOEP_PLANE_B;  // lo plane, hi plane
 
 constexpr int NLD = RDSP_TC_A_TMEM_EARLY ? 4 : 8;             // loader warps (the TMEM-operand variant maps them on lane quadrants)
 constexpr int ITEMS = 32 / NLD;                               // (row group, k-group) items per loader warp and chunk
-constexpr int W_E2 = 4, W_LD = 8, W_MMA = W_LD + NLD, W_MMA2 = W_MMA + 1, NWARPS = W_MMA2 + 1;    // warps 0-3 are epilogue 1
+// warps 0-3: epilogue 1, outputs 0..15 of a chunk; W_E1B..+3: epilogue 1, outputs 16..31 (same TMEM lane quadrants)
+constexpr int W_E2 = 4, W_LD = 8, W_E1B = W_LD + NLD, W_MMA = W_E1B + 4, W_MMA2 = W_MMA + 1, NWARPS = W_MMA2 + 1;
+static_assert(W_E1B % 4 == 0, "the second epilogue-1 group must sit on the lane quadrants of its warp indices");
 constexpr int NTHREADS = NWARPS * 32;
 
 constexpr int OFF_RING = 0;                                   // [line 0..2][plane 0..1][PLANE_B]
@@ -349,10 +351,10 @@ __device__ __forceinline__ void slice_to_tmem(const TcSmem &s, uint32_t tmem_lan
 struct SamState { float phi, omega, dc; };
 
 template <int MODE>
-__device__ __forceinline__ void epilogue1(const TcSmem &s, uint32_t tmem_row, int row, int slice, bool usb, SamState &sam)
+__device__ __forceinline__ void epilogue1(const TcSmem &s, uint32_t tmem_row, int row, int slice, bool usb, SamState &sam, int it0, int it1)
 {
 #pragma unroll 1
-    for (int it = 0; it < 4; it++) {
+    for (int it = it0; it < it1; it++) {
         uint32_t v[6][8];
 #pragma unroll
         for (int k = 0; k < 6; k++) tmem_ld8(tmem_row + k * NOUT + it * 8, v[k]);
@@ -438,11 +440,11 @@ __device__ unsigned long long g_tc_cta[4096][2];
 #endif
 
 // ---- the kernel: warp-specialised pipeline over the chunks of one tile -----------------------------------------------
-//   warps 0-3   epilogue 1 (TMEM lane quadrant = warp)         warps 8-15  loader (HBM -> gain -> byte planes)
-//   warps 4-7   epilogue 2 (quadrant = warp - 4)               warps 16,17 MMA issue (one lane each)
+//   warps 0-3, 16-19  epilogue 1 (TMEM lane quadrant = warp % 4) warps 8-15  loader (HBM -> gain -> byte planes)
+//   warps 4-7         epilogue 2 (quadrant = warp - 4)           warps 20,21 MMA issue (one lane each)
 //   in_full[2]   loader -> MMA      chunk c's I'/Q' slice is in shared memory                      (128 arrivals)
 //   m1_done[2]   MMA -> E1, loader  Hilbert-pair MMAs of chunk c retired: acc1[c&1] valid, slice c%6 free (commit)
-//   e1_done[2]   E1 -> MMA          acc1[c&1] drained and the D slice of chunk c written           (128 arrivals)
+//   e1_done[2]   E1 -> MMA          acc1[c&1] drained and the D slice of chunk c written           (256 arrivals)
 //   m2_done[2]   MMA -> E2, E1      band-pass MMAs of chunk c retired: acc2 valid, D slice c%6 free     (commit)
 //   e2_done      E2 -> MMA          acc2 drained                                                    (128 arrivals)
 // The band-pass MMAs of chunk c-1 are issued after the Hilbert MMAs of chunk c, so epilogue 1 overlaps tensor work.
@@ -499,7 +501,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
     if (threadIdx.x == 0) {
         mbar_init(bar(B_IN_FULL), NLD * 32); mbar_init(bar(B_IN_FULL + 1), NLD * 32);
         mbar_init(bar(B_M1_DONE), RDSP_TC_A_TMEM ? 1 : 2); mbar_init(bar(B_M1_DONE + 1), RDSP_TC_A_TMEM ? 1 : 2);   // two issuing threads commit (I' FIR, Q' FIR)
-        mbar_init(bar(B_E1_DONE), ROWS); mbar_init(bar(B_E1_DONE + 1), ROWS);
+        mbar_init(bar(B_E1_DONE), 2 * ROWS); mbar_init(bar(B_E1_DONE + 1), 2 * ROWS);     // both epilogue-1 groups arrive
         mbar_init(bar(B_M2_DONE), RDSP_TC_A_TMEM ? 1 : 2); mbar_init(bar(B_M2_DONE + 1), RDSP_TC_A_TMEM ? 1 : 2);
         mbar_init(bar(B_E2_DONE), ROWS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -665,14 +667,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
             }
         }
         __syncwarp();
-    } else if (warp < W_E2) {
-        // ===== epilogue 1 =====
-        const int row = threadIdx.x;
+    } else if (warp < W_E2 || (warp >= W_E1B && warp < W_E1B + 4)) {
+        // ===== epilogue 1: two groups of four warps share the 32 outputs of a chunk (the SAM loop is sequential over
+        // the samples of a row: there the first group takes all of them and the second only keeps the barriers moving) =====
+        const bool second = warp >= W_E1B;
+        const int quad = second ? warp - W_E1B : warp;
+        const int row = quad * 32 + lane;
         const bool usb = s.row_usb()[row] != 0;
-        const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t tmem_row = tmem + ((uint32_t)(quad * 32) << 16);
         const int ch1 = s.row_ch()[row];
+        const bool sam_tile = WITH_SAM && dmode == 2;
+        const int it0 = sam_tile ? (second ? 4 : 0) : (second ? 2 : 0), it1 = sam_tile ? 4 : (second ? 4 : 2);
         SamState sam{0.f, 0.f, 0.f};
-        if (WITH_SAM && dmode == 2 && ch1 >= 0) {
+        if (sam_tile && !second && ch1 >= 0) {
             const float4 st = *reinterpret_cast<const float4 *>(a.sam_state + (size_t)ch1 * 4);
             sam.phi = st.x; sam.omega = st.y; sam.dc = st.z;
         }
@@ -686,15 +693,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
             if (warp == 0) TCP(9);
             tc_fence_after();
             const uint32_t acc1 = tmem_row + (RDSP_TC_A_TMEM ? TM_ACC1B : (c & 1) * TM_ACC1B);
-            if (dmode == 1) epilogue1<1>(s, acc1, row, (c + 4) % SLICES, usb, sam);
-            else if (WITH_SAM && dmode == 2) epilogue1<2>(s, acc1, row, (c + 4) % SLICES, usb, sam);
-            else epilogue1<0>(s, acc1, row, (c + 4) % SLICES, usb, sam);
+            if (dmode == 1) epilogue1<1>(s, acc1, row, (c + 4) % SLICES, usb, sam, it0, it1);
+            else if (WITH_SAM && dmode == 2) epilogue1<2>(s, acc1, row, (c + 4) % SLICES, usb, sam, it0, it1);
+            else epilogue1<0>(s, acc1, row, (c + 4) % SLICES, usb, sam, it0, it1);
             tc_fence_before();
             fence_async_smem();
             mbar_arrive(bar(B_E1_DONE + (c & 1)));
             if (warp == 0) TCP(10);
         }
-        if (WITH_SAM && dmode == 2 && ch1 >= 0) *reinterpret_cast<float4 *>(a.sam_state + (size_t)ch1 * 4) = make_float4(sam.phi, sam.omega, sam.dc, 0.f);
+        if (sam_tile && !second && ch1 >= 0) *reinterpret_cast<float4 *>(a.sam_state + (size_t)ch1 * 4) = make_float4(sam.phi, sam.omega, sam.dc, 0.f);
     } else {
         // ===== epilogue 2 =====
         const int row = threadIdx.x - W_E2 * 32;
