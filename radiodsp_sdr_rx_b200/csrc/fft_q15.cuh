@@ -111,6 +111,17 @@ QHD void last(int2 *src, int b)
 
 // ---- the same butterflies on registers (in place: x0..x3 = elements i, i+n2, i+2 n2, i+3 n2) ----------------------
 // A thread that holds 16 elements can run two consecutive stages between two shared-memory round trips.
+QHD void first_r(int2 &x0, int2 &x1, int2 &x2, int2 &x3, int2 t1, int2 t2, int2 t3)          // t1 = tw[ic], t2 = tw[2ic], t3 = tw[3ic]
+{
+    int2 xa = x0, xb = x1, xc = x2, xd = x3;
+    xa.x >>= 2; xa.y >>= 2; xb.x >>= 2; xb.y >>= 2; xc.x >>= 2; xc.y >>= 2; xd.x >>= 2; xd.y >>= 2;
+    const int Rx = xa.x + xc.x, Ry = xa.y + xc.y, Sx = xa.x - xc.x, Sy = xa.y - xc.y;
+    const int Tx = xb.x + xd.x, Ty = xb.y + xd.y, Ux = xb.x - xd.x, Uy = xb.y - xd.y;
+    x0 = make_int2((Rx + Tx) >> 1, (Ry + Ty) >> 1);
+    x1 = cmul(t2, make_int2(Rx - Tx, Ry - Ty));
+    x2 = cmul(t1, make_int2(Sx + Uy, Sy - Ux));
+    x3 = cmul(t3, make_int2(Sx - Uy, Sy + Ux));
+}
 QHD void first_real_r(int2 &x0, int2 &x1, int2 &x2, int2 &x3, int2 t1, int2 t2, int2 t3)     // t1 = tw[ic], t2 = tw[2ic], t3 = tw[3ic]
 {
     const int xa = x0.x >> 2, xb = x1.x >> 2, xc = x2.x >> 2, xd = x3.x >> 2;
