@@ -7,14 +7,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 import radiodsp_sdr_rx_b200 as rd
 
-wl, C_, T = "cfg5", 8192, 8
+wl, C_, T = "cfg5", 8192, int(sys.argv[1]) if len(sys.argv) > 1 else 8
 dev = torch.device("cuda", 0)
 iq = bench.make_inputs(wl, 0, C_, T)
 d_in = torch.from_numpy(iq).to(dev)
 d_out = torch.zeros((T, C_, 128, 2), dtype=torch.int16, device=dev)
 stream = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(stream)
-for chunks in (1, 2, 4):
+for chunks in ((1,) if len(sys.argv) > 1 else (1, 2, 4)):
     cfg = rd.default_config(n_channels=C_, device=0, stage_mask=0x7F, max_blocks_per_call=T, io_location=rd.IO_DEVICE, pipeline_chunks=chunks)
     cfg.async_ = 1
     b = rd.ReceiverBank(cfg)
