@@ -25,6 +25,11 @@
 // delayed input (static indices through unrolling); the block sits in shared memory with a row stride that
 // keeps every 16-byte access of a quarter-warp on distinct banks.
 //
+// Both tap-sized loops run on the packed f32x2 FMA of sm_100 (FFMA2 = two IEEE f32 FMAs in one issue slot): taps are
+// held as pairs (c[i+1], c[i]) and the window twice, as even pairs (w[2q], w[2q+1]) and as odd pairs (w[2q+1], w[2q+2]),
+// so that every (x[k-1], x[k]) a pair of taps meets is an aligned register pair.  Each lane of a pair is exactly the
+// scalar FMA sequence of the unpacked form (even taps in one lane, odd taps in the other), so results do not change.
+//
 // The per-channel state in HBM is coefficients (384 B) + previous block (512 B) + energy: the CMSIS state
 // buffer (last 95 inputs), x0 and the lag sums are functions of the previous block, so they are not stored.
 #include "rdsp_common.cuh"
@@ -53,6 +58,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
     constexpr int CPW = 32 / G;                  // channels per warp
     static_assert(W % 4 == 0, "taps per lane must be a multiple of 4");
     __shared__ __align__(16) float s_x[NWARPS * CPW][XS];     // [0,128) previous block / outputs, [128,256) current
+    __shared__ __align__(16) float s_x1[NWARPS * CPW][XS];    // the same samples one to the left: s_x1[i] = x[i + 1]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane % G;                      // lane within the channel group
@@ -60,8 +66,13 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
     const bool active = li < a.n_list;
     const int ch = active ? (a.list ? a.list[li] : li) : 0;
     float *xb = s_x[warp * CPW + lane / G];
+    float *xs = s_x1[warp * CPW + lane / G];     // odd window pairs load from here as aligned 16-byte quads
 
-    float c[W], u[S];
+    constexpr int HP = S / 2;                    // window pairs
+    float2 cp[W / 2];                            // (c[2r+1], c[2r])
+    float2 E[HP] = {}, O[HP] = {};                       // E[q] = (w[2q], w[2q+1]), O[q] = (w[2q+1], w[(2q+2) % S])
+    auto w1 = [&](int m) -> float { m = ((m % S) + S) % S; return (m & 1) ? E[m / 2].y : E[m / 2].x; };
+    auto w2 = [&](int m) -> float2 { m = ((m % S) + S) % S; return (m & 1) ? O[m / 2] : E[m / 2]; };      // (w[m], w[m+1])
     float energy = 0.0f, mu = 0.0f;
     bool first = false, peak = false;
     if (active) {
@@ -70,16 +81,28 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
         peak = !a.mode && p.als_peak != 0;                               // ALS "peak": the notch stage emits the estimate
         const float *cf = a.coeff + (size_t)ch * RDSP_LMS_NTAPS;
 #pragma unroll
-        for (int i = 0; i < W; i++) c[i] = cf[95 - W * g - i];        // register i <-> delay W*g + i
+        for (int r = 0; r < W / 2; r++)                                // tap register i <-> delay W*g + i
+            cp[r] = *reinterpret_cast<const float2 *>(cf + 94 - W * g - 2 * r);
         const float4 *pv = reinterpret_cast<const float4 *>(a.prev + (size_t)ch * RDSP_BLK);
         for (int i = g; i < 32; i += G) st4(xb + 4 * i, pv[i]);
         energy = a.energy[ch];
         first = a.first[ch] != 0;
     } else {
 #pragma unroll
-        for (int i = 0; i < W; i++) c[i] = 0.0f;
+        for (int r = 0; r < W / 2; r++) cp[r] = make_float2(0.f, 0.f);
         for (int i = g; i < 32; i += G) st4(xb + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
     }
+    __syncwarp();
+    // shifted copy of [from, from + 128): xs[from + i] = xb[from + i + 1], and xs[from - 1] = xb[from]
+    auto shift_copy = [&](int from) {
+        for (int i = g; i < 32; i += G) {
+            const float4 v = ld4(xb + from + 4 * i);
+            const float nx = (from + 4 * i + 4 < 256) ? xb[from + 4 * i + 4] : 0.0f;
+            st4(xs + from + 4 * i, make_float4(v.y, v.z, v.w, nx));
+            if (i == 0 && from > 0) xs[from - 1] = v.x;
+        }
+    };
+    shift_copy(0);                               // xs[127] is completed when the first block is staged
     __syncwarp();
 
     for (int t = 0; t < a.T; t++) {
@@ -103,12 +126,16 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
             for (int i = g; i < 32; i += G) st4(xb + 128 + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
         }
         __syncwarp();
+        shift_copy(128);
+        __syncwarp();
 
         // ---- lane-relative window u[m] = x[m - W*g]; slots m mod S.  Before sample 0: m = -S .. -1 (all slots)
 #pragma unroll
         for (int q = 0; q < S / 4; q++) {
             const float4 v = ld4(xb + 128 - W * g - S + 4 * q);             // m = -S + 4q .. -S + 4q + 3
-            u[(4 * q + 0) % S] = v.x; u[(4 * q + 1) % S] = v.y; u[(4 * q + 2) % S] = v.z; u[(4 * q + 3) % S] = v.w;
+            E[2 * q] = make_float2(v.x, v.y); E[2 * q + 1] = make_float2(v.z, v.w);
+            const float4 o = ld4(xs + 128 - W * g - S + 4 * q);             // m + 1: the last one (slot 0) is sample 0 already
+            O[2 * q] = make_float2(o.x, o.y); O[2 * q + 1] = make_float2(o.z, o.w);
         }
         float4 xn_p = ld4(xb + 124);                 // x[-4..-1]
         float4 xo_p = ld4(xb + 28);                  // x[-100..-97]
@@ -129,10 +156,10 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
                         s1 = 0.f; s2 = 0.f; s3 = 0.f;
 #pragma unroll
                         for (int i = 0; i < W; i++) {
-                            const float uk = u[(sb - 1 - i + 2 * S) % S];
-                            s1 = fmaf(u[(sb - 2 - i + 2 * S) % S], uk, s1);
-                            s2 = fmaf(u[(sb - 3 - i + 2 * S) % S], uk, s2);
-                            s3 = fmaf(u[(sb - 4 - i + 2 * S) % S], uk, s3);
+                            const float uk = w1(sb - 1 - i);
+                            s1 = fmaf(w1(sb - 2 - i), uk, s1);
+                            s2 = fmaf(w1(sb - 3 - i), uk, s2);
+                            s3 = fmaf(w1(sb - 4 - i), uk, s3);
                         }
 #pragma unroll
                         for (int o = G / 2; o > 0; o >>= 1) {
@@ -143,7 +170,10 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
                     }
                     // ---- loads
                     const float4 un = ld4(xb + 128 + n - W * g);
-                    u[(sb + 0) % S] = un.x; u[(sb + 1) % S] = un.y; u[(sb + 2) % S] = un.z; u[(sb + 3) % S] = un.w;
+                    E[sb / 2] = make_float2(un.x, un.y); E[sb / 2 + 1] = make_float2(un.z, un.w);
+                    // odd pairs (w[sb+1], w[sb+2]), (w[sb+3], w[sb+4]): the slot of w[sb+4] held w[sb-W], which no pair needs any more
+                    const float4 uo = ld4(xs + 128 + n - W * g);
+                    O[sb / 2] = make_float2(uo.x, uo.y); O[sb / 2 + 1] = make_float2(uo.z, uo.w);
                     const float4 xn4 = ld4(xb + 128 + n);                   // in[n..n+3]
                     const float4 xo4 = ld4(xb + 32 + n);                    // x[n-96 .. n-93]
                     const float4 d4 = same_block_ref ? xn4 : ld4(xb + n);   // desired
@@ -155,21 +185,18 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
                     const float xq[8] = {xo_p.x, xo_p.y, xo_p.z, xo_p.w, xo4.x, xo4.y, xo4.z, xo4.w};   // x[n-100 .. n-93]
 
                     // ---- p[j] = c' x[n+j] with the coefficients at the start of the group
-                    float p0[4], p1[4];
+                    // (.y: even taps, .x: odd taps — two accumulators per sample, as the scalar form had them)
+                    float2 pa[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) { p0[j] = 0.f; p1[j] = 0.f; }
+                    for (int j = 0; j < 4; j++) pa[j] = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int i = 0; i < W; i++) {
+                    for (int r = 0; r < W / 2; r++) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const float uv = u[(sb + j - i + 2 * S) % S];
-                            if (i & 1) p1[j] = fmaf(c[i], uv, p1[j]);
-                            else p0[j] = fmaf(c[i], uv, p0[j]);
-                        }
+                        for (int j = 0; j < 4; j++) pa[j] = __ffma2_rn(cp[r], w2(sb + j - 2 * r - 1), pa[j]);
                     }
                     float p[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) p[j] = p0[j] + p1[j];
+                    for (int j = 0; j < 4; j++) p[j] = pa[j].y + pa[j].x;
 #pragma unroll
                     for (int o = G / 2; o > 0; o >>= 1) {
 #pragma unroll
@@ -213,9 +240,9 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
 
                     // ---- coefficient update c += sum_j g[j] x[n+j]
 #pragma unroll
-                    for (int i = 0; i < W; i++) {
+                    for (int r = 0; r < W / 2; r++) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) c[i] = fmaf(gj[j], u[(sb + j - i + 2 * S) % S], c[i]);
+                        for (int j = 0; j < 4; j++) cp[r] = __ffma2_rn(make_float2(gj[j], gj[j]), w2(sb + j - 2 * r - 1), cp[r]);
                     }
                     xn_p = xn4;
                     xo_p = xo4;
@@ -246,22 +273,28 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
             }
         }
         __syncwarp();
-        for (int i = g; i < 32; i += G) st4(xb + 4 * i, ld4(xb + 128 + 4 * i));   // current block becomes the previous one
+        for (int i = g; i < 32; i += G) {                                         // current block becomes the previous one
+            st4(xb + 4 * i, ld4(xb + 128 + 4 * i));
+            st4(xs + 4 * i, ld4(xs + 128 + 4 * i));
+        }
         // Safety net, outside the reference's arithmetic: when the running energy has lost its digits the recurrence can
         // run away to inf / NaN (it does in the reference too, and its coefficients then stay NaN for ever because
         // Init_LMS_NR never clears them).  A channel whose filter went non-finite restarts from zero coefficients.
         {
             float chk = energy;
 #pragma unroll
-            for (int i = 0; i < W; i++) chk += c[i];
+            for (int r = 0; r < W / 2; r++) chk += cp[r].x + cp[r].y;
             bool bad = !isfinite(chk);
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) bad |= (__shfl_xor_sync(0xffffffffu, (int)bad, o) != 0);
             if (bad) {
 #pragma unroll
-                for (int i = 0; i < W; i++) c[i] = 0.0f;
+                for (int r = 0; r < W / 2; r++) cp[r] = make_float2(0.f, 0.f);
                 energy = 0.0f;
-                for (int i = g; i < 32; i += G) st4(xb + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));   // like Init_LMS_NR: history cleared too
+                for (int i = g; i < 32; i += G) {                                                    // like Init_LMS_NR: history cleared too
+                    st4(xb + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+                    st4(xs + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+                }
             }
         }
         __syncwarp();
@@ -270,7 +303,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
     if (active) {
         float *cf = a.coeff + (size_t)ch * RDSP_LMS_NTAPS;
 #pragma unroll
-        for (int i = 0; i < W; i++) cf[95 - W * g - i] = c[i];
+        for (int r = 0; r < W / 2; r++) *reinterpret_cast<float2 *>(cf + 94 - W * g - 2 * r) = cp[r];
         float4 *pv = reinterpret_cast<float4 *>(a.prev + (size_t)ch * RDSP_BLK);
         for (int i = g; i < 32; i += G) pv[i] = ld4(xb + 4 * i);
         if (g == 0) {

@@ -158,10 +158,11 @@ class ReceiverBank:
             self._h = None
             raise RdspError(rc, lib().rdsp_gpu_last_error(None).decode())
         self.n_channels = int(cfg.n_channels)
+        self._destroy = lib().rdsp_gpu_destroy             # bound here: module globals are gone at interpreter exit
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().rdsp_gpu_destroy(self._h)
+            self._destroy(self._h)
             self._h = None
 
     __del__ = close
