@@ -22,11 +22,31 @@
 
 #define HD __host__ __device__ __forceinline__
 
-HD float2 c_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-HD float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-HD float2 c_mul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-HD float2 c_mulconj(float2 a, float2 w) { return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y); }   // a * conj(w)
+// Complex arithmetic on the packed f32x2 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: two IEEE f32 operations in one
+// issue slot; half swaps, per-half negation and scalar broadcast are operand modifiers, so the swapped / negated pairs
+// below cost nothing).  The host versions perform the same roundings (an explicit fmaf where the device fuses), which
+// keeps tests/host/test_device_math.cu a test of the device arithmetic.
+#ifndef RDSP_FFT_PACKED
+#define RDSP_FFT_PACKED 1
+#endif
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000 && RDSP_FFT_PACKED
+HD float2 p_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+HD float2 p_mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+HD float2 p_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#else
+HD float2 p_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+HD float2 p_mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+HD float2 p_fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+HD float2 c_add(float2 a, float2 b) { return p_add(a, b); }
+HD float2 c_sub(float2 a, float2 b) { return p_add(a, make_float2(-b.x, -b.y)); }
 HD float2 c_mul_mj(float2 a) { return make_float2(a.y, -a.x); }                                               // a * (-j)
+// a * b = (a.x b.x - a.y b.y, a.y b.x + a.x b.y)
+HD float2 c_mul(float2 a, float2 b) { return p_fma(make_float2(a.y, a.x), make_float2(-b.y, b.y), p_mul(a, make_float2(b.x, b.x))); }
+// conj(a * b) = (a.x b.x - a.y b.y, -a.y b.x - a.x b.y)
+HD float2 c_mul_conj_result(float2 a, float2 b) { return p_fma(make_float2(a.y, a.x), make_float2(-b.y, -b.y), p_mul(a, make_float2(b.x, -b.x))); }
+// a * conj(w) = (a.x w.x + a.y w.y, a.y w.x - a.x w.y)
+HD float2 c_mulconj(float2 a, float2 w) { return p_fma(make_float2(a.y, -a.x), make_float2(w.y, w.y), p_mul(a, make_float2(w.x, w.x))); }
 
 HD void dft4(float2 &c0, float2 &c1, float2 &c2, float2 &c3)
 {
@@ -41,9 +61,9 @@ HD void dft8(float2 v[8])
     float2 a0 = c_add(v[0], v[4]), a1 = c_add(v[1], v[5]), a2 = c_add(v[2], v[6]), a3 = c_add(v[3], v[7]);
     float2 b0 = c_sub(v[0], v[4]);
     const float2 d1 = c_sub(v[1], v[5]), d3 = c_sub(v[3], v[7]);
-    float2 b1 = make_float2(r * (d1.x + d1.y), r * (d1.y - d1.x));        // * W8^1
-    float2 b2 = c_mul_mj(c_sub(v[2], v[6]));                              // * W8^2
-    float2 b3 = make_float2(r * (d3.y - d3.x), -r * (d3.x + d3.y));       // * W8^3
+    float2 b1 = p_mul(p_add(d1, make_float2(d1.y, -d1.x)), make_float2(r, r));                       // * W8^1
+    float2 b2 = c_mul_mj(c_sub(v[2], v[6]));                                                         // * W8^2
+    float2 b3 = p_mul(p_add(make_float2(d3.y, -d3.x), make_float2(-d3.x, -d3.y)), make_float2(r, r)); // * W8^3
     dft4(a0, a1, a2, a3);
     dft4(b0, b1, b2, b3);
     v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;

@@ -71,16 +71,18 @@ __global__ void __launch_bounds__(WARPS * 32, 3) k_fftfilt(FftFiltArgs a)
         float2 v[8];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            v[j] = make_float2((float)lo16(pw[j]) / 32768.0f, (float)hi16(pw[j]) / 32768.0f);
-            v[4 + j] = make_float2((float)lo16(cw[j]) / 32768.0f, (float)hi16(cw[j]) / 32768.0f);
+            const float2 q15 = make_float2(1.0f / 32768.0f, 1.0f / 32768.0f);      // exact scaling, two lanes per instruction
+            v[j] = p_mul(make_float2((float)lo16(pw[j]), (float)hi16(pw[j])), q15);
+            v[4 + j] = p_mul(make_float2((float)lo16(cw[j]), (float)hi16(cw[j])), q15);
             pw[j] = cw[j];
         }
 
         fft256_warp(lane, v, buf, s_tw);                   // v[j] = X[lane + 32 j]
 
+        // the inverse transform is conj -> forward -> conj -> 1/N: the first conjugation rides on the product
         if (!spectral) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = c_mul(v[j], mk[j]);
+            for (int j = 0; j < 8; j++) v[j] = c_mul_conj_result(v[j], mk[j]);
         } else {
             float mag[8], part = 0.0f;
 #pragma unroll
@@ -99,19 +101,16 @@ __global__ void __launch_bounds__(WARPS * 32, 3) k_fftfilt(FftFiltArgs a)
             for (int j = 0; j < 8; j++) {
                 const float nm = mag[j] <= nfloor ? (float)((double)mag[j] * 0.2) : mag[j] - nfloor;
                 const float sc = mag[j] > 0.0f ? nm / mag[j] : 0.0f;     // keep the phase, new magnitude
-                v[j] = make_float2(v[j].x * sc, v[j].y * sc);
+                v[j] = p_mul(v[j], make_float2(sc, -sc));
             }
         }
 
-        // inverse = conj, forward, conj, 1/N
-#pragma unroll
-        for (int j = 0; j < 8; j++) v[j].y = -v[j].y;
         fft256_warp(lane, v, buf, s_tw);
 
         // keep x[128 + lane + 32 h]; re-distribute so that each lane owns 4 consecutive samples
 #pragma unroll
         for (int h = 0; h < 4; h++)
-            buf[lane + 32 * h] = make_float2(v[4 + h].x * (1.0f / 256.0f), -v[4 + h].y * (1.0f / 256.0f));
+            buf[lane + 32 * h] = p_mul(v[4 + h], make_float2(1.0f / 256.0f, -1.0f / 256.0f));
         __syncwarp();
         float2 o[4];
 #pragma unroll

@@ -50,7 +50,7 @@ constexpr float LMS_EPS = 0.000000119209289f;
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
-template <int G>
+template <int G, bool PACKED>
 __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
 {
     constexpr int W = RDSP_LMS_NTAPS / G;        // taps per lane (24 or 12)
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
     constexpr int CPW = 32 / G;                  // channels per warp
     static_assert(W % 4 == 0, "taps per lane must be a multiple of 4");
     __shared__ __align__(16) float s_x[NWARPS * CPW][XS];     // [0,128) previous block / outputs, [128,256) current
-    __shared__ __align__(16) float s_x1[NWARPS * CPW][XS];    // the same samples one to the left: s_x1[i] = x[i + 1]
+    __shared__ __align__(16) float s_x1[PACKED ? NWARPS * CPW : 1][XS];   // the same samples one to the left: s_x1[i] = x[i + 1]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane % G;                      // lane within the channel group
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
     const bool active = li < a.n_list;
     const int ch = active ? (a.list ? a.list[li] : li) : 0;
     float *xb = s_x[warp * CPW + lane / G];
-    float *xs = s_x1[warp * CPW + lane / G];     // odd window pairs load from here as aligned 16-byte quads
+    float *xs = s_x1[PACKED ? warp * CPW + lane / G : 0];     // odd window pairs load from here as aligned 16-byte quads
 
     constexpr int HP = S / 2;                    // window pairs
     float2 cp[W / 2];                            // (c[2r+1], c[2r])
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
     __syncwarp();
     // shifted copy of [from, from + 128): xs[from + i] = xb[from + i + 1], and xs[from - 1] = xb[from]
     auto shift_copy = [&](int from) {
+        if (!PACKED) return;
         for (int i = g; i < 32; i += G) {
             const float4 v = ld4(xb + from + 4 * i);
             const float nx = (from + 4 * i + 4 < 256) ? xb[from + 4 * i + 4] : 0.0f;
@@ -134,8 +135,10 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
         for (int q = 0; q < S / 4; q++) {
             const float4 v = ld4(xb + 128 - W * g - S + 4 * q);             // m = -S + 4q .. -S + 4q + 3
             E[2 * q] = make_float2(v.x, v.y); E[2 * q + 1] = make_float2(v.z, v.w);
-            const float4 o = ld4(xs + 128 - W * g - S + 4 * q);             // m + 1: the last one (slot 0) is sample 0 already
-            O[2 * q] = make_float2(o.x, o.y); O[2 * q + 1] = make_float2(o.z, o.w);
+            if (PACKED) {
+                const float4 o = ld4(xs + 128 - W * g - S + 4 * q);         // m + 1: the last one (slot 0) is sample 0 already
+                O[2 * q] = make_float2(o.x, o.y); O[2 * q + 1] = make_float2(o.z, o.w);
+            }
         }
         float4 xn_p = ld4(xb + 124);                 // x[-4..-1]
         float4 xo_p = ld4(xb + 28);                  // x[-100..-97]
@@ -172,8 +175,10 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
                     const float4 un = ld4(xb + 128 + n - W * g);
                     E[sb / 2] = make_float2(un.x, un.y); E[sb / 2 + 1] = make_float2(un.z, un.w);
                     // odd pairs (w[sb+1], w[sb+2]), (w[sb+3], w[sb+4]): the slot of w[sb+4] held w[sb-W], which no pair needs any more
-                    const float4 uo = ld4(xs + 128 + n - W * g);
-                    O[sb / 2] = make_float2(uo.x, uo.y); O[sb / 2 + 1] = make_float2(uo.z, uo.w);
+                    if (PACKED) {
+                        const float4 uo = ld4(xs + 128 + n - W * g);
+                        O[sb / 2] = make_float2(uo.x, uo.y); O[sb / 2 + 1] = make_float2(uo.z, uo.w);
+                    }
                     const float4 xn4 = ld4(xb + 128 + n);                   // in[n..n+3]
                     const float4 xo4 = ld4(xb + 32 + n);                    // x[n-96 .. n-93]
                     const float4 d4 = same_block_ref ? xn4 : ld4(xb + n);   // desired
@@ -192,7 +197,13 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
 #pragma unroll
                     for (int r = 0; r < W / 2; r++) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) pa[j] = __ffma2_rn(cp[r], w2(sb + j - 2 * r - 1), pa[j]);
+                        for (int j = 0; j < 4; j++) {
+                            if (PACKED) pa[j] = __ffma2_rn(cp[r], w2(sb + j - 2 * r - 1), pa[j]);
+                            else {
+                                pa[j].y = fmaf(cp[r].y, w1(sb + j - 2 * r), pa[j].y);
+                                pa[j].x = fmaf(cp[r].x, w1(sb + j - 2 * r - 1), pa[j].x);
+                            }
+                        }
                     }
                     float p[4];
 #pragma unroll
@@ -242,7 +253,13 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
 #pragma unroll
                     for (int r = 0; r < W / 2; r++) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) cp[r] = __ffma2_rn(make_float2(gj[j], gj[j]), w2(sb + j - 2 * r - 1), cp[r]);
+                        for (int j = 0; j < 4; j++) {
+                            if (PACKED) cp[r] = __ffma2_rn(make_float2(gj[j], gj[j]), w2(sb + j - 2 * r - 1), cp[r]);
+                            else {
+                                cp[r].y = fmaf(gj[j], w1(sb + j - 2 * r), cp[r].y);
+                                cp[r].x = fmaf(gj[j], w1(sb + j - 2 * r - 1), cp[r].x);
+                            }
+                        }
                     }
                     xn_p = xn4;
                     xo_p = xo4;
@@ -275,7 +292,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
         __syncwarp();
         for (int i = g; i < 32; i += G) {                                         // current block becomes the previous one
             st4(xb + 4 * i, ld4(xb + 128 + 4 * i));
-            st4(xs + 4 * i, ld4(xs + 128 + 4 * i));
+            if (PACKED) st4(xs + 4 * i, ld4(xs + 128 + 4 * i));
         }
         // Safety net, outside the reference's arithmetic: when the running energy has lost its digits the recurrence can
         // run away to inf / NaN (it does in the reference too, and its coefficients then stay NaN for ever because
@@ -293,7 +310,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
                 energy = 0.0f;
                 for (int i = g; i < 32; i += G) {                                                    // like Init_LMS_NR: history cleared too
                     st4(xb + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
-                    st4(xs + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+                    if (PACKED) st4(xs + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
                 }
             }
         }
@@ -330,9 +347,16 @@ void launch_nlms(const NlmsArgs &a, cudaStream_t st)
     // a handle and its channel-range shards then run the same form and agree bit for bit (tests/test_gpu_parity.py).
     int G = a.n_list >= 12288 ? 4 : 8;
     if (const char *env = getenv("RDSP_NLMS_LANES")) G = atoi(env) == 4 ? 4 : 8;       // experiments only
+    // The packed f32x2 form issues half the tap FMAs (FFMA2) for the same FMA-pipe time and a second window copy.  It
+    // wins where other kernels compete for the issue slots (cfg5: 0.585 -> 0.537 ms per step although the kernel alone
+    // takes the same 145 us) and loses where the NLMS has the GPU to itself (cfg3, 8192 notch channels: 270 -> 315 us),
+    // so the caller says which situation this is.  Both forms perform the same roundings per lane: bit-identical output.
+    bool packed = a.packed != 0;
+    if (const char *env = getenv("RDSP_NLMS_PACKED")) packed = env[0] == '1';          // experiments only
     const int cpb = NWARPS * (32 / G);
     const int grid = (a.n_list + cpb - 1) / cpb;
-    RDSP_CARVEOUT_ONCE(k_nlms<4>); RDSP_CARVEOUT_ONCE(k_nlms<8>);
-    if (G == 4) k_nlms<4><<<grid, NWARPS * 32, 0, st>>>(a);
-    else k_nlms<8><<<grid, NWARPS * 32, 0, st>>>(a);
+    RDSP_CARVEOUT_ONCE((k_nlms<4, false>)); RDSP_CARVEOUT_ONCE((k_nlms<8, false>)); RDSP_CARVEOUT_ONCE((k_nlms<8, true>));
+    if (G == 4) k_nlms<4, false><<<grid, NWARPS * 32, 0, st>>>(a);
+    else if (packed) k_nlms<8, true><<<grid, NWARPS * 32, 0, st>>>(a);
+    else k_nlms<8, false><<<grid, NWARPS * 32, 0, st>>>(a);
 }

@@ -65,6 +65,7 @@ struct NlmsArgs {
     uint8_t *first;             // [C] 1 until the instance ran once (RDSP_noise_reduction.h:69 statics)
     const RdspChanParams *par;
     int mode;                   // 0 = notch (output error), 1 = DNR (output estimate)
+    int packed;                 // 1: other kernels run beside this one (spectrum branches): use the FFMA2 form
 };
 void launch_nlms(const NlmsArgs &a, cudaStream_t st);
 

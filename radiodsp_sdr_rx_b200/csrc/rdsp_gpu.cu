@@ -770,6 +770,8 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
     //   0 = every channel (no split), 1 = the channels that bypass the notch, 2 = the channels whose notch runs.
     // With classes 1 and 2 on two streams the latency-bound notch -> AGC -> ... chain of the (few) notched channels runs
     // beside the wide kernels of the others instead of in front of them.
+    // the spectrum branches keep the issue slots contended while the NLMS kernels run (k_nlms.cu, launch_nlms)
+    const int nlms_packed = (has(h, RDSP_STAGE_SPEC256) || has(h, RDSP_STAGE_SPEC1024)) ? 1 : 0;
     auto run_chain = [&](cudaStream_t cs, int cls, int c0, int c1) -> int {
         const int nc = c1 - c0;
         int f_notch = 0, n_notch = 0, f_plain = 0, n_plain = 0;
@@ -797,7 +799,7 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
                     n.list = h->d_list_notch + f_notch; n.n_list = n_notch; n.C = C; n.T = T;
                     n.in_q15 = h->d_mid_a; n.out_f32 = h->d_scr;
                     n.coeff = h->d_nc_coeff; n.prev = h->d_nc_prev; n.energy = h->d_nc_energy; n.first = h->d_nc_first;
-                    n.par = h->d_par; n.mode = 0;
+                    n.par = h->d_par; n.mode = 0; n.packed = nlms_packed;
                     { Prof pr(h, KK_NOTCH, cs); launch_nlms(n, cs); }
                     // ... the others read the notch's f32 error signal
                     ag.list = h->d_list_notch + f_notch; ag.n_list = n_notch; ag.in_q15 = nullptr; ag.in_f32 = h->d_scr;
@@ -822,7 +824,7 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
                     n.list = dl + f_dnr; n.n_list = n_dnr; n.C = C; n.T = T;
                     n.in_f32 = h->d_scr; n.out_stereo = audio; n.dbg = dbg;
                     n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
-                    n.par = h->d_par; n.mode = 1;
+                    n.par = h->d_par; n.mode = 1; n.packed = nlms_packed;
                     { Prof pr(h, KK_DNR, cs); launch_nlms(n, cs); }
                 }
             }
