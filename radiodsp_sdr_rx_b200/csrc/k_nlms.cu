@@ -189,45 +189,96 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
                     const float xr[8] = {xn_p.x, xn_p.y, xn_p.z, xn_p.w, xn4.x, xn4.y, xn4.z, xn4.w};   // x[n-4 .. n+3]
                     const float xq[8] = {xo_p.x, xo_p.y, xo_p.z, xo_p.w, xo4.x, xo4.y, xo4.z, xo4.w};   // x[n-100 .. n-93]
 
-                    // ---- p[j] = c' x[n+j] with the coefficients at the start of the group
-                    // (.y: even taps, .x: odd taps — two accumulators per sample, as the scalar form had them)
-                    float2 pa[4];
+                    // ---- p[j] = c' x[n+j] with the coefficients at the start of the group: even taps and odd taps in
+                    // accumulators of their own, added at the end (both forms sum in this order)
+                    float p[4];
+                    if (PACKED) {
+                        // pairs over the samples (j, j+1): tap i is a broadcast scalar, (x[n+j-i], x[n+j+1-i]) an aligned pair
+                        float2 pe01 = make_float2(0.f, 0.f), po01 = pe01, pe23 = pe01, po23 = pe01;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) pa[j] = make_float2(0.f, 0.f);
+                        for (int i = 0; i < W; i++) {
+                            const float ci = (i & 1) ? cp[i / 2].x : cp[i / 2].y;
+                            const float2 cc = make_float2(ci, ci);
+                            if (i & 1) { po01 = __ffma2_rn(cc, w2(sb - i), po01); po23 = __ffma2_rn(cc, w2(sb + 2 - i), po23); }
+                            else { pe01 = __ffma2_rn(cc, w2(sb - i), pe01); pe23 = __ffma2_rn(cc, w2(sb + 2 - i), pe23); }
+                        }
+                        float2 p01 = __fadd2_rn(pe01, po01), p23 = __fadd2_rn(pe23, po23);
 #pragma unroll
-                    for (int r = 0; r < W / 2; r++) {
+                        for (int o = G / 2; o > 0; o >>= 1) {
+                            p01 = __fadd2_rn(p01, make_float2(__shfl_xor_sync(0xffffffffu, p01.x, o), __shfl_xor_sync(0xffffffffu, p01.y, o)));
+                            p23 = __fadd2_rn(p23, make_float2(__shfl_xor_sync(0xffffffffu, p23.x, o), __shfl_xor_sync(0xffffffffu, p23.y, o)));
+                        }
+                        p[0] = p01.x; p[1] = p01.y; p[2] = p23.x; p[3] = p23.y;
+                    } else {
+                        float2 pa[4];                                       // .y: even taps, .x: odd taps
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            if (PACKED) pa[j] = __ffma2_rn(cp[r], w2(sb + j - 2 * r - 1), pa[j]);
-                            else {
+                        for (int j = 0; j < 4; j++) pa[j] = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int r = 0; r < W / 2; r++) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
                                 pa[j].y = fmaf(cp[r].y, w1(sb + j - 2 * r), pa[j].y);
                                 pa[j].x = fmaf(cp[r].x, w1(sb + j - 2 * r - 1), pa[j].x);
                             }
                         }
-                    }
-                    float p[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) p[j] = pa[j].y + pa[j].x;
+                        for (int j = 0; j < 4; j++) p[j] = pa[j].y + pa[j].x;
 #pragma unroll
-                    for (int o = G / 2; o > 0; o >>= 1) {
+                        for (int o = G / 2; o > 0; o >>= 1) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) p[j] += __shfl_xor_sync(0xffffffffu, p[j], o);
+                            for (int j = 0; j < 4; j++) p[j] += __shfl_xor_sync(0xffffffffu, p[j], o);
+                        }
                     }
 
                     // ---- scalars that do not depend on the error: energy, normaliser, lag sums
                     float qn[4], r1[4], r2[4], r3[4];
+                    // squares, the + eps and the * mu two samples per instruction in the packed form (same roundings)
+                    float xo2[4], xn2[4], en[4];
+                    if (PACKED) {
+                        const float2 a0 = __fmul2_rn(make_float2(xo4.x, xo4.y), make_float2(xo4.x, xo4.y));
+                        const float2 a1 = __fmul2_rn(make_float2(xo4.z, xo4.w), make_float2(xo4.z, xo4.w));
+                        const float2 b0 = __fmul2_rn(make_float2(xn4.x, xn4.y), make_float2(xn4.x, xn4.y));
+                        const float2 b1 = __fmul2_rn(make_float2(xn4.z, xn4.w), make_float2(xn4.z, xn4.w));
+                        xo2[0] = a0.x; xo2[1] = a0.y; xo2[2] = a1.x; xo2[3] = a1.y;
+                        xn2[0] = b0.x; xn2[1] = b0.y; xn2[2] = b1.x; xn2[3] = b1.y;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) { xo2[j] = __fmul_rn(xo[j], xo[j]); xn2[j] = __fmul_rn(xn[j], xn[j]); }
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        energy = __fsub_rn(energy, __fmul_rn(xo[j], xo[j]));
-                        energy = __fadd_rn(energy, __fmul_rn(xn[j], xn[j]));
-                        // energy is a running difference: never divide by <= 0.  MUFU.RCP (relative error 2^-23; the
-                        // reference divides, which this path never reproduced bit for bit anyway)
-                        {
-                            const float den = fmaxf(energy + LMS_EPS, LMS_EPS);
-                            float r;
-                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
-                            qn[j] = mu * r;
+                        energy = __fsub_rn(energy, xo2[j]);
+                        energy = __fadd_rn(energy, xn2[j]);
+                        en[j] = energy;
+                    }
+                    // energy is a running difference: never divide by <= 0.  MUFU.RCP (relative error 2^-23; the
+                    // reference divides, which this path never reproduced bit for bit anyway)
+                    {
+                        float den[4], rc[4];
+                        if (PACKED) {
+                            const float2 eps2 = make_float2(LMS_EPS, LMS_EPS);
+                            const float2 d0 = __fadd2_rn(make_float2(en[0], en[1]), eps2), d1 = __fadd2_rn(make_float2(en[2], en[3]), eps2);
+                            den[0] = d0.x; den[1] = d0.y; den[2] = d1.x; den[3] = d1.y;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) den[j] = en[j] + LMS_EPS;
                         }
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float dj = fmaxf(den[j], LMS_EPS);
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc[j]) : "f"(dj));
+                        }
+                        if (PACKED) {
+                            const float2 m2 = make_float2(mu, mu);
+                            const float2 q0 = __fmul2_rn(m2, make_float2(rc[0], rc[1])), q1 = __fmul2_rn(m2, make_float2(rc[2], rc[3]));
+                            qn[0] = q0.x; qn[1] = q0.y; qn[2] = q1.x; qn[3] = q1.y;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) qn[j] = mu * rc[j];
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
                         // s_l(b) = s_l(b-1) + x[b-l] x[b] - x[b-l-96] x[b-96],  b = n + j
                         s1 = fmaf(xr[4 + j - 1], xn[j], s1); s1 = fmaf(-xq[4 + j - 1], xo[j], s1);
                         s2 = fmaf(xr[4 + j - 2], xn[j], s2); s2 = fmaf(-xq[4 + j - 2], xo[j], s2);
