@@ -428,6 +428,25 @@ def test_ten_seconds_no_drift(rd, po, stage):
     assert (errs[:, -3:].mean(axis=1) <= 0.5 * REL_RMS_TOL).all(), errs
 
 
+def test_nlms_packed_form_is_bit_identical(rd, po, monkeypatch):
+    """k_nlms runs its tap loops on the packed f32x2 FMA (FFMA2) when spectrum branches share the GPU and as scalar FMAs
+    otherwise; every lane of a pair performs the scalar FMA sequence, so both forms give the same bits (notch error
+    signal and DNR estimate, through AGC / FFT filter down to the q15 audio)"""
+    nc, nb = 40, 12
+    params, demod = _all_mode_params(po, nc)
+    iq = synth.synth_iq(np.arange(nc), nb, demod, interferer=True)
+    outs = []
+    for packed in ("0", "1"):
+        monkeypatch.setenv("RDSP_NLMS_PACKED", packed)
+        bank = make_bank(rd, nc, rd.STAGE_ALL, max_blocks=4)
+        for c, p in enumerate(params):
+            bank.set_mode(c, 1, to_rd_params(rd, p))
+        o = [bank.process_host(iq[b:b + 4]) for b in range(0, nb, 4)]
+        outs.append((np.concatenate(o), bank.read_debug_f32(4), bank.read_audio_spectrum()[0]))
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+
+
 def test_blocks_per_call_invariance(rd, po):
     """process_blocks(T) == T x process_block, bit for bit (state makes a clean round trip through HBM)"""
     nc, nb = 21, 24

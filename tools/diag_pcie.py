@@ -21,3 +21,8 @@ run(True, True, 2)
 print("H2D alone  %.1f GB/s" % run(True, False)[0])
 print("D2H alone  %.1f GB/s" % run(False, True)[1])
 print("both       H2D %.1f GB/s, D2H %.1f GB/s" % run(True, True))
+# the sizes one call of the bank moves (8192 / 4096 channels x 8 blocks), back to back on each stream
+for mb in (32, 16, 4):
+    n = mb << 20
+    h_in, h_out, d_in, d_out = h_in[:n], h_out[:n], d_in[:n], d_out[:n]
+    print("both, %2d MiB copies: H2D %.1f GB/s, D2H %.1f GB/s" % ((mb,) + run(True, True, 40)))
