@@ -95,34 +95,56 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
     __syncwarp();
     // shifted copy of [from, from + 128): xs[from + i] = xb[from + i + 1], and xs[from - 1] = xb[from]
     auto shift_copy = [&](int from) {
-        if (!PACKED) return;
-        for (int i = g; i < 32; i += G) {
-            const float4 v = ld4(xb + from + 4 * i);
-            const float nx = (from + 4 * i + 4 < 256) ? xb[from + 4 * i + 4] : 0.0f;
-            st4(xs + from + 4 * i, make_float4(v.y, v.z, v.w, nx));
-            if (i == 0 && from > 0) xs[from - 1] = v.x;
+        if constexpr (PACKED) {
+            for (int i = g; i < 32; i += G) {
+                const float4 v = ld4(xb + from + 4 * i);
+                const float nxt = (from + 4 * i + 4 < 256) ? xb[from + 4 * i + 4] : 0.0f;
+                st4(xs + from + 4 * i, make_float4(v.y, v.z, v.w, nxt));
+                if (i == 0 && from > 0) xs[from - 1] = v.x;
+            }
         }
     };
     shift_copy(0);                               // xs[127] is completed when the first block is staged
     __syncwarp();
+
+    // the input row of the next block travels while the current one is processed (16-byte pieces g, g + G, ... of the row)
+    constexpr int NPF = 32 / G;
+    int4 nx[NPF];
+    auto fetch = [&](int t) {
+        if (!active || t >= a.T) return;
+        const size_t rb = ((size_t)t * a.C + ch) * RDSP_BLK;
+        if (a.in_f32) {
+            const int4 *src = reinterpret_cast<const int4 *>(a.in_f32 + rb);
+#pragma unroll
+            for (int k = 0; k < NPF; k++) nx[k] = src[g + G * k];
+        } else {
+            const int4 *src = reinterpret_cast<const int4 *>(a.in_q15 + rb);
+#pragma unroll
+            for (int k = 0; k < NPF / 2; k++) nx[k] = src[g + G * k];
+        }
+    };
+    fetch(0);
 
     for (int t = 0; t < a.T; t++) {
         const size_t cb = (size_t)t * a.C + ch;
         // ---- stage the current block into xb[128..255]
         if (active) {
             if (a.in_f32) {
-                const float4 *src = reinterpret_cast<const float4 *>(a.in_f32 + cb * RDSP_BLK);
-                for (int i = g; i < 32; i += G) st4(xb + 128 + 4 * i, src[i]);
+#pragma unroll
+                for (int k = 0; k < NPF; k++)
+                    st4(xb + 128 + 4 * (g + G * k), make_float4(__int_as_float(nx[k].x), __int_as_float(nx[k].y), __int_as_float(nx[k].z), __int_as_float(nx[k].w)));
             } else {
-                const int4 *src = reinterpret_cast<const int4 *>(a.in_q15 + cb * RDSP_BLK);
-                for (int i = g; i < 16; i += G) {
-                    const int4 v = src[i];
+#pragma unroll
+                for (int k = 0; k < NPF / 2; k++) {
+                    const int4 v = nx[k];
+                    const int i = g + G * k;
                     st4(xb + 128 + 8 * i, make_float4((float)lo16(v.x) / 32768.0f, (float)hi16(v.x) / 32768.0f,
                                                       (float)lo16(v.y) / 32768.0f, (float)hi16(v.y) / 32768.0f));
                     st4(xb + 128 + 8 * i + 4, make_float4((float)lo16(v.z) / 32768.0f, (float)hi16(v.z) / 32768.0f,
                                                           (float)lo16(v.w) / 32768.0f, (float)hi16(v.w) / 32768.0f));
                 }
             }
+            fetch(t + 1);                        // in flight while this block is processed
         } else {
             for (int i = g; i < 32; i += G) st4(xb + 128 + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
         }
