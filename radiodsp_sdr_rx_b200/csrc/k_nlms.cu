@@ -38,7 +38,9 @@
 
 namespace {
 
-constexpr int NWARPS = 2;
+// warps per CTA: 2 for the scalar forms, 4 for the packed one (measured inside the cfg5 step: 1 warp 0.542 ms, 2 warps
+// 0.519, 4 warps 0.504 — the kernel alone takes the same time with each; the scalar form of cfg3 LOSES 9 % with 4)
+constexpr int NWARPS_SCALAR = 2, NWARPS_PACKED = 4;
 constexpr int XS = 260;                      // floats per row: 16-byte aligned, rows 4 banks apart
 constexpr int D = 4;                         // samples per group
 #ifndef RDSP_NLMS_ANCHOR
@@ -51,12 +53,13 @@ __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
 template <int G, bool PACKED>
-__global__ void __launch_bounds__(NWARPS * 32) k_nlms(NlmsArgs a)
+__global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32) k_nlms(NlmsArgs a)
 {
     constexpr int W = RDSP_LMS_NTAPS / G;        // taps per lane (24 or 12)
     constexpr int S = W + D;                     // circular window (slots = lane-relative sample index mod S)
     constexpr int CPW = 32 / G;                  // channels per warp
     static_assert(W % 4 == 0, "taps per lane must be a multiple of 4");
+    constexpr int NWARPS = PACKED ? NWARPS_PACKED : NWARPS_SCALAR;
     __shared__ __align__(16) float s_x[NWARPS * CPW][XS];     // [0,128) previous block / outputs, [128,256) current
     __shared__ __align__(16) float s_x1[PACKED ? NWARPS * CPW : 1][XS];   // the same samples one to the left: s_x1[i] = x[i + 1]
 
@@ -426,11 +429,12 @@ void launch_nlms(const NlmsArgs &a, cudaStream_t st)
     // so the caller says which situation this is.  Both forms perform the same roundings per lane: bit-identical output.
     bool packed = a.packed != 0;
     if (const char *env = getenv("RDSP_NLMS_PACKED")) packed = env[0] == '1';          // experiments only
-    const int cpb = NWARPS * (32 / G);
+    const int nw = (G == 8 && packed) ? NWARPS_PACKED : NWARPS_SCALAR;
+    const int cpb = nw * (32 / G);
     const int grid = (a.n_list + cpb - 1) / cpb;
     RDSP_CARVEOUT_ONCE((k_nlms<4, false>)); RDSP_CARVEOUT_ONCE((k_nlms<8, false>)); RDSP_CARVEOUT_ONCE((k_nlms<8, true>));
     // (G = 4 packed measured slower than G = 4 scalar everywhere: cfg5 0.565 vs 0.530 ms for G = 8 packed, cfg4a 0.381 vs 0.333)
-    if (G == 4) k_nlms<4, false><<<grid, NWARPS * 32, 0, st>>>(a);
-    else if (packed) k_nlms<8, true><<<grid, NWARPS * 32, 0, st>>>(a);
-    else k_nlms<8, false><<<grid, NWARPS * 32, 0, st>>>(a);
+    if (G == 4) k_nlms<4, false><<<grid, nw * 32, 0, st>>>(a);
+    else if (packed) k_nlms<8, true><<<grid, nw * 32, 0, st>>>(a);
+    else k_nlms<8, false><<<grid, nw * 32, 0, st>>>(a);
 }
