@@ -121,12 +121,12 @@ def ncu_traffic(kernel: str, workload: str, C_: int, T: int):
     def rows_of(prefix):
         return [r for name, rows in k.items() if name.split("<")[0] == prefix for r in rows]
     if kernel in ("k_nlms_notch", "k_nlms_dnr"):
-        rows = sorted(rows_of("k_nlms"), key=lambda r: r["grid"])
+        # rows are in launch order: the notch (first kernel of the notched channels' chain), then the DNR of that class
+        # and the DNR of the channels that bypass the notch
+        rows = rows_of("k_nlms")
         if len(rows) < 2:
             return None
-        # cfg5: 2048 notched channels (grid 256) / their 1639 DNR channels (205) / the 4915 other DNR channels (615)
-        notch = [r for r in rows if r["grid"] == 256]
-        rows = notch if kernel == "k_nlms_notch" else [r for r in rows if r["grid"] != 256]
+        rows = rows[:1] if kernel == "k_nlms_notch" else rows[1:]
     elif kernel == "k_front":
         rows = rows_of("k_front_tc") or rows_of("k_front")
     elif kernel == "k_agc":
