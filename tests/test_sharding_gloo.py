@@ -73,3 +73,16 @@ def test_workload_tables_are_consistent():
     # config 5: mode by c mod 4, DNR level by c mod 5
     assert [bench.channel_params("cfg5", c)["demod"] for c in range(4)] == [0, 1, 2, 4]
     assert [bench.channel_params("cfg5", c)["nr_level"] for c in range(5)] == [0, 20, 30, 40, 50]
+
+
+def test_roofline_traffic_lookup_reads_the_committed_capture():
+    """bench.py's `roofline.traffic` comes from the newest profiles/r*_traffic.json (one `ncu --set full` capture of the
+    un-profiled step, where a stage may run as two launches): every kernel of the cfg5 step resolves to a byte count,
+    and nothing is claimed for configurations the capture was not taken on"""
+    import bench
+    for k in ("k_front", "k_nlms_notch", "k_nlms_dnr", "k_agc", "k_fftfilt", "k_biquad", "k_spec256", "k_spec1024"):
+        t = bench.ncu_traffic(k, "cfg5", 8192, 8)
+        assert t is not None and 1e6 < t < 1e9, (k, t)
+    # the notch covers a quarter of the channels of cfg5 and reads q15: far less traffic than the DNR launches
+    assert bench.ncu_traffic("k_nlms_notch", "cfg5", 8192, 8) < bench.ncu_traffic("k_nlms_dnr", "cfg5", 8192, 8)
+    assert bench.ncu_traffic("k_front", "cfg3", 8192, 8) is None and bench.ncu_traffic("k_front", "cfg5", 4096, 8) is None
