@@ -39,7 +39,8 @@
 namespace {
 
 // warps per CTA: 2 for the scalar forms, 4 for the packed one (measured inside the cfg5 step: 1 warp 0.542 ms, 2 warps
-// 0.519, 4 warps 0.504 — the kernel alone takes the same time with each; the scalar form of cfg3 LOSES 9 % with 4)
+// 0.519, 3 warps 0.549, 4 warps 0.504, 5 warps 0.551 — the kernel alone takes the same time with each; the scalar form
+// of cfg3 LOSES 9 % with 4)
 constexpr int NWARPS_SCALAR = 2, NWARPS_PACKED = 4;
 constexpr int XS = 260;                      // floats per row: 16-byte aligned, rows 4 banks apart
 constexpr int D = 4;                         // samples per group
