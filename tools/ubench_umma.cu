@@ -13,7 +13,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return ((uint64_t)hi << 32) | lo;
 }
 
-template <int N, bool TS, int KIND /*0 i8, 1 f8f6f4*/, int ND /* distinct accumulators in rotation */>
+template <int N, bool TS, int KIND /*0 i8, 1 f8f6f4*/, int ND /* distinct accumulators in rotation */, int MM = 128>
 __global__ void __launch_bounds__(128, 1) k(long long *out, int iters)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(128, 1) k(long long *out, int iters)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tptr;
-    const uint32_t idesc = (KIND == 0 ? (2u << 4) : (1u << 4)) | ((uint32_t)(N >> 3) << 17) | (8u << 24);   // S32 / F32 accum, M = 128
+    const uint32_t idesc = (KIND == 0 ? (2u << 4) : (1u << 4)) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(MM >> 4) << 24);   // S32 / F32 accum, M = MM
     if (threadIdx.x == 0) {
         const uint64_t adesc = make_desc(smem_u32(smem), 2048);
         const uint64_t bdesc = make_desc(smem_u32(smem) + 16384, N * 16);
@@ -121,16 +121,16 @@ void run_multi(long long *d_out)
     printf("i8 N=%3d, %d issuing warps: %7.1f clk per MMA of the SM (%d MMAs)  (%s)\n", N, NW, (double)clk / (iters * NW), iters * NW, cudaGetErrorString(e));
 }
 
-template <int N, bool TS, int KIND, int ND = 1>
+template <int N, bool TS, int KIND, int ND = 1, int MM = 128>
 void run(const char *name, long long *d_out)
 {
     const int iters = 4096;
-    cudaFuncSetAttribute(k<N, TS, KIND, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    for (int rep = 0; rep < 2; rep++) k<N, TS, KIND, ND><<<148, 128, 48 * 1024>>>(d_out, iters);
+    cudaFuncSetAttribute(k<N, TS, KIND, ND, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    for (int rep = 0; rep < 2; rep++) k<N, TS, KIND, ND, MM><<<148, 128, 48 * 1024>>>(d_out, iters);
     cudaError_t e = cudaDeviceSynchronize();
     long long clk = 0;
     cudaMemcpy(&clk, d_out, 8, cudaMemcpyDeviceToHost);
-    printf("%-8s N=%3d %s, %d accumulator(s) in rotation: %7.1f clk / MMA  (%s)\n", name, N, TS ? "A in TMEM" : "A in smem", ND, (double)clk / iters, cudaGetErrorString(e));
+    printf("%-8s M=%3d N=%3d %s, %d accumulator(s) in rotation: %7.1f clk / MMA  (%s)\n", name, MM, N, TS ? "A in TMEM" : "A in smem", ND, (double)clk / iters, cudaGetErrorString(e));
 }
 
 int main()
@@ -143,6 +143,7 @@ int main()
     run<32, false, 0, 2>("i8", d_out); run<32, false, 0, 4>("i8", d_out); run<32, false, 0, 8>("i8", d_out);
     run<32, true, 0, 4>("i8", d_out); run<32, true, 0, 8>("i8", d_out); run<16, true, 0, 8>("i8", d_out); run<64, true, 0, 4>("i8", d_out);
     run<32, false, 1>("f8f6f4", d_out); run<32, true, 1>("f8f6f4", d_out); run<256, false, 1>("f8f6f4", d_out);
+    run<32, false, 0, 1, 64>("i8", d_out); run<64, false, 0, 1, 64>("i8", d_out); run<32, false, 0, 4, 64>("i8", d_out);   // M = 64: is a half-height MMA cheaper?
     run_multi<32, 1>(d_out); run_multi<32, 2>(d_out); run_multi<32, 4>(d_out); run_multi<64, 4>(d_out);
     return 0;
 }
