@@ -129,8 +129,10 @@ typedef struct {
     float    agc_max_gain;       /* linear */
     float    agc_attack_ms;
     float    agc_decay_ms[4];    /* per RDSP_AGC_* mode; [RDSP_AGC_OFF] unused */
-    uint32_t pipeline_chunks;    /* process_blocks(T) advances through the stages as a wavefront of this many chunks
-                                    of blocks (0 = auto: min(T, 4); 1 = no overlap between stages; max 8) */
+    uint32_t pipeline_chunks;    /* channel groups: behind the front end the channels of a call walk the graph as this
+                                    many independent groups on streams of their own (0 = default = 1 group; max 8;
+                                    reduced silently while a group would hold < 256 channels).  Every launch still
+                                    covers all n_blocks of the call.  Measured: 1 is fastest */
 } rdsp_gpu_config_t;
 
 typedef struct {

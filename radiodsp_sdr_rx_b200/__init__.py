@@ -13,6 +13,5 @@ from .native import (  # noqa: F401
     STAGE_FRONTEND, STAGE_NOTCH, STAGE_AGC, STAGE_FFTFILT, STAGE_NR, STAGE_SPEC256, STAGE_SPEC1024, STAGE_ALL,
     IO_DEVICE, IO_HOST, TAPS_HILBERT_I, TAPS_HILBERT_Q, TAPS_BANDPASS,
 )
-from .sdr import SDRChannel  # noqa: F401
 
-__all__ = ["ReceiverBank", "SDRChannel", "Config", "Params", "default_config", "default_params", "RdspError"]
+__all__ = ["ReceiverBank", "Config", "Params", "default_config", "default_params", "RdspError"]

@@ -154,6 +154,12 @@ void make_twiddle_256_f32(float *cs)
     }
 }
 
+// sinTable_f32 of CMSIS-DSP's arm_sin_f32 / arm_cos_f32: 513 entries, sin(2 pi k / 512) rounded to f32
+void make_sin512_f32(float *t513)
+{
+    for (int k = 0; k <= 512; k++) t513[k] = (float)sin(kTwoPi * (double)k / 512.0);
+}
+
 void make_hann_q15(int16_t *w, int n)
 {
     for (int i = 0; i < n; i++) {

@@ -7,7 +7,10 @@
 //   f32 -> q15 with truncation + saturation (:346-347).
 // With nr_kind == SPECTRAL the product is replaced by the spectral subtraction of the backup sketch
 // (backup/RDSP_convolutional_spec.h:181-238, loop bounds restated as FFT_length): magnitudes, noise floor
-// from the mean of bins 30..180, one-pole tracker, subtract / floor, keep the phase.
+// from the mean of bins 30..180, one-pole tracker, subtract / floor, then the bin is rebuilt from the new magnitude
+// and the ORIGINAL phase exactly the way the sketch does it (:221-238): phi = atan2(im, re), re' = m * arm_cos_f32(phi),
+// im' = m * arm_sin_f32(phi) — the CMSIS fast-math pair, a 512-entry sine table with linear interpolation whose
+// 1.9e-5 absolute error is part of the reference's output, so the same table and the same interpolation run here.
 //
 // Mapping: one warp per channel, 8 points per lane, the whole forward FFT -> product -> inverse FFT chain
 // stays in registers (fft_f32_lanes.cuh) with warp-private shared memory exchanges.  The previous input
@@ -21,12 +24,31 @@ namespace {
 
 constexpr int WARPS = 8;
 
+// arm_sin_f32 / arm_cos_f32 (CMSIS-DSP fast math): quarter = 0 for the sine, 0.25 for the cosine.
+// Every operation is a separately rounded f32 operation, in the order of the C source (no FMA contraction).
+__device__ __forceinline__ float arm_trig_f32(float x, bool cosine, const float *tab)
+{
+    float in = __fmul_rn(x, 0.159154943092f);
+    if (cosine) in = __fadd_rn(in, 0.25f);
+    int n = (int)in;
+    if (in < 0.0f) n--;
+    in = __fsub_rn(in, (float)n);
+    const float findex = __fmul_rn(512.0f, in);
+    const unsigned whole = (unsigned)findex & 0xFFFFu;                  // (uint16_t)findex
+    const float fract = __fsub_rn(findex, (float)whole);
+    const float a = tab[whole & 0x1FFu], b = tab[(whole & 0x1FFu) + 1];
+    return __fadd_rn(__fmul_rn(__fsub_rn(1.0f, fract), a), __fmul_rn(fract, b));
+}
+
 __global__ void __launch_bounds__(WARPS * 32, 3) k_fftfilt(FftFiltArgs a)
 {
     __shared__ float2 s_tw[256];
     __shared__ __align__(16) float2 s_buf[WARPS][FFT256_BUF];
+    __shared__ float s_sin[513];
 
     for (int i = threadIdx.x; i < 256; i += WARPS * 32) s_tw[i] = a.tw256[i];
+    if (a.nr_stage)
+        for (int i = threadIdx.x; i < 513; i += WARPS * 32) s_sin[i] = a.sin512[i];
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,9 +121,10 @@ __global__ void __launch_bounds__(WARPS * 32, 3) k_fftfilt(FftFiltArgs a)
             nfloor = nfloor > 0.0f ? nfloor : 0.0f;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const float nm = mag[j] <= nfloor ? (float)((double)mag[j] * 0.2) : mag[j] - nfloor;
-                const float sc = mag[j] > 0.0f ? nm / mag[j] : 0.0f;     // keep the phase, new magnitude
-                v[j] = p_mul(v[j], make_float2(sc, -sc));
+                const float nm = mag[j] <= nfloor ? (float)((double)mag[j] * 0.2) : __fsub_rn(mag[j], nfloor);
+                const float phi = atan2f(v[j].y, v[j].x);
+                // conjugated on the way (the inverse transform below is conj -> forward -> conj -> 1/N)
+                v[j] = make_float2(__fmul_rn(nm, arm_trig_f32(phi, true, s_sin)), -__fmul_rn(nm, arm_trig_f32(phi, false, s_sin)));
             }
         }
 

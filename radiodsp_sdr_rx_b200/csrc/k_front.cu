@@ -182,16 +182,19 @@ __global__ void __launch_bounds__(MAXWARPS * 32, 2) k_front(FrontArgs a)
 // channel costs the same, so a ragged last wave is pure loss (8192 channels on 148 SMs = 55.35 per SM).
 void launch_front(const FrontArgs &a, cudaStream_t st)
 {
-    static int n_sm = 0;
-    static size_t smem_max = 0;
+    // per (kernel, device) set-up, see launch_front_tc
+    static std::atomic<int> n_sm_dev[RDSP_MAX_DEVICES], smem_dev[RDSP_MAX_DEVICES];
+    const int dev = rdsp_current_device();
+    int n_sm = n_sm_dev[dev].load(std::memory_order_acquire);
     if (!n_sm) {
-        int dev = 0, v = 0;
-        cudaGetDevice(&dev);
+        int v = 0;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        smem_max = (size_t)v;
         cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+        smem_dev[dev].store(v, std::memory_order_release);
+        n_sm_dev[dev].store(n_sm, std::memory_order_release);
     }
+    const size_t smem_max = (size_t)smem_dev[dev].load(std::memory_order_acquire);
     auto need = [](int w) { return (size_t)(15 * TROW + 2 * w * 3 * 256) * sizeof(int16_t); };
     int best_w = 4, best_r = 4;
     double best = -1.0;

@@ -834,13 +834,15 @@ void front_tc_plan_segments(int n_tiles, int T, int n_sm, int *bounds, int *n_se
 
 void launch_front_tc(const FrontArgs &a_in, const FrontTcTables &tb_in, cudaStream_t st)
 {
-    static int n_sm = 0;
+    // the opt-in to > 48 KB of dynamic shared memory is per (kernel, device): a process with one handle per GPU needs it on each
+    static std::atomic<int> n_sm_dev[RDSP_MAX_DEVICES];
+    const int dev = rdsp_current_device();
+    int n_sm = n_sm_dev[dev].load(std::memory_order_acquire);
     if (!n_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         cudaFuncSetAttribute(k_front_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B);
         cudaFuncSetAttribute(k_front_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_B);
+        n_sm_dev[dev].store(n_sm, std::memory_order_release);
     }
     FrontArgs a = a_in;
     FrontTcTables tb = tb_in;

@@ -414,8 +414,7 @@ void launch_nlms_direct(const NlmsArgs &a, cudaStream_t st);
 void launch_nlms(const NlmsArgs &a, cudaStream_t st)
 {
     if (a.n_list <= 0) return;
-    static const bool direct = [] { const char *e = getenv("RDSP_NLMS_IMPL"); return e && e[0] == 'd'; }();
-    if (direct) { launch_nlms_direct(a, st); return; }
+    if (a.direct) { launch_nlms_direct(a, st); return; }
     // 4 lanes per channel minimise instructions (the reductions are two shuffle stages, 30 % fewer instructions per
     // sample); 8 lanes halve the dependent chain of a group.  Measured alone (8 blocks per launch, us, G = 4 / G = 8):
     // 2048 channels 170 / 100, 6554 channels 167 / 165, 8192 channels 165 / 211, 16384 channels 324 / 336; inside the

@@ -14,7 +14,13 @@ inline void rdsp_uniform_carveout(K kernel)
     static const int pct = [] { const char *e = getenv("RDSP_CARVEOUT"); return e ? atoi(e) : 50; }();
     if (pct >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
-#define RDSP_CARVEOUT_ONCE(kernel) do { static bool done_ = false; if (!done_) { rdsp_uniform_carveout(kernel); done_ = true; } } while (0)
+// function attributes belong to a (kernel, device) pair: once per device, and safe when handles on different GPUs
+// launch from different host threads
+#include <atomic>
+constexpr int RDSP_MAX_DEVICES = 64;
+inline int rdsp_current_device() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < RDSP_MAX_DEVICES) ? d : 0; }
+#define RDSP_CARVEOUT_ONCE(kernel) do { static std::atomic<bool> done_[RDSP_MAX_DEVICES]; const int d_ = rdsp_current_device(); \
+        if (!done_[d_].load(std::memory_order_acquire)) { rdsp_uniform_carveout(kernel); done_[d_].store(true, std::memory_order_release); } } while (0)
 
 // K0+K1+K2 -----------------------------------------------------------------------------------
 struct FrontArgs {
@@ -66,6 +72,7 @@ struct NlmsArgs {
     const RdspChanParams *par;
     int mode;                   // 0 = notch (output error), 1 = DNR (output estimate)
     int packed;                 // 1: other kernels run beside this one (spectrum branches): use the FFMA2 form
+    int direct;                 // 1: the sample-by-sample cross-check kernel (k_nlms_direct.cu; RDSP_NLMS_IMPL=direct at create)
 };
 void launch_nlms(const NlmsArgs &a, cudaStream_t st);
 
@@ -98,6 +105,7 @@ struct FftFiltArgs {
     float *nfloor;              // [C] spectral-NR noise floor
     const float2 *masks;        // [n_masks][256]
     const float2 *tw256;        // [256] (cos, sin)(2*pi*k/256)
+    const float *sin512;        // [513] sinTable_f32 of arm_sin_f32 / arm_cos_f32 (K8 rebuilds bins through it)
     const RdspChanParams *par;
     int C, T;
     const int *list;            // channels of this launch (n entries), or nullptr: [ch0, ch0 + n)

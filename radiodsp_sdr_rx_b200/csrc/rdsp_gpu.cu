@@ -6,8 +6,9 @@
 //   audio path    : k_front (K0-K2) -> k_nlms<notch> (K3, listed channels) -> k_agc (K4)
 //                   -> k_fftfilt (K5/K8/K7) -> k_nlms<dnr> (K6, listed channels) -> k_spec1024 (K10)
 // Intermediates between kernels are int16 mono / f32 rows in handle-owned scratch (L2 resident at
-// the batch sizes of BASELINE.json); per-channel state makes one HBM round trip per chunk.
-// Each stage has its own stream and the blocks of a call advance through the stages as a wavefront of chunks.
+// the batch sizes of BASELINE.json).  Every launch covers all T blocks of the call, so per-channel state makes
+// one HBM round trip per call.  Behind the front end the call forks into up to three streams (the channels whose
+// notch runs, the channels that bypass it, the spectrum branch) joined by events on the handle's stream.
 #include "../../include/rdsp_gpu.h"
 #include "host_design.h"
 #include "kernels.h"
@@ -73,13 +74,17 @@ struct rdsp_gpu {
     int16_t taps[15][RDSP_FIR_TAPS];
     bool taps_dirty = true;
     int32_t *d_taps = nullptr;
-    std::map<std::pair<float, float>, int> mask_ids;
+    std::map<std::pair<float, float>, int> mask_ids;     // masks designed from (pbt_lo, pbt_hi)
+    std::map<std::vector<float>, int> custom_mask_ids;   // masks installed with rdsp_gpu_set_mask, by content
+    std::vector<int> custom_mask;              // [C] id of the installed mask, -1 = the designed one; survives set_mode
+                                               // until the channel's pbt cut-offs change (reInitializeFilter redesigns)
     std::vector<float> masks;                  // [n][512]
     int masks_uploaded = 0, mask_cap = 0;
     float2 *d_masks = nullptr;
     int2 *d_tw = nullptr;
     int16_t *d_win256 = nullptr, *d_win1024 = nullptr;
     float2 *d_tw256 = nullptr;
+    float *d_sin512 = nullptr;
     int32_t bq[5];
     float agc_alpha_a = 0.f, agc_alpha_d[4] = {0.f, 0.f, 0.f, 0.f};
 
@@ -88,6 +93,7 @@ struct rdsp_gpu {
     int16_t *d_fe_hist2 = nullptr;             // buffers so that a call's blocks can run as concurrent time segments
     int fe_hist_cur = 0;
     bool front_tc = true;                      // RDSP_FRONT_IMPL=cuda-core selects k_front.cu (cross-check)
+    bool nlms_direct = false;                  // RDSP_NLMS_IMPL=direct selects k_nlms_direct.cu (cross-check); read at create
     uint8_t *d_toep = nullptr;                 // Toeplitz byte planes of the 15 tap rows
     float *d_sam_state = nullptr;              // [C][4] SAM carrier loop
     int32_t *d_nb_ref = nullptr;               // [C] noise blanker running magnitude
@@ -101,6 +107,7 @@ struct rdsp_gpu {
     int16_t *d_ring = nullptr; uint16_t *d_spec1024_out = nullptr;
     uint16_t *d_view = nullptr; float *d_smeter = nullptr;
     uint16_t *d_waterfall = nullptr; int *d_wf_head = nullptr; std::vector<int> wf_head;   // [C][50][128] ring + newest slot
+    uint16_t *d_wf_rows = nullptr; uint8_t *d_wf_col = nullptr; size_t wf_scratch_ch = 0;  // read-out scratch, grown on demand
 
     // scratch
     int16_t *d_mid_a = nullptr, *d_mid_b = nullptr;
@@ -354,10 +361,10 @@ void free_all(rdsp_gpu *h)
 {
     void *ptrs[] = {h->d_fe_hist2, h->d_toep, h->d_tile_ch, h->d_tile_rows, h->d_sam_state, h->d_nb_ref,
                     h->d_par, h->d_list_notch, h->d_list_plain, h->d_list_dnr, h->d_list_dnr_p, h->d_list_dnr_n, h->d_taps, h->d_masks, h->d_tw, h->d_win256, h->d_win1024,
-                    h->d_tw256, h->d_fe_hist, h->d_nc_coeff, h->d_nc_prev, h->d_nc_energy, h->d_nc_first, h->d_dn_coeff,
+                    h->d_tw256, h->d_sin512, h->d_fe_hist, h->d_nc_coeff, h->d_nc_prev, h->d_nc_energy, h->d_nc_first, h->d_dn_coeff,
                     h->d_dn_prev, h->d_dn_energy, h->d_dn_first, h->d_agc_env, h->d_conv_last, h->d_nfloor, h->d_bq_state,
                     h->d_spec_prev, h->d_spec_sum, h->d_spec_out, h->d_ring, h->d_spec1024_out, h->d_view, h->d_smeter,
-                    h->d_waterfall, h->d_wf_head,
+                    h->d_waterfall, h->d_wf_head, h->d_wf_rows, h->d_wf_col,
                     h->d_mid_a, h->d_mid_b, h->d_scr, h->d_dbg, h->d_hp_iq};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < rdsp_gpu::kMaxStage; i++) {
@@ -503,6 +510,7 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     h->dpar.resize(C);
     h->dnr_old_level.assign(C, 15);                                 // oldNRLevel = 15 + Init_LMS_NR(15): RDSP_convolutional.h:80, .ino:172
     h->notch_old_level.assign(C, -1);
+    h->custom_mask.assign(C, -1);
     const int mid = mask_id_for(h, defp.pbt_lo_hz, defp.pbt_hi_hz);
     for (size_t ch = 0; ch < C; ch++) { derive_params(h, (int)ch); h->dpar[ch].mask_id = mid; }
     h->spec_ready.assign(C, 0);
@@ -518,6 +526,9 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
         CKC(dalloc(&h->d_nb_ref, C));
         if (const char *e = getenv("RDSP_FRONT_IMPL")) h->front_tc = !(e[0] == 'c' || e[0] == 'C');
         if (const char *e = getenv("RDSP_TIMELINE")) h->timeline = e[0] == '1';
+    }
+    if (const char *e = getenv("RDSP_NLMS_IMPL")) h->nlms_direct = e[0] == 'd';
+    if (sm & RDSP_STAGE_FRONTEND) {
         CKC(dalloc(&h->d_mid_a, T * C * RDSP_BLK));
     }
     if (sm & RDSP_STAGE_NOTCH) {
@@ -541,6 +552,10 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
         float cs[512];
         rdsp_host::make_twiddle_256_f32(cs);
         CKC(cudaMemcpy(h->d_tw256, cs, sizeof(cs), cudaMemcpyHostToDevice));
+        CKC(dalloc(&h->d_sin512, (size_t)513));
+        float st[513];
+        rdsp_host::make_sin512_f32(st);
+        CKC(cudaMemcpy(h->d_sin512, st, sizeof(st), cudaMemcpyHostToDevice));
     }
     if (sm & RDSP_STAGE_NR) {
         CKC(dalloc(&h->d_list_dnr, C));
@@ -625,12 +640,16 @@ int rdsp_gpu_set_mode(rdsp_gpu_t *h, uint32_t ch_first, uint32_t ch_count, const
     int rc = validate_params(p, why);
     if (rc != RDSP_OK) { h->err = why; return rc; }
     const int mid = mask_id_for(h, p->pbt_lo_hz, p->pbt_hi_hz);
+    bool changed = false;
     for (uint32_t ch = ch_first; ch < ch_first + ch_count; ch++) {
+        if (memcmp(&h->par[ch], p, sizeof(*p)) == 0) continue;           // the sketch re-sends its settings every tick
+        if (h->par[ch].pbt_lo_hz != p->pbt_lo_hz || h->par[ch].pbt_hi_hz != p->pbt_hi_hz) h->custom_mask[ch] = -1;
         h->par[ch] = *p;
         derive_params(h, (int)ch);
-        h->dpar[ch].mask_id = mid;
+        h->dpar[ch].mask_id = h->custom_mask[ch] >= 0 ? h->custom_mask[ch] : mid;
+        changed = true;
     }
-    h->par_dirty = true;
+    if (changed) h->par_dirty = true;
     return RDSP_OK;
 }
 
@@ -799,7 +818,7 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
                     n.list = h->d_list_notch + f_notch; n.n_list = n_notch; n.C = C; n.T = T;
                     n.in_q15 = h->d_mid_a; n.out_f32 = h->d_scr;
                     n.coeff = h->d_nc_coeff; n.prev = h->d_nc_prev; n.energy = h->d_nc_energy; n.first = h->d_nc_first;
-                    n.par = h->d_par; n.mode = 0; n.packed = nlms_packed;
+                    n.par = h->d_par; n.mode = 0; n.packed = nlms_packed; n.direct = h->nlms_direct;
                     { Prof pr(h, KK_NOTCH, cs); launch_nlms(n, cs); }
                     // ... the others read the notch's f32 error signal
                     ag.list = h->d_list_notch + f_notch; ag.n_list = n_notch; ag.in_q15 = nullptr; ag.in_f32 = h->d_scr;
@@ -811,7 +830,7 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
         if (ff) {
             FftFiltArgs f{};
             f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq; f.out_stereo = audio; f.out_f32_L = h->d_scr;
-            f.dbg = dbg; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256;
+            f.dbg = dbg; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256; f.sin512 = h->d_sin512;
             f.par = h->d_par; f.C = C; f.T = T; f.list = cls_list; f.ch0 = c0; f.n = cls_n; f.nr_stage = nr ? 1 : 0;
             { Prof pr(h, KK_FFTFILT, cs); launch_fftfilt(f, cs); }
             if (nr) {
@@ -824,7 +843,7 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
                     n.list = dl + f_dnr; n.n_list = n_dnr; n.C = C; n.T = T;
                     n.in_f32 = h->d_scr; n.out_stereo = audio; n.dbg = dbg;
                     n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
-                    n.par = h->d_par; n.mode = 1; n.packed = nlms_packed;
+                    n.par = h->d_par; n.mode = 1; n.packed = nlms_packed; n.direct = h->nlms_direct;
                     { Prof pr(h, KK_DNR, cs); launch_nlms(n, cs); }
                 }
             }
@@ -983,10 +1002,20 @@ int rdsp_gpu_read_waterfall(rdsp_gpu_t *h, uint32_t ch_first, uint32_t ch_count,
     if (ch_count == 0 || (uint64_t)ch_first + ch_count > (uint64_t)h->C) { h->err = "channel range out of bounds"; return RDSP_ERR_RANGE; }
     CK(cudaSetDevice(h->cfg.device));
     const size_t n = (size_t)ch_count * 50 * 128;
-    uint16_t *d_rows = nullptr;
-    uint8_t *d_col = nullptr;
-    CK(cudaMalloc((void **)&d_rows, n * sizeof(uint16_t)));
-    if (colour && cudaMalloc((void **)&d_col, n) != cudaSuccess) { cudaFree(d_rows); h->err = "out of device memory"; return RDSP_ERR_NOMEM; }
+    if (ch_count > h->wf_scratch_ch) {                  // read-out scratch lives in the handle: no allocation per call
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->d_wf_rows) cudaFree(h->d_wf_rows);
+        if (h->d_wf_col) cudaFree(h->d_wf_col);
+        h->d_wf_rows = nullptr; h->d_wf_col = nullptr; h->wf_scratch_ch = 0;
+        if (cudaMalloc((void **)&h->d_wf_rows, n * sizeof(uint16_t)) != cudaSuccess ||
+            cudaMalloc((void **)&h->d_wf_col, n) != cudaSuccess) {
+            if (h->d_wf_rows) { cudaFree(h->d_wf_rows); h->d_wf_rows = nullptr; }
+            h->err = "out of device memory"; return RDSP_ERR_NOMEM;
+        }
+        h->wf_scratch_ch = ch_count;
+    }
+    uint16_t *d_rows = h->d_wf_rows;
+    uint8_t *d_col = colour ? h->d_wf_col : nullptr;
     cudaError_t e = cudaMemcpyAsync(h->d_wf_head, &h->wf_head[ch_first], ch_count * sizeof(int), cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) {
         WaterfallArgs w{};
@@ -997,8 +1026,6 @@ int rdsp_gpu_read_waterfall(rdsp_gpu_t *h, uint32_t ch_first, uint32_t ch_count,
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e == cudaSuccess) e = cudaMemcpy(rows, d_rows, n * sizeof(uint16_t), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && colour) e = cudaMemcpy(colour, d_col, n, cudaMemcpyDeviceToHost);
-    cudaFree(d_rows);
-    if (d_col) cudaFree(d_col);
     if (e != cudaSuccess) { h->err = std::string("read_waterfall: ") + cudaGetErrorString(e); return RDSP_ERR_CUDA; }
     return RDSP_OK;
 }
@@ -1042,9 +1069,17 @@ int rdsp_gpu_set_mask(rdsp_gpu_t *h, uint32_t ch_first, uint32_t ch_count, const
 {
     if (!h || !mask512) return RDSP_ERR_INVALID;
     if (ch_count == 0 || (uint64_t)ch_first + ch_count > (uint64_t)h->C) { h->err = "channel range out of bounds"; return RDSP_ERR_RANGE; }
-    const int id = (int)(h->masks.size() / 512);
-    h->masks.insert(h->masks.end(), mask512, mask512 + 512);
-    for (uint32_t ch = ch_first; ch < ch_first + ch_count; ch++) h->dpar[ch].mask_id = id;
+    // rows are immutable and shared: the same table installed twice (or on many ranges) is stored once
+    std::vector<float> key(mask512, mask512 + 512);
+    auto it = h->custom_mask_ids.find(key);
+    int id;
+    if (it != h->custom_mask_ids.end()) id = it->second;
+    else {
+        id = (int)(h->masks.size() / 512);
+        h->masks.insert(h->masks.end(), mask512, mask512 + 512);
+        h->custom_mask_ids.emplace(std::move(key), id);
+    }
+    for (uint32_t ch = ch_first; ch < ch_first + ch_count; ch++) { h->custom_mask[ch] = id; h->dpar[ch].mask_id = id; }
     h->par_dirty = true;
     return RDSP_OK;
 }

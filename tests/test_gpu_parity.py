@@ -9,19 +9,12 @@ import os
 import numpy as np
 import pytest
 
+import bench
 from conftest import GOLDEN
+from parity_util import REL_RMS_TOL, SNR_TOL_DB, check_chain, rel_rms
 from radiodsp_sdr_rx_b200 import synth
 
 pytestmark = pytest.mark.gpu
-
-REL_RMS_TOL = 1e-4          # float32 stages, relative RMS of the pre-quantisation signal
-SNR_TOL_DB = 0.1
-
-
-def rel_rms(a, b):
-    a = a.astype(np.float64); b = b.astype(np.float64)
-    den = np.sqrt(np.mean(b * b))
-    return float(np.sqrt(np.mean((a - b) ** 2)) / den) if den > 0 else float(np.sqrt(np.mean((a - b) ** 2)))
 
 
 def make_bank(rd, n_channels, stage_mask, max_blocks=64, **kw):
@@ -273,10 +266,12 @@ def test_conv_and_nr_kinds_vs_oracle(rd, po):
         level = (0, 20, 1, 50, 3)[c % 5]
         params.append(po.default_params(nr_kind=kind, nr_level=level, pbt_lo_hz=float(50 * (c % 8)), pbt_hi_hz=float(4000 - 250 * c)))
     g_out, g_f32, o_out, o_f32, _, _ = run_both(rd, po, rd.STAGE_FFTFILT | rd.STAGE_NR, params, iq, blocks_per_call=6)
+    # K8 rebuilds every bin through atan2 + arm_cos_f32 / arm_sin_f32 like the sketch; the kernel interpolates the same
+    # 512-entry table (k_fftfilt.cu, arm_trig_f32), so the spectral-subtraction channels meet the same bar as the rest
     for c in range(nc):
-        tol = 3e-4 if params[c].nr_kind == po.NR_SPECTRAL else REL_RMS_TOL    # oracle uses arm_sin/cos_f32 table interpolation (1.9e-5 abs)
-        assert rel_rms(g_f32[:, c, :, 0], o_f32[:, c, :, 0]) <= tol, c
-        assert np.abs(g_out[:, c].astype(np.int32) - o_out[:, c]).max() <= (2 if params[c].nr_kind == po.NR_SPECTRAL else 1), c
+        assert rel_rms(g_f32[:, c, :, 0], o_f32[:, c, :, 0]) <= REL_RMS_TOL, c
+        assert rel_rms(g_f32[:, c, :, 1], o_f32[:, c, :, 1]) <= REL_RMS_TOL or params[c].nr_kind == po.NR_LMS, c
+        assert np.abs(g_out[:, c].astype(np.int32) - o_out[:, c]).max() <= 1, c
 
 
 def test_explicit_mask_is_data(rd, po):
@@ -366,44 +361,24 @@ def test_spec1024_bit_exact(rd, po, blocks_per_call):
 # ------------------------------------------------------------------------------------------ whole chain
 
 def _all_mode_params(po, nc):
-    """config 5 of BASELINE.json: mode by c mod 4, notch on CW channels, DNR level by c mod 5, AGC by c mod 4"""
-    params, demod = [], []
-    for c in range(nc):
-        d = (po.DEMOD_LSB, po.DEMOD_USB, po.DEMOD_CW_LSB, po.DEMOD_AM)[c % 4]
-        lvl = (0, 20, 30, 40, 50)[c % 5]
-        flt = {po.DEMOD_CW_LSB: po.FILTER_CW, po.DEMOD_AM: po.FILTER_AM}.get(d, po.FILTER_2700)
-        params.append(po.default_params(demod=d, audio_filter=flt, agc_mode=c % 4, notch_on=int(d == po.DEMOD_CW_LSB),
-                                        nr_kind=po.NR_LMS if lvl else po.NR_OFF, nr_level=lvl))
-        demod.append(d)
-    return params, demod
+    """config 5 of BASELINE.json as bench.py defines it (bench.channel_params): mode by c mod 4, notch on CW channels,
+    DNR level by c mod 5, AGC by c mod 4"""
+    params = [po.default_params(**bench.channel_params("cfg5", c)) for c in range(nc)]
+    return params, [p.demod for p in params]
 
 
 def test_full_chain_all_modes(rd, po):
+    """The whole graph on 40 all-mode channels over 96 blocks: every f32 stage group within 1e-4 on identical inputs,
+    integer stages and spectra bit-exact, demodulated-audio SNR equal within 0.1 dB on every channel — NR on or off,
+    AGC on or off (tests/parity_util.py)."""
     nc, nb = 40, 96
-    params, demod = _all_mode_params(po, nc)
-    iq = synth.synth_iq(np.arange(nc), nb, demod, interferer=[d == po.DEMOD_CW_LSB for d in demod])
-    g_out, g_f32, o_out, o_f32, bank, chans = run_both(rd, po, rd.STAGE_ALL, params, iq, blocks_per_call=8)
-    # The chain has a q15 boundary in the middle (SDR output, K4 -> K5): an f32 value that straddles a truncation
-    # boundary flips one LSB of the FFT-filter input, and the NLMS behind it can turn that into a few output LSBs.
-    # Per-stage f32 parity (<= 1e-4) is asserted by the stage tests above; here: whole-chain closeness.
-    d = np.abs(g_out.astype(np.int32) - o_out)
-    assert d.max() <= 8 and (d > 0).mean() < 2e-2, (d.max(), (d > 0).mean())
-    for c in range(nc):
-        assert rel_rms(g_f32[16:, c], o_f32[16:, c]) <= 5e-4, c
-        s_g = synth.snr_db(o_out[16:, c, :, 0], g_out[16:, c, :, 0])
-        assert s_g > 60.0, (c, s_g)
-    # demodulated-audio SNR equal within 0.1 dB on the tone channels (LSB / USB carry the 5-tone surrogate)
-    tones = [400.0, 700.0, 1100.0, 1700.0, 2300.0]
-    for c in range(nc):
-        if demod[c] in (po.DEMOD_LSB, po.DEMOD_USB) and params[c].nr_level == 0 and params[c].agc_mode == po.AGC_OFF:
-            a = synth.tone_snr_db(g_out[40:, c, :, 0], tones)
-            b = synth.tone_snr_db(o_out[40:, c, :, 0], tones)
-            assert abs(a - b) <= SNR_TOL_DB, (c, a, b)
-    # spectra stay bit-exact inside the full pipeline (they only depend on integer stages / raw IQ)
-    spec, ready = bank.read_spectrum()
-    assert ready.all()
-    for c, ch in enumerate(chans):
-        assert np.array_equal(spec[c], ch.read_spectrum()[0])
+    iq = bench.make_inputs("cfg5", 0, nc, nb)
+    report = {}
+    g_out, bank, chans = check_chain(rd, po, lambda c: bench.channel_params("cfg5", c), rd.STAGE_ALL, nc, iq, np.arange(nc), 8,
+                                     snr_from=40, report=report)
+    print("full chain:", report)
+    aspec, aready = bank.read_audio_spectrum()
+    assert aready.all() and aspec.any()
 
 
 @pytest.mark.parametrize("stage", ["notch", "dnr"])
@@ -487,8 +462,6 @@ def test_mode_changes_between_blocks(rd, po):
     nc, nb = 6, 40
     iq = synth.synth_iq(np.arange(nc), nb, [0, 1, 2, 3, 4, 0], interferer=True)
     sm = rd.STAGE_ALL
-    bank = make_bank(rd, nc, sm, max_blocks=8)
-    chans = [po.OracleChan(po.default_config(stage_mask=sm)) for _ in range(nc)]
     schedule = {
         0: dict(),
         8: dict(demod=po.DEMOD_USB, nr_kind=po.NR_LMS, nr_level=20, notch_on=1),
@@ -496,32 +469,22 @@ def test_mode_changes_between_blocks(rd, po):
         24: dict(nr_kind=po.NR_OFF, nr_level=0, notch_on=0, out_gain=0.8),
         32: dict(demod=po.DEMOD_CW_LSB, audio_filter=po.FILTER_CW, nr_kind=po.NR_LMS, nr_level=50, notch_on=1, notch_level=30),
     }
-    cur = po.default_params()
-    g_all, o_all = [], []
-    for b0 in range(0, nb, 8):
-        cur = cur.copy(**schedule[b0])
-        bank.set_mode(0, nc, to_rd_params(rd, cur))
-        chunk = np.ascontiguousarray(iq[b0:b0 + 8])
-        g_all.append(bank.process_host(chunk))
-        o = np.zeros_like(chunk)
-        for c, ch in enumerate(chans):
-            ch.set_mode(cur)
-            o[:, c] = ch.process(chunk[:, c])
-        o_all.append(o)
-    g, o = np.concatenate(g_all), np.concatenate(o_all)
-    d = np.abs(g.astype(np.int32) - o)
-    assert d.max() <= 8 and (d > 0).mean() < 2e-2, (d.max(), (d > 0).mean())
-    assert synth.snr_db(o, g) > 60.0
+    cum, cur = {}, {}
+    for b0 in sorted(schedule):
+        cur = dict(cur, **schedule[b0])
+        cum[b0] = cur
+    # every f32 stage group within 1e-4 on identical inputs THROUGH the re-initialisations (the schedule applies to the
+    # stage-wise banks too), integer stages bit-exact, tone SNR equal within 0.1 dB over the last setting
+    check_chain(rd, po, lambda c, b0: cum[b0], sm, nc, iq, np.arange(nc), 8, snr_from=32,
+                tones=[400.0, 700.0, 1000.0, 1100.0, 1500.0, 1700.0, 2300.0])
 
 
 # ------------------------------------------------------------------------------------------ edges, ABI on device
 
 @pytest.mark.parametrize("nc", [1, 5, 17, 33])
 def test_ragged_channel_counts(rd, po, nc):
-    params, demod = _all_mode_params(po, nc)
-    iq = synth.synth_iq(np.arange(nc), 12, demod)
-    g_out, _, o_out, _, _, _ = run_both(rd, po, rd.STAGE_ALL, params, iq, blocks_per_call=5)
-    assert np.abs(g_out.astype(np.int32) - o_out).max() <= 8 and synth.snr_db(o_out, g_out) > 60.0
+    iq = bench.make_inputs("cfg5", 0, nc, 12)
+    check_chain(rd, po, lambda c: bench.channel_params("cfg5", c), rd.STAGE_ALL, nc, iq, np.arange(nc), 5)
 
 
 def test_extreme_inputs(rd, po):
@@ -538,17 +501,18 @@ def test_extreme_inputs(rd, po):
     # reference recurrence multiplies every rounding difference by 1/eps = 8.4e6 and any two f32 evaluation orders
     # (the oracle's sequential sums, this kernel's grouped look-ahead) decorrelate until the window has drained.
     # Outside that window the usual closeness holds; inside it the output must stay bounded and drain to zero too.
-    d = np.abs(g_out.astype(np.int32) - o_out)
     keep = np.ones(nb, bool)
     keep[3:5] = False
-    assert d[keep].max() <= 8, d[keep].max()
     assert np.abs(g_out[3:5].astype(np.int32)).max() <= 2 * np.abs(o_out.astype(np.int32)).max() + 64
     assert not g_out[5:].any() and not o_out[5:].any()
     spec = bank.read_audio_spectrum()[0]
     assert np.isfinite(spec.astype(float)).all()
-    # the stages in front of the collapse are unaffected: bit-exact / 1 LSB
+    # the stages in front of the collapse are unaffected: bit-exact / 1 LSB ...
     g2, _, o2, _, _, _ = run_both(rd, po, rd.STAGE_FRONTEND | rd.STAGE_NOTCH | rd.STAGE_AGC, params, iq, blocks_per_call=3)
     assert np.abs(g2.astype(np.int32) - o2).max() <= 1
+    # ... and so are K5 + K6 on identical inputs (the audio K4 produced) outside the collapse window
+    g3, _, o3, _, _, _ = run_both(rd, po, rd.STAGE_FFTFILT | rd.STAGE_NR, params, g2, blocks_per_call=3)
+    assert np.abs(g3.astype(np.int32) - o3)[keep].max() <= 1
 
 
 def test_level_collapse_with_a_noise_floor(rd, po):
@@ -645,3 +609,30 @@ def test_full_size_slot_independence(rd):
     small.set_mode(0, 3, rd.default_params(nr_kind=rd.NR_LMS, nr_level=30, notch_on=1))
     ref = small.process_host(np.ascontiguousarray(np.broadcast_to(one, (nb, 3, 128, 2))))
     assert np.array_equal(out[:, 4000], ref[:, 1])
+
+
+def test_nlms_direct_cross_check_kernel(rd, po, monkeypatch):
+    """RDSP_NLMS_IMPL=direct (read at create): the sample-by-sample k_nlms_direct — the textbook evaluation order — meets
+    the same bar against the oracle as the look-ahead kernel, on the notch and on the DNR"""
+    monkeypatch.setenv("RDSP_NLMS_IMPL", "direct")
+    nc, nb = 20, 24
+    iq = bench.make_inputs("cfg5", 0, nc, nb)
+    check_chain(rd, po, lambda c: bench.channel_params("cfg5", c), rd.STAGE_ALL, nc, iq, np.arange(nc), 8)
+
+
+def test_two_devices_in_one_process(rd, po):
+    """one handle per GPU inside ONE process: per-device kernel attributes (the > 48 KB shared-memory
+    opt-in of k_front_tc, the carve-outs) are set on each device, and both handles give the single-device result"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    nc, nb = 300, 8
+    iq = bench.make_inputs("cfg5", 0, nc, nb)
+    outs = []
+    for dev in (0, 1, 0):
+        cfg = rd.default_config(n_channels=nc, device=dev, stage_mask=rd.STAGE_ALL, max_blocks_per_call=nb, io_location=rd.IO_HOST)
+        bank = rd.ReceiverBank(cfg)
+        for c in range(nc):
+            bank.set_mode(c, 1, rd.default_params(**bench.channel_params("cfg5", c)))
+        outs.append(bank.process_host(iq))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
