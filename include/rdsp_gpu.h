@@ -107,6 +107,20 @@ enum {
 /* where iq_in / audio_out of process_block(s) live */
 enum { RDSP_IO_DEVICE = 0, RDSP_IO_HOST = 1 };
 
+/* layout of audio_out */
+enum {
+    RDSP_AUDIO_STEREO = 0,     /* [n_blocks][n_channels][128][2]  L,R interleaved (the two AudioPlayQueue ports) */
+    RDSP_AUDIO_MONO   = 1      /* [n_blocks][n_channels][128]     L only: the sketch plays L == R whenever the DNR runs
+                                  (RDSP_convolutional.h:333-336) and whenever the chain ends in the SDR block; with the
+                                  FFT filter last and no DNR, R (the quadrature output of the analytic filter) is dropped */
+};
+
+/* CUDA graphs on the block path */
+enum {
+    RDSP_GRAPH_AUTO = 0,       /* a call shape (n_blocks, buffers, tables) seen twice is captured and replayed with one launch */
+    RDSP_GRAPH_OFF  = 1        /* always enqueue kernel by kernel */
+};
+
 /* tap-table kinds for rdsp_gpu_set_taps / get_taps */
 enum {
     RDSP_TAPS_HILBERT_I = 0,   /* filter applied to I, index = demod mode */
@@ -133,6 +147,8 @@ typedef struct {
                                     many independent groups on streams of their own (0 = default = 1 group; max 8;
                                     reduced silently while a group would hold < 256 channels).  Every launch still
                                     covers all n_blocks of the call.  Measured: 1 is fastest */
+    uint32_t audio_layout;       /* RDSP_AUDIO_STEREO (default) or RDSP_AUDIO_MONO */
+    uint32_t graph_mode;         /* RDSP_GRAPH_AUTO (default) or RDSP_GRAPH_OFF */
 } rdsp_gpu_config_t;
 
 typedef struct {
@@ -221,7 +237,8 @@ int  rdsp_gpu_get_mask(rdsp_gpu_t *h, uint32_t ch, float *mask512);
 int  rdsp_gpu_read_debug_f32(rdsp_gpu_t *h, uint32_t n_blocks, uint32_t ch_first, uint32_t ch_count, float *out);
 
 /* Instrumentation */
-uint64_t    rdsp_gpu_kernel_launches(const rdsp_gpu_t *h);     /* kernels launched so far by this handle */
+uint64_t    rdsp_gpu_kernel_launches(const rdsp_gpu_t *h);     /* kernels launched so far by this handle (graph replays count their kernels) */
+uint64_t    rdsp_gpu_graph_replays(const rdsp_gpu_t *h);       /* process calls that ran as ONE cudaGraphLaunch */
 int         rdsp_gpu_profile(rdsp_gpu_t *h, int enable);        /* 1: bracket every kernel with CUDA events */
 /* Accumulated per-kernel device time since profiling was enabled. Returns the number of
  * kernel kinds; for i < n: names[i] (static string), ms[i], launches[i]. */

@@ -40,6 +40,7 @@ class Config(C.Structure):
         ("async_", C.c_uint32), ("debug_f32", C.c_uint32), ("spec256_naverage", C.c_uint32),
         ("agc_target", C.c_float), ("agc_max_gain", C.c_float), ("agc_attack_ms", C.c_float),
         ("agc_decay_ms", C.c_float * 4), ("pipeline_chunks", C.c_uint32),
+        ("audio_layout", C.c_uint32), ("graph_mode", C.c_uint32),
     ]
 
 
@@ -84,6 +85,7 @@ def lib():
         L.rdsp_oracle_chan_process.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p,
                                                C.c_size_t, C.c_void_p, C.c_size_t]
         L.rdsp_oracle_chan_spec256_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rdsp_oracle_chan_dnr_f32.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.rdsp_oracle_chan_read_spectrum.argtypes = [C.c_void_p, C.c_void_p]
         L.rdsp_oracle_chan_read_audio_spectrum.argtypes = [C.c_void_p, C.c_void_p]
         L.rdsp_oracle_chan_read_panadapter.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
@@ -167,6 +169,13 @@ class OracleChan:
         lib().rdsp_oracle_chan_process(self._h, nb, _ptr(iq), 2 * BLK, _ptr(out), 2 * BLK,
                                        _ptr(f32) if want_f32 else None, 2 * BLK)
         return (out, f32) if want_f32 else out
+
+    def dnr_f32(self, x: np.ndarray) -> np.ndarray:
+        """K6 alone (+ the 1.1 post-NR gain) on f32 blocks [n_blocks,128]: what the chain would emit for this K5 output."""
+        x = np.ascontiguousarray(x, np.float32)
+        y = np.zeros_like(x)
+        lib().rdsp_oracle_chan_dnr_f32(self._h, x.shape[0], _ptr(x), _ptr(y))
+        return y
 
     def spec256_raw(self, I: np.ndarray, Q: np.ndarray):
         """K9 alone (no biquads) on int16 [n_blocks,128] I/Q -> list of (block_index, output[256])."""

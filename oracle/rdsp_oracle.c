@@ -479,6 +479,33 @@ static void spectral_subtract(rdsp_oracle_chan_t *c, const float *fft_buf, float
     }
 }
 
+/* K6 + the post-NR gain: the DNR branch of doConvolutionalProcessing, RDSP_convolutional.h:326-337 */
+static void stage_dnr(rdsp_oracle_chan_t *c, float *float_buffer_L, float *float_buffer_R)
+{
+    if (c->par.nr_level != c->old_nr_level) {
+        nlms_init(&c->dnr, c->par.nr_level);
+        c->old_nr_level = c->par.nr_level;
+    }
+    nlms_run(&c->dnr, 128, float_buffer_L);
+    for (int i = 0; i < BLK; i++) {
+        float_buffer_L[i] = float_buffer_L[i] * 1.1;                 /* double multiply, :334 */
+        float_buffer_R[i] = float_buffer_L[i];
+    }
+}
+
+/* test hook: K6 alone on f32 blocks x [n_blocks][128] (in the chain: the L output of K5), y = what the chain emits.
+ * Lets a test hand the DNR of both sides IDENTICAL inputs: K6 multiplies a 1e-7 difference in its input (two FFT
+ * algorithms) by ~1e3 in the two blocks after its same-block-reference first call. */
+void rdsp_oracle_chan_dnr_f32(rdsp_oracle_chan_t *c, uint32_t n_blocks, const float *x, float *y)
+{
+    float L[BLK], R[BLK];
+    for (uint32_t b = 0; b < n_blocks; b++) {
+        memcpy(L, x + (size_t)b * BLK, sizeof(L));
+        if (c->par.nr_kind == RDSP_NR_LMS && c->par.nr_level > 0) stage_dnr(c, L, R);
+        memcpy(y + (size_t)b * BLK, L, sizeof(L));
+    }
+}
+
 /* K5 + K6/K8: doConvolutionalProcessing body, RDSP_convolutional.h:250-337 */
 static void stage_conv(rdsp_oracle_chan_t *c, const int16_t *sp_L, const int16_t *sp_R, float *out_L, float *out_R)
 {
@@ -514,17 +541,7 @@ static void stage_conv(rdsp_oracle_chan_t *c, const int16_t *sp_L, const int16_t
         float_buffer_L[i] = iFFT_buffer[FFT_L + i * 2];
         float_buffer_R[i] = iFFT_buffer[FFT_L + i * 2 + 1];
     }
-    if (kind == RDSP_NR_LMS && c->par.nr_level > 0) {                /* :326-337 */
-        if (c->par.nr_level != c->old_nr_level) {
-            nlms_init(&c->dnr, c->par.nr_level);
-            c->old_nr_level = c->par.nr_level;
-        }
-        nlms_run(&c->dnr, 128, float_buffer_L);
-        for (int i = 0; i < BLK; i++) {
-            float_buffer_L[i] = float_buffer_L[i] * 1.1;             /* double multiply, :334 */
-            float_buffer_R[i] = float_buffer_L[i];
-        }
-    }
+    if (kind == RDSP_NR_LMS && c->par.nr_level > 0) stage_dnr(c, float_buffer_L, float_buffer_R);
     memcpy(out_L, float_buffer_L, sizeof(float_buffer_L));
     memcpy(out_R, float_buffer_R, sizeof(float_buffer_R));
 }

@@ -45,6 +45,7 @@ void rdsp_oracle_chan_process(rdsp_oracle_chan_t *c, uint32_t n_blocks,
                               int16_t *audio, size_t stride_out,
                               float *f32, size_t stride_f32);
 
+void rdsp_oracle_chan_dnr_f32(rdsp_oracle_chan_t *c, uint32_t n_blocks, const float *x, float *y);   /* K6 alone (+ the 1.1 gain) on f32 blocks */
 void rdsp_oracle_chan_spec256_raw(rdsp_oracle_chan_t *c, const int16_t *i_blk, const int16_t *q_blk);  /* K9 without biquads */
 int  rdsp_oracle_chan_read_spectrum(rdsp_oracle_chan_t *c, uint16_t *out256);        /* returns available() */
 int  rdsp_oracle_chan_read_audio_spectrum(rdsp_oracle_chan_t *c, uint16_t *out512);

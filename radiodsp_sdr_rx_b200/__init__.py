@@ -11,7 +11,7 @@ from .native import (  # noqa: F401
     FILTER_CW, FILTER_2100, FILTER_2700, FILTER_3100, FILTER_AM,
     AGC_OFF, AGC_FAST, AGC_MEDIUM, AGC_SLOW, NR_OFF, NR_LMS, NR_SPECTRAL,
     STAGE_FRONTEND, STAGE_NOTCH, STAGE_AGC, STAGE_FFTFILT, STAGE_NR, STAGE_SPEC256, STAGE_SPEC1024, STAGE_ALL,
-    IO_DEVICE, IO_HOST, TAPS_HILBERT_I, TAPS_HILBERT_Q, TAPS_BANDPASS,
+    IO_DEVICE, IO_HOST, AUDIO_STEREO, AUDIO_MONO, GRAPH_AUTO, GRAPH_OFF, TAPS_HILBERT_I, TAPS_HILBERT_Q, TAPS_BANDPASS,
 )
 
 __all__ = ["ReceiverBank", "Config", "Params", "default_config", "default_params", "RdspError"]

@@ -92,8 +92,10 @@ __global__ void __launch_bounds__(NT) k_spec1024(Spec1024Args a)
     int16_t *ring = a.ring + (size_t)ch * 8 * RDSP_BLK;
     uint2 *gring = reinterpret_cast<uint2 *>(ring);               // 32 uint2 (4 samples each) per slot
 
+    const unsigned long long tick0 = a.tick_in->tick;
+    if (blockIdx.x == 0 && tid == 0) a.tick_out->tick = tick0 + (unsigned long long)a.T;
     for (int t = 0; t < a.T; t++) {
-        const unsigned long long tick = a.tick0 + t;
+        const unsigned long long tick = tick0 + t;
         const int slot = (int)(tick & 7ull);
         if (tid < 32) {                                             // append L of this block: 4 frames (16 bytes) per lane
             const int4 v = *reinterpret_cast<const int4 *>(a.audio + ((size_t)t * a.C + ch) * 2 * RDSP_BLK + tid * 8);

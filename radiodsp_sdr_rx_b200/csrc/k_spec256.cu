@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) k_spec256(Spec256Args a)
     uint32_t wp[8];                                               // window of elements 16 q + l (low half) and 16 (8 + q) + l (high half)
 #pragma unroll
     for (int q = 0; q < 8; q++) wp[q] = mk16(s_win[16 * q + l], s_win[16 * (8 + q) + l]);
-    int have_prev = a.have_prev, count = a.count;
+    int have_prev = a.tick_in->have_prev, count = a.tick_in->count;
 
     for (int t = 0; t < a.T; t++) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.iq + ((size_t)t * a.C + ch) * 2 * RDSP_BLK);
@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) k_spec256(Spec256Args a)
         have_prev = 1;
     }
 
+    if (blockIdx.x == 0 && threadIdx.x == 0) { a.tick_out->have_prev = have_prev; a.tick_out->count = count; }
     if (active) {
 #pragma unroll
         for (int k = 0; k < 16; k++) a.sum[(size_t)ch * 256 + (__brev((unsigned)(16 * l + k)) >> 24)] = sum[k];

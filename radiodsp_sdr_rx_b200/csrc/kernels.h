@@ -133,8 +133,8 @@ struct Spec256Args {
     uint16_t *output;           // [C][256]
     int C, T;
     int ch0, n;                 // channel range of this launch: [ch0, ch0 + n)
-    int have_prev;              // 0 on the very first tick
-    int count;                  // averaging counter at the first tick of this call
+    const RdspTick *tick_in;    // have_prev / count at the first tick of this call ...
+    RdspTick *tick_out;         // ... and where their values after the call go (the other copy)
     int naverage;
     unsigned long long div_magic;   // ceil(2^div_shift / naverage), div_shift = 32 + ceil(log2 naverage):
     int div_shift;                  // (magsq * div_magic) >> div_shift == magsq / naverage for magsq <= 2^31
@@ -151,8 +151,8 @@ struct Spec1024Args {
     int C, T;
     const int *list;            // channels of this launch (n entries), or nullptr: [ch0, ch0 + n)
     int ch0, n;
-    unsigned long long tick0;   // global tick index of block 0 of this call
-    int any_fft;                // some tick of this call completes a 1024-sample frame
+    const RdspTick *tick_in;    // tick index of block 0 of this call ...
+    RdspTick *tick_out;         // ... and where tick + T goes (the other copy)
     const int2 *tw;             // [3072]
     const int16_t *win;         // [1024] Hann
 };

@@ -48,6 +48,15 @@ struct __align__(16) RdspChanParams {
 };
 static_assert(sizeof(RdspChanParams) == 48, "RdspChanParams layout");
 
+// Tick bookkeeping that is uniform over channels, kept ON THE DEVICE so that a process call needs no per-call kernel
+// argument that changes from call to call (a captured CUDA graph replays as is).  Two copies: a call reads copy
+// `parity` and its kernels write the advanced values into copy `parity ^ 1`, which nothing reads during that call.
+struct RdspTick {
+    unsigned long long tick;   // index of the first block of the call (AudioAnalyzeFFT1024 frame cadence); advanced by k_spec1024
+    int have_prev;             // 0 until the IQ spectrum has seen a block (analyze_fft256iq.cpp:73-77); advanced by k_spec256
+    int count;                 // averaging counter of the IQ spectrum (analyze_fft256iq.cpp:99-113)
+};
+
 // ---- saturating / packed-q15 arithmetic (ARMv7E-M DSP instruction semantics) --------------
 __device__ __forceinline__ int32_t sat16(int32_t v) { return max(-32768, min(32767, v)); }
 __device__ __forceinline__ int32_t lo16(uint32_t a) { return (int32_t)(int16_t)(a & 0xFFFFu); }

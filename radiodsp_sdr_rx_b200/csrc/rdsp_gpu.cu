@@ -33,6 +33,14 @@ const char *const kKernelNames[KK_COUNT] = {"k_front", "k_nlms_notch", "k_agc", 
 
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
 
+// one captured call shape (run_call)
+struct GraphEntry {
+    int T; const void *iq; void *audio; int fe_cur, par; cudaStream_t st;
+    cudaGraphExec_t exec;                      // nullptr: seen once, not captured yet
+    uint64_t launches;                         // kernels in the graph
+    unsigned long long last_use;
+};
+
 constexpr int kMaxGroups = 8;
 constexpr int kStreams = 3 * kMaxGroups + 1;   // per channel group: main chain, spectrum branch, side branch; + the front end
 
@@ -114,9 +122,17 @@ struct rdsp_gpu {
     float *d_scr = nullptr, *d_dbg = nullptr;
     int16_t *d_hp_iq = nullptr;                // high-passed IQ between k_biquad and k_spec256
 
-    // tick bookkeeping (uniform over channels)
+    // tick bookkeeping (uniform over channels): the kernels read it from the device copy d_tick[tick_par] and write the
+    // advanced values into d_tick[tick_par ^ 1]; the host keeps a mirror for the ready flags
     int spec_have_prev = 0, spec_count = 0;
     unsigned long long tick = 0;
+    RdspTick *d_tick = nullptr;
+    int tick_par = 0;
+    // CUDA graphs of the call shapes seen so far (run_call); dropped whenever tables, lists or tiles change
+    static constexpr size_t kMaxGraphs = 32;
+    std::vector<GraphEntry> graphs;
+    bool use_graphs = true;
+    unsigned long long graph_clock = 0, graph_replays = 0;
     std::vector<uint8_t> spec_ready, spec1024_ready;
 
     // instrumentation
@@ -239,9 +255,12 @@ cudaError_t zero_rows(T *base, size_t row, const std::vector<int> &chs, cudaStre
     return cudaSuccess;
 }
 
+void drop_graphs(rdsp_gpu *h);
+
 // bring the device view of parameters, work lists, taps and masks up to date (start of a process call)
 int sync_tables(rdsp_gpu *h)
 {
+    if (h->taps_dirty || h->par_dirty) drop_graphs(h);     // launch shapes and table pointers may change
     if (h->taps_dirty) {
         std::vector<int32_t> t(15 * RDSP_TAPS_PAD, 0);
         for (int r = 0; r < 15; r++)
@@ -360,7 +379,7 @@ void prof_collect(rdsp_gpu *h)
 void free_all(rdsp_gpu *h)
 {
     void *ptrs[] = {h->d_fe_hist2, h->d_toep, h->d_tile_ch, h->d_tile_rows, h->d_sam_state, h->d_nb_ref,
-                    h->d_par, h->d_list_notch, h->d_list_plain, h->d_list_dnr, h->d_list_dnr_p, h->d_list_dnr_n, h->d_taps, h->d_masks, h->d_tw, h->d_win256, h->d_win1024,
+                    h->d_par, h->d_tick, h->d_list_notch, h->d_list_plain, h->d_list_dnr, h->d_list_dnr_p, h->d_list_dnr_n, h->d_taps, h->d_masks, h->d_tw, h->d_win256, h->d_win1024,
                     h->d_tw256, h->d_sin512, h->d_fe_hist, h->d_nc_coeff, h->d_nc_prev, h->d_nc_energy, h->d_nc_first, h->d_dn_coeff,
                     h->d_dn_prev, h->d_dn_energy, h->d_dn_first, h->d_agc_env, h->d_conv_last, h->d_nfloor, h->d_bq_state,
                     h->d_spec_prev, h->d_spec_sum, h->d_spec_out, h->d_ring, h->d_spec1024_out, h->d_view, h->d_smeter,
@@ -384,6 +403,304 @@ void free_all(rdsp_gpu *h)
         if (h->stage_stream[s]) cudaStreamDestroy(h->stage_stream[s]);
     }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+}
+
+// ---- one call on the device ---------------------------------------------------------------------------------
+// Everything a process call enqueues between the fork on the handle's stream `st` and the joins back onto it.
+// Nothing in here depends on how many calls came before except through (fe_cur, par) — the ping-pong index of the
+// front end's delay lines and of the device-resident tick state — so the whole fork/join DAG can be captured into
+// a CUDA graph once per (T, buffers, fe_cur, par, table version) and replayed (graph_launch below).
+//
+// Channel groups.  Channels are independent, and every kernel after the front end is bound by the latency of a
+// per-channel recurrence rather than by throughput.  The call is therefore cut ACROSS channels: the front end takes
+// all channels in one launch (tiles x time segments fill the SMs), then G channel groups walk the rest of the graph
+// on streams of their own — notch -> AGC -> FFT filter -> DNR -> audio spectrum on one, high-pass -> IQ spectrum
+// on another — with no dependency between groups, so the hardware overlaps G latency-bound chains.  Every launch
+// still covers all T blocks of the call: state makes one round trip and the launch latency is paid once.
+// (The first version cut the call along TIME instead; its timeline, tools/diag_timeline.py, showed every stage
+// paying its launch + state latency per chunk and the DNR stage of 4 chunks taking twice its one-launch time.)
+// While per-kernel profiling is on, everything runs as one group on one stream so that each kernel's time is its own.
+int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStream_t st, bool piped, int fe_cur, int par)
+{
+    const bool fe = has(h, RDSP_STAGE_FRONTEND), notch = has(h, RDSP_STAGE_NOTCH), agc = has(h, RDSP_STAGE_AGC);
+    const bool ff = has(h, RDSP_STAGE_FFTFILT), nr = has(h, RDSP_STAGE_NR);
+    const int C = h->C;
+    const RdspTick *tick_in = h->d_tick + par;
+    RdspTick *tick_out = h->d_tick + (par ^ 1);
+    int G = 1;
+    if (piped) {
+        // measured (cfg5, 8192 channels, T = 8): 1 group 0.71 ms, 2 groups 0.90, 4 groups 0.83, 8 groups 1.11 — small
+        // concurrent launches of the same kernel slow each other more than they overlap, so the default is ONE group
+        // (main chain + spectrum branch + the AGC of the channels that bypass the notch on three streams)
+        G = h->cfg.pipeline_chunks ? (int)h->cfg.pipeline_chunks : 1;
+        if (G > kMaxGroups) G = kMaxGroups;
+        while (G > 1 && C / G < 256) G--;
+        CK(cudaEventRecord(h->ev_fork, st));                             // the input (and earlier calls) are in place
+    }
+    cudaStream_t s_front = piped ? h->stage_stream[3 * kMaxGroups] : st;
+    const int naverage = (int)h->cfg.spec256_naverage;
+    int lgn = 0; while ((1u << lgn) < h->cfg.spec256_naverage) lgn++;
+    float *dbg = h->d_dbg;
+
+    // ---- K0+K1+K2, all channels
+    bool front_last = false;
+    if (fe) {
+        if (piped) CK(cudaStreamWaitEvent(s_front, h->ev_fork, 0));
+        front_last = !(notch || agc || ff);
+        FrontArgs a{};
+        a.iq = iq; a.out_mono = front_last ? nullptr : h->d_mid_a; a.out_stereo = front_last ? audio : nullptr;
+        a.dbg = front_last ? dbg : nullptr; a.par = h->d_par; a.taps = h->d_taps; a.C = C; a.T = T;
+        Prof pr(h, KK_FRONT, s_front);
+        if (h->front_tc) {
+            a.hist = fe_cur ? h->d_fe_hist2 : h->d_fe_hist;
+            a.hist_out = fe_cur ? h->d_fe_hist : h->d_fe_hist2;
+            FrontTcTables tb{};
+            tb.tile_ch = h->d_tile_ch; tb.tile_rows = h->d_tile_rows; tb.toep = h->d_toep; tb.n_tiles = h->n_tiles;
+            tb.any_sam = h->any_sam; tb.sam_tiles = h->sam_tiles;
+            a.sam_state = h->d_sam_state; a.nb_ref = h->d_nb_ref;
+            launch_front_tc(a, tb, s_front);
+        } else {
+            if (h->any_sam) { h->err = "SAM and the noise blanker are only built in the tensor-core front end (unset RDSP_FRONT_IMPL)"; return RDSP_ERR_STATE; }
+            a.hist = fe_cur ? h->d_fe_hist2 : h->d_fe_hist;
+            launch_front(a, s_front);
+        }
+    }
+    if (piped && fe) CK(cudaEventRecord(h->ev_front, s_front));
+
+    // sub-range of a sorted channel list that falls into [c0, c1)
+    auto sub = [](const std::vector<int> &l, int c0, int c1, int &first, int &count) {
+        first = (int)(std::lower_bound(l.begin(), l.end(), c0) - l.begin());
+        count = (int)(std::lower_bound(l.begin(), l.end(), c1) - l.begin()) - first;
+    };
+
+    // one chain of the audio graph on stream `cs` for the channels [c0, c1) of class `cls`:
+    //   0 = every channel (no split), 1 = the channels that bypass the notch, 2 = the channels whose notch runs.
+    // With classes 1 and 2 on two streams the latency-bound notch -> AGC -> ... chain of the (few) notched channels runs
+    // beside the wide kernels of the others instead of in front of them.
+    // the spectrum branches keep the issue slots contended while the NLMS kernels run (k_nlms.cu, launch_nlms)
+    const int nlms_packed = (has(h, RDSP_STAGE_SPEC256) || has(h, RDSP_STAGE_SPEC1024)) ? 1 : 0;
+    auto run_chain = [&](cudaStream_t cs, int cls, int c0, int c1) -> int {
+        const int nc = c1 - c0;
+        int f_notch = 0, n_notch = 0, f_plain = 0, n_plain = 0;
+        if (notch) { sub(h->l_notch, c0, c1, f_notch, n_notch); sub(h->l_plain, c0, c1, f_plain, n_plain); }
+        const int *cls_list = cls == 1 ? h->d_list_plain + f_plain : (cls == 2 ? h->d_list_notch + f_notch : nullptr);
+        const int cls_n = cls == 1 ? n_plain : (cls == 2 ? n_notch : nc);
+        if (cls_n <= 0) return RDSP_OK;
+        const int16_t *mono = nullptr;
+        if (fe) {
+            mono = h->d_mid_a;
+            if (notch || agc) {
+                AgcArgs ag{};
+                ag.out_mono = ff ? h->d_mid_b : nullptr; ag.out_stereo = ff ? nullptr : audio;
+                ag.dbg = ff ? nullptr : dbg; ag.env = h->d_agc_env; ag.par = h->d_par; ag.C = C; ag.T = T;
+                ag.agc_stage = agc ? 1 : 0;
+                ag.target = h->cfg.agc_target; ag.max_gain = h->cfg.agc_max_gain; ag.alpha_a = h->agc_alpha_a;
+                if (cls != 2) {
+                    // channels that bypass the notch read the front end's q15 rows ...
+                    ag.list = notch ? h->d_list_plain + f_plain : nullptr; ag.n_list = notch ? n_plain : nc; ag.ch0 = c0;
+                    ag.in_q15 = h->d_mid_a; ag.in_f32 = nullptr;
+                    if (ag.n_list > 0) { Prof pr(h, KK_AGC, cs); launch_agc(ag, cs); }
+                }
+                if (cls != 1 && notch && n_notch > 0) {
+                    NlmsArgs n{};
+                    n.list = h->d_list_notch + f_notch; n.n_list = n_notch; n.C = C; n.T = T;
+                    n.in_q15 = h->d_mid_a; n.out_f32 = h->d_scr;
+                    n.coeff = h->d_nc_coeff; n.prev = h->d_nc_prev; n.energy = h->d_nc_energy; n.first = h->d_nc_first;
+                    n.par = h->d_par; n.mode = 0; n.packed = nlms_packed; n.direct = h->nlms_direct;
+                    { Prof pr(h, KK_NOTCH, cs); launch_nlms(n, cs); }
+                    // ... the others read the notch's f32 error signal
+                    ag.list = h->d_list_notch + f_notch; ag.n_list = n_notch; ag.in_q15 = nullptr; ag.in_f32 = h->d_scr;
+                    { Prof pr(h, KK_AGC, cs); launch_agc(ag, cs); }
+                }
+                mono = h->d_mid_b;
+            }
+        }
+        if (ff) {
+            FftFiltArgs f{};
+            f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq; f.out_stereo = audio; f.out_f32_L = h->d_scr;
+            f.dbg = dbg; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256; f.sin512 = h->d_sin512;
+            f.par = h->d_par; f.C = C; f.T = T; f.list = cls_list; f.ch0 = c0; f.n = cls_n; f.nr_stage = nr ? 1 : 0;
+            { Prof pr(h, KK_FFTFILT, cs); launch_fftfilt(f, cs); }
+            if (nr) {
+                const std::vector<int> &ld = cls == 1 ? h->l_dnr_p : (cls == 2 ? h->l_dnr_n : h->l_dnr);
+                const int *dl = cls == 1 ? h->d_list_dnr_p : (cls == 2 ? h->d_list_dnr_n : h->d_list_dnr);
+                int f_dnr = 0, n_dnr = 0;
+                sub(ld, c0, c1, f_dnr, n_dnr);
+                if (n_dnr > 0) {
+                    NlmsArgs n{};
+                    n.list = dl + f_dnr; n.n_list = n_dnr; n.C = C; n.T = T;
+                    n.in_f32 = h->d_scr; n.out_stereo = audio; n.dbg = dbg;
+                    n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
+                    n.par = h->d_par; n.mode = 1; n.packed = nlms_packed; n.direct = h->nlms_direct;
+                    { Prof pr(h, KK_DNR, cs); launch_nlms(n, cs); }
+                }
+            }
+        }
+        if (has(h, RDSP_STAGE_SPEC1024)) {
+            Spec1024Args s1{};
+            s1.audio = audio; s1.ring = h->d_ring; s1.output = h->d_spec1024_out; s1.C = C; s1.T = T;
+            s1.list = cls_list; s1.ch0 = c0; s1.n = cls_n;
+            s1.tick_in = tick_in; s1.tick_out = tick_out; s1.tw = h->d_tw; s1.win = h->d_win1024;
+            { Prof pr(h, KK_SPEC1024, cs); launch_spec1024(s1, cs); }
+        }
+        return RDSP_OK;
+    };
+
+    for (int g = 0; g < G; g++) {
+        const int c0 = (int)((long long)C * g / G), c1 = (int)((long long)C * (g + 1) / G), nc = c1 - c0;
+        cudaStream_t s_main = piped ? h->stage_stream[g] : st;
+        cudaStream_t s_spec = piped ? h->stage_stream[kMaxGroups + g] : st;
+        cudaStream_t s_side = piped ? h->stage_stream[2 * kMaxGroups + g] : st;
+        if (piped) {
+            // the spectrum branch needs only the input, but it starts behind the front end: beside it, it slowed the
+            // kernel everything else waits for (0.67 ms per step against 0.61; RDSP_SPEC_WITH_FRONT=1 restores that order)
+            static const bool spec_with_front = [] { const char *e = getenv("RDSP_SPEC_WITH_FRONT"); return e && e[0] == '1'; }();
+            CK(cudaStreamWaitEvent(s_main, fe ? h->ev_front : h->ev_fork, 0));
+            CK(cudaStreamWaitEvent(s_spec, (fe && !spec_with_front) ? h->ev_front : h->ev_fork, 0));
+        }
+
+        if (has(h, RDSP_STAGE_SPEC256)) {
+            BiquadArgs b{};
+            b.iq = iq; b.out = h->d_hp_iq; b.state = h->d_bq_state; b.C = C; b.T = T; b.ch0 = c0; b.n = nc;
+            b.b0 = h->bq[0]; b.b1 = h->bq[1]; b.b2 = h->bq[2]; b.a1 = h->bq[3]; b.a2 = h->bq[4];
+            { Prof pr(h, KK_BIQUAD, s_spec); launch_biquad(b, s_spec); }
+            Spec256Args a{};
+            a.iq = h->d_hp_iq; a.prev = h->d_spec_prev; a.sum = h->d_spec_sum; a.output = h->d_spec_out;
+            a.C = C; a.T = T; a.ch0 = c0; a.n = nc; a.tick_in = tick_in; a.tick_out = tick_out; a.naverage = naverage;
+            a.div_shift = 32 + lgn;
+            a.div_magic = ((1ull << a.div_shift) + h->cfg.spec256_naverage - 1) / h->cfg.spec256_naverage;
+            a.tw = h->d_tw; a.win = h->d_win256;
+            { Prof pr(h, KK_SPEC256, s_spec); launch_spec256(a, s_spec); }
+        }
+
+        // the channels whose notch runs form their own chain on the side stream (when both classes exist)
+        int fn = 0, nn = 0, fp = 0, np = 0;
+        if (fe && notch) { sub(h->l_notch, c0, c1, fn, nn); sub(h->l_plain, c0, c1, fp, np); }
+        static const bool no_split = [] { const char *e = getenv("RDSP_NO_SPLIT"); return e && e[0] == '1'; }();   // experiments
+        const bool split = piped && fe && notch && nn > 0 && np > 0 && !no_split;
+        if (split) {
+            CK(cudaStreamWaitEvent(s_side, h->ev_front, 0));
+            int rc2 = run_chain(s_side, 2, c0, c1);
+            if (rc2 != RDSP_OK) return rc2;
+            rc2 = run_chain(s_main, 1, c0, c1);
+            if (rc2 != RDSP_OK) return rc2;
+            CK(cudaEventRecord(h->ev_group[g][2], s_side));
+            CK(cudaStreamWaitEvent(st, h->ev_group[g][2], 0));
+        } else {
+            const int rc2 = run_chain(s_main, 0, c0, c1);
+            if (rc2 != RDSP_OK) return rc2;
+        }
+        if (piped) {
+            // join: the call is complete on the handle's stream when every group has finished all of its streams
+            CK(cudaEventRecord(h->ev_group[g][0], s_main));
+            CK(cudaEventRecord(h->ev_group[g][1], s_spec));
+            CK(cudaStreamWaitEvent(st, h->ev_group[g][0], 0));
+            CK(cudaStreamWaitEvent(st, h->ev_group[g][1], 0));
+        }
+    }
+    if (piped && fe && front_last) CK(cudaStreamWaitEvent(st, h->ev_front, 0));
+    CK(cudaGetLastError());
+    return RDSP_OK;
+}
+
+// host mirror of the uniform counters (analyze_fft256iq.cpp:73-77,99-113; AudioAnalyzeFFT1024 frame cadence): which
+// read-outs became available, where the ping-pong buffers stand after the call
+void advance_host_state(rdsp_gpu *h, int T)
+{
+    const int naverage = (int)h->cfg.spec256_naverage;
+    if (has(h, RDSP_STAGE_SPEC256)) {
+        const int updates = T - (h->spec_have_prev ? 0 : 1);
+        h->spec_have_prev = 1;
+        const int total = h->spec_count + updates;
+        if (total / naverage > 0) std::fill(h->spec_ready.begin(), h->spec_ready.end(), (uint8_t)1);
+        h->spec_count = total % naverage;
+    }
+    if (has(h, RDSP_STAGE_SPEC1024)) {
+        int n_fft_frames = 0;
+        for (int t = 0; t < T; t++) {
+            const unsigned long long tk = h->tick + t;
+            if (tk >= 7 && ((tk - 7) & 3) == 0) n_fft_frames++;
+        }
+        if (n_fft_frames) std::fill(h->spec1024_ready.begin(), h->spec1024_ready.end(), (uint8_t)1);
+    }
+    h->tick += T;
+    h->tick_par ^= 1;
+    if (has(h, RDSP_STAGE_FRONTEND) && h->front_tc) h->fe_hist_cur ^= 1;
+}
+
+void drop_graphs(rdsp_gpu *h)
+{
+    for (auto &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+}
+
+// The device side of one call through the graph cache.  The sketch's calling pattern is one tick per 128 samples
+// (RadioDSP_SDR_RX.ino:198): about a dozen launches on three streams plus ~30 event calls for 130 us of GPU work.  A call
+// shape is captured the second time it is seen (same T, same buffers, same ping-pong phase, same tables) and replayed with
+// ONE cudaGraphLaunch from then on; the first sight runs the plain path (it also performs the one-time per-device kernel
+// attribute set-up, which must not happen inside a capture).
+int run_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStream_t st)
+{
+    const bool piped = !h->profiling;
+    const int fe_cur = h->fe_hist_cur, par = h->tick_par;
+    if (!h->use_graphs || h->profiling || h->timeline) return enqueue_call(h, T, iq, audio, st, piped, fe_cur, par);
+
+    GraphEntry *e = nullptr;
+    for (auto &g : h->graphs)
+        if (g.T == T && g.iq == iq && g.audio == audio && g.fe_cur == fe_cur && g.par == par && g.st == st) { e = &g; break; }
+    h->graph_clock++;
+    if (e && e->exec) {
+        e->last_use = h->graph_clock;
+        CK(cudaGraphLaunch(e->exec, st));
+        h->launches += e->launches;
+        h->graph_replays++;
+        return RDSP_OK;
+    }
+    if (!e) {
+        // first sight: remember the shape, run it plainly
+        if (h->graphs.size() >= rdsp_gpu::kMaxGraphs) {
+            size_t victim = 0;
+            for (size_t i = 1; i < h->graphs.size(); i++) if (h->graphs[i].last_use < h->graphs[victim].last_use) victim = i;
+            if (h->graphs[victim].exec) cudaGraphExecDestroy(h->graphs[victim].exec);
+            h->graphs.erase(h->graphs.begin() + (long)victim);
+        }
+        GraphEntry n{};
+        n.T = T; n.iq = iq; n.audio = audio; n.fe_cur = fe_cur; n.par = par; n.st = st; n.last_use = h->graph_clock;
+        h->graphs.push_back(n);
+        return enqueue_call(h, T, iq, audio, st, piped, fe_cur, par);
+    }
+    // second sight: capture, instantiate, launch
+    e->last_use = h->graph_clock;
+    const uint64_t l0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_call(h, T, iq, audio, st, piped, fe_cur, par);
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    const uint64_t n_launch = h->launches - l0;
+    h->launches = l0;
+    if (rc != RDSP_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc != RDSP_OK) return rc;
+        h->use_graphs = false;                                   // capture not possible here (e.g. a caller stream that is itself capturing)
+        drop_graphs(h);
+        return enqueue_call(h, T, iq, audio, st, piped, fe_cur, par);
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+        cudaGetLastError();
+        h->use_graphs = false;
+        drop_graphs(h);
+        return enqueue_call(h, T, iq, audio, st, piped, fe_cur, par);
+    }
+    e->exec = exec;
+    e->launches = n_launch;
+    CK(cudaGraphLaunch(exec, st));
+    h->launches += n_launch;
+    h->graph_replays++;
+    return RDSP_OK;
 }
 
 }  // namespace
@@ -449,6 +766,8 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     if (cfg->spec256_naverage == 0 || cfg->spec256_naverage > 255) { g_create_error = "spec256_naverage must be 1..255"; return RDSP_ERR_RANGE; }
     if (cfg->io_location > RDSP_IO_HOST) { g_create_error = "io_location invalid"; return RDSP_ERR_RANGE; }
     if (cfg->pipeline_chunks > (uint32_t)kMaxGroups) { g_create_error = "pipeline_chunks must be 0 (auto) .. 8"; return RDSP_ERR_RANGE; }
+    if (cfg->graph_mode > RDSP_GRAPH_OFF) { g_create_error = "graph_mode invalid"; return RDSP_ERR_RANGE; }
+    if (cfg->audio_layout > RDSP_AUDIO_MONO) { g_create_error = "audio_layout invalid"; return RDSP_ERR_RANGE; }
     if (!(cfg->agc_target > 0.f) || !(cfg->agc_max_gain > 0.f) || !(cfg->agc_attack_ms > 0.f)) { g_create_error = "AGC constants invalid"; return RDSP_ERR_RANGE; }
 
     int ndev = 0;
@@ -517,6 +836,9 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     h->spec1024_ready.assign(C, 0);
 
     CKC(dalloc(&h->d_par, C));
+    CKC(dalloc(&h->d_tick, (size_t)2));
+    h->use_graphs = cfg->graph_mode == RDSP_GRAPH_AUTO;
+    if (const char *e = getenv("RDSP_GRAPH")) h->use_graphs = e[0] != '0';
     CKC(dalloc(&h->d_taps, (size_t)15 * RDSP_TAPS_PAD));
     if (sm & RDSP_STAGE_FRONTEND) {
         CKC(dalloc(&h->d_fe_hist, C * 3 * RDSP_BLK));
@@ -628,6 +950,7 @@ void rdsp_gpu_destroy(rdsp_gpu_t *h)
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     prof_collect(h);
+    drop_graphs(h);
     free_all(h);
     delete h;
 }
@@ -667,6 +990,7 @@ int rdsp_gpu_set_stream(rdsp_gpu_t *h, void *cuda_stream)
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->stream));
     h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    drop_graphs(h);                                          // captured shapes belong to the stream they were captured on
     return RDSP_OK;
 }
 
@@ -693,9 +1017,7 @@ int rdsp_gpu_stream_join(rdsp_gpu_t *h)
 int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_in, int16_t *audio_out)
 {
     if (!h || !iq_in) return RDSP_ERR_INVALID;
-    const bool fe = has(h, RDSP_STAGE_FRONTEND), notch = has(h, RDSP_STAGE_NOTCH), agc = has(h, RDSP_STAGE_AGC);
-    const bool ff = has(h, RDSP_STAGE_FFTFILT), nr = has(h, RDSP_STAGE_NR);
-    const bool audio_path = fe || ff;
+    const bool audio_path = has(h, RDSP_STAGE_FRONTEND) || has(h, RDSP_STAGE_FFTFILT);
     if (audio_path && !audio_out) { h->err = "audio_out is NULL"; return RDSP_ERR_INVALID; }
     if (n_blocks == 0) return RDSP_OK;
     if (n_blocks > (uint32_t)h->maxT) { h->err = "n_blocks exceeds max_blocks_per_call"; return RDSP_ERR_RANGE; }
@@ -722,207 +1044,9 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
         audio = h->d_out_stage2[hb];
     }
 
-    // ---- channel groups -----------------------------------------------------------------------------------
-    // Channels are independent, and every kernel after the front end is bound by the latency of a per-channel
-    // recurrence rather than by throughput.  The call is therefore cut ACROSS channels: the front end takes all
-    // channels in one launch (tiles x time segments fill the SMs), then G channel groups walk the rest of the graph
-    // on streams of their own — notch -> AGC -> FFT filter -> DNR -> audio spectrum on one, high-pass -> IQ spectrum
-    // on another — with no dependency between groups, so the hardware overlaps G latency-bound chains.  Every launch
-    // still covers all T blocks of the call: state makes one round trip and the launch latency is paid once.
-    // (The first version cut the call along TIME instead; its timeline, tools/diag_timeline.py, showed every stage
-    // paying its launch + state latency per chunk and the DNR stage of 4 chunks taking twice its one-launch time.)
-    // While per-kernel profiling is on, everything runs as one group on one stream so that each kernel's time is its own.
-    const bool piped = !h->profiling;
-    int G = 1;
-    if (piped) {
-        // measured (cfg5, 8192 channels, T = 8): 1 group 0.71 ms, 2 groups 0.90, 4 groups 0.83, 8 groups 1.11 — small
-        // concurrent launches of the same kernel slow each other more than they overlap, so the default is ONE group
-        // (main chain + spectrum branch + the AGC of the channels that bypass the notch on three streams)
-        G = h->cfg.pipeline_chunks ? (int)h->cfg.pipeline_chunks : 1;
-        if (G > kMaxGroups) G = kMaxGroups;
-        while (G > 1 && C / G < 256) G--;
-        CK(cudaEventRecord(h->ev_fork, st));                             // the input (and earlier calls) are in place
-    }
-    cudaStream_t s_front = piped ? h->stage_stream[3 * kMaxGroups] : st;
-    const int naverage = (int)h->cfg.spec256_naverage;
-    int lgn = 0; while ((1u << lgn) < h->cfg.spec256_naverage) lgn++;
-    float *dbg = h->d_dbg;
-
-    // ---- K0+K1+K2, all channels
-    bool front_last = false;
-    if (fe) {
-        if (piped) CK(cudaStreamWaitEvent(s_front, h->ev_fork, 0));
-        front_last = !(notch || agc || ff);
-        FrontArgs a{};
-        a.iq = iq; a.out_mono = front_last ? nullptr : h->d_mid_a; a.out_stereo = front_last ? audio : nullptr;
-        a.dbg = front_last ? dbg : nullptr; a.par = h->d_par; a.taps = h->d_taps; a.C = C; a.T = T;
-        Prof pr(h, KK_FRONT, s_front);
-        if (h->front_tc) {
-            a.hist = h->fe_hist_cur ? h->d_fe_hist2 : h->d_fe_hist;
-            a.hist_out = h->fe_hist_cur ? h->d_fe_hist : h->d_fe_hist2;
-            h->fe_hist_cur ^= 1;
-            FrontTcTables tb{};
-            tb.tile_ch = h->d_tile_ch; tb.tile_rows = h->d_tile_rows; tb.toep = h->d_toep; tb.n_tiles = h->n_tiles;
-            tb.any_sam = h->any_sam; tb.sam_tiles = h->sam_tiles;
-            a.sam_state = h->d_sam_state; a.nb_ref = h->d_nb_ref;
-            launch_front_tc(a, tb, s_front);
-        } else {
-            if (h->any_sam) { h->err = "SAM and the noise blanker are only built in the tensor-core front end (unset RDSP_FRONT_IMPL)"; return RDSP_ERR_STATE; }
-            a.hist = h->fe_hist_cur ? h->d_fe_hist2 : h->d_fe_hist;
-            launch_front(a, s_front);
-        }
-    }
-    if (piped && fe) CK(cudaEventRecord(h->ev_front, s_front));
-
-    // sub-range of a sorted channel list that falls into [c0, c1)
-    auto sub = [](const std::vector<int> &l, int c0, int c1, int &first, int &count) {
-        first = (int)(std::lower_bound(l.begin(), l.end(), c0) - l.begin());
-        count = (int)(std::lower_bound(l.begin(), l.end(), c1) - l.begin()) - first;
-    };
-    int n_fft_frames = 0;
-    for (int t = 0; t < T; t++) {
-        const unsigned long long tk = h->tick + t;
-        if (tk >= 7 && ((tk - 7) & 3) == 0) n_fft_frames++;
-    }
-
-    // one chain of the audio graph on stream `cs` for the channels [c0, c1) of class `cls`:
-    //   0 = every channel (no split), 1 = the channels that bypass the notch, 2 = the channels whose notch runs.
-    // With classes 1 and 2 on two streams the latency-bound notch -> AGC -> ... chain of the (few) notched channels runs
-    // beside the wide kernels of the others instead of in front of them.
-    // the spectrum branches keep the issue slots contended while the NLMS kernels run (k_nlms.cu, launch_nlms)
-    const int nlms_packed = (has(h, RDSP_STAGE_SPEC256) || has(h, RDSP_STAGE_SPEC1024)) ? 1 : 0;
-    auto run_chain = [&](cudaStream_t cs, int cls, int c0, int c1) -> int {
-        const int nc = c1 - c0;
-        int f_notch = 0, n_notch = 0, f_plain = 0, n_plain = 0;
-        if (notch) { sub(h->l_notch, c0, c1, f_notch, n_notch); sub(h->l_plain, c0, c1, f_plain, n_plain); }
-        const int *cls_list = cls == 1 ? h->d_list_plain + f_plain : (cls == 2 ? h->d_list_notch + f_notch : nullptr);
-        const int cls_n = cls == 1 ? n_plain : (cls == 2 ? n_notch : nc);
-        if (cls_n <= 0) return RDSP_OK;
-        const int16_t *mono = nullptr;
-        if (fe) {
-            mono = h->d_mid_a;
-            if (notch || agc) {
-                AgcArgs ag{};
-                ag.out_mono = ff ? h->d_mid_b : nullptr; ag.out_stereo = ff ? nullptr : audio;
-                ag.dbg = ff ? nullptr : dbg; ag.env = h->d_agc_env; ag.par = h->d_par; ag.C = C; ag.T = T;
-                ag.agc_stage = agc ? 1 : 0;
-                ag.target = h->cfg.agc_target; ag.max_gain = h->cfg.agc_max_gain; ag.alpha_a = h->agc_alpha_a;
-                if (cls != 2) {
-                    // channels that bypass the notch read the front end's q15 rows ...
-                    ag.list = notch ? h->d_list_plain + f_plain : nullptr; ag.n_list = notch ? n_plain : nc; ag.ch0 = c0;
-                    ag.in_q15 = h->d_mid_a; ag.in_f32 = nullptr;
-                    if (ag.n_list > 0) { Prof pr(h, KK_AGC, cs); launch_agc(ag, cs); }
-                }
-                if (cls != 1 && notch && n_notch > 0) {
-                    NlmsArgs n{};
-                    n.list = h->d_list_notch + f_notch; n.n_list = n_notch; n.C = C; n.T = T;
-                    n.in_q15 = h->d_mid_a; n.out_f32 = h->d_scr;
-                    n.coeff = h->d_nc_coeff; n.prev = h->d_nc_prev; n.energy = h->d_nc_energy; n.first = h->d_nc_first;
-                    n.par = h->d_par; n.mode = 0; n.packed = nlms_packed; n.direct = h->nlms_direct;
-                    { Prof pr(h, KK_NOTCH, cs); launch_nlms(n, cs); }
-                    // ... the others read the notch's f32 error signal
-                    ag.list = h->d_list_notch + f_notch; ag.n_list = n_notch; ag.in_q15 = nullptr; ag.in_f32 = h->d_scr;
-                    { Prof pr(h, KK_AGC, cs); launch_agc(ag, cs); }
-                }
-                mono = h->d_mid_b;
-            }
-        }
-        if (ff) {
-            FftFiltArgs f{};
-            f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq; f.out_stereo = audio; f.out_f32_L = h->d_scr;
-            f.dbg = dbg; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256; f.sin512 = h->d_sin512;
-            f.par = h->d_par; f.C = C; f.T = T; f.list = cls_list; f.ch0 = c0; f.n = cls_n; f.nr_stage = nr ? 1 : 0;
-            { Prof pr(h, KK_FFTFILT, cs); launch_fftfilt(f, cs); }
-            if (nr) {
-                const std::vector<int> &ld = cls == 1 ? h->l_dnr_p : (cls == 2 ? h->l_dnr_n : h->l_dnr);
-                const int *dl = cls == 1 ? h->d_list_dnr_p : (cls == 2 ? h->d_list_dnr_n : h->d_list_dnr);
-                int f_dnr = 0, n_dnr = 0;
-                sub(ld, c0, c1, f_dnr, n_dnr);
-                if (n_dnr > 0) {
-                    NlmsArgs n{};
-                    n.list = dl + f_dnr; n.n_list = n_dnr; n.C = C; n.T = T;
-                    n.in_f32 = h->d_scr; n.out_stereo = audio; n.dbg = dbg;
-                    n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
-                    n.par = h->d_par; n.mode = 1; n.packed = nlms_packed; n.direct = h->nlms_direct;
-                    { Prof pr(h, KK_DNR, cs); launch_nlms(n, cs); }
-                }
-            }
-        }
-        if (has(h, RDSP_STAGE_SPEC1024)) {
-            Spec1024Args s1{};
-            s1.audio = audio; s1.ring = h->d_ring; s1.output = h->d_spec1024_out; s1.C = C; s1.T = T;
-            s1.list = cls_list; s1.ch0 = c0; s1.n = cls_n;
-            s1.tick0 = h->tick; s1.tw = h->d_tw; s1.win = h->d_win1024;
-            s1.any_fft = n_fft_frames > 0;
-            { Prof pr(h, KK_SPEC1024, cs); launch_spec1024(s1, cs); }
-        }
-        return RDSP_OK;
-    };
-
-    for (int g = 0; g < G; g++) {
-        const int c0 = (int)((long long)C * g / G), c1 = (int)((long long)C * (g + 1) / G), nc = c1 - c0;
-        cudaStream_t s_main = piped ? h->stage_stream[g] : st;
-        cudaStream_t s_spec = piped ? h->stage_stream[kMaxGroups + g] : st;
-        cudaStream_t s_side = piped ? h->stage_stream[2 * kMaxGroups + g] : st;
-        if (piped) {
-            // the spectrum branch needs only the input, but it starts behind the front end: beside it, it slowed the
-            // kernel everything else waits for (0.67 ms per step against 0.61; RDSP_SPEC_WITH_FRONT=1 restores that order)
-            static const bool spec_with_front = [] { const char *e = getenv("RDSP_SPEC_WITH_FRONT"); return e && e[0] == '1'; }();
-            CK(cudaStreamWaitEvent(s_main, fe ? h->ev_front : h->ev_fork, 0));
-            CK(cudaStreamWaitEvent(s_spec, (fe && !spec_with_front) ? h->ev_front : h->ev_fork, 0));
-        }
-
-        if (has(h, RDSP_STAGE_SPEC256)) {
-            BiquadArgs b{};
-            b.iq = iq; b.out = h->d_hp_iq; b.state = h->d_bq_state; b.C = C; b.T = T; b.ch0 = c0; b.n = nc;
-            b.b0 = h->bq[0]; b.b1 = h->bq[1]; b.b2 = h->bq[2]; b.a1 = h->bq[3]; b.a2 = h->bq[4];
-            { Prof pr(h, KK_BIQUAD, s_spec); launch_biquad(b, s_spec); }
-            Spec256Args a{};
-            a.iq = h->d_hp_iq; a.prev = h->d_spec_prev; a.sum = h->d_spec_sum; a.output = h->d_spec_out;
-            a.C = C; a.T = T; a.ch0 = c0; a.n = nc; a.have_prev = h->spec_have_prev; a.count = h->spec_count; a.naverage = naverage;
-            a.div_shift = 32 + lgn;
-            a.div_magic = ((1ull << a.div_shift) + h->cfg.spec256_naverage - 1) / h->cfg.spec256_naverage;
-            a.tw = h->d_tw; a.win = h->d_win256;
-            { Prof pr(h, KK_SPEC256, s_spec); launch_spec256(a, s_spec); }
-        }
-
-        // the channels whose notch runs form their own chain on the side stream (when both classes exist)
-        int fn = 0, nn = 0, fp = 0, np = 0;
-        if (fe && notch) { sub(h->l_notch, c0, c1, fn, nn); sub(h->l_plain, c0, c1, fp, np); }
-        static const bool no_split = [] { const char *e = getenv("RDSP_NO_SPLIT"); return e && e[0] == '1'; }();   // experiments
-        const bool split = piped && fe && notch && nn > 0 && np > 0 && !no_split;
-        if (split) {
-            CK(cudaStreamWaitEvent(s_side, h->ev_front, 0));
-            int rc2 = run_chain(s_side, 2, c0, c1);
-            if (rc2 != RDSP_OK) return rc2;
-            rc2 = run_chain(s_main, 1, c0, c1);
-            if (rc2 != RDSP_OK) return rc2;
-            CK(cudaEventRecord(h->ev_group[g][2], s_side));
-            CK(cudaStreamWaitEvent(st, h->ev_group[g][2], 0));
-        } else {
-            const int rc2 = run_chain(s_main, 0, c0, c1);
-            if (rc2 != RDSP_OK) return rc2;
-        }
-        if (piped) {
-            // join: the call is complete on the handle's stream when every group has finished all of its streams
-            CK(cudaEventRecord(h->ev_group[g][0], s_main));
-            CK(cudaEventRecord(h->ev_group[g][1], s_spec));
-            CK(cudaStreamWaitEvent(st, h->ev_group[g][0], 0));
-            CK(cudaStreamWaitEvent(st, h->ev_group[g][1], 0));
-        }
-    }
-    // host mirror of the uniform counters (analyze_fft256iq.cpp:73-77,99-113; AudioAnalyzeFFT1024 frame cadence)
-    if (has(h, RDSP_STAGE_SPEC256)) {
-        const int updates = T - (h->spec_have_prev ? 0 : 1);
-        h->spec_have_prev = 1;
-        const int total = h->spec_count + updates;
-        if (total / naverage > 0) std::fill(h->spec_ready.begin(), h->spec_ready.end(), (uint8_t)1);
-        h->spec_count = total % naverage;
-    }
-    if (has(h, RDSP_STAGE_SPEC1024) && n_fft_frames) std::fill(h->spec1024_ready.begin(), h->spec1024_ready.end(), (uint8_t)1);
-    h->tick += T;
-    if (piped && fe && front_last) CK(cudaStreamWaitEvent(st, h->ev_front, 0));
-    CK(cudaGetLastError());
+    rc = run_call(h, T, iq, audio, st);
+    if (rc != RDSP_OK) return rc;
+    advance_host_state(h, T);
 
     if (host_io) {
         CK(cudaEventRecord(h->ev_comp[hb], st));
@@ -1107,6 +1231,7 @@ int rdsp_gpu_read_debug_f32(rdsp_gpu_t *h, uint32_t n_blocks, uint32_t ch_first,
 }
 
 uint64_t rdsp_gpu_kernel_launches(const rdsp_gpu_t *h) { return h ? h->launches : 0; }
+uint64_t rdsp_gpu_graph_replays(const rdsp_gpu_t *h) { return h ? h->graph_replays : 0; }
 
 int rdsp_gpu_profile(rdsp_gpu_t *h, int enable)
 {

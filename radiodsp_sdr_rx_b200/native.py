@@ -18,6 +18,8 @@ NR_OFF, NR_LMS, NR_SPECTRAL = range(3)
 STAGE_FRONTEND, STAGE_NOTCH, STAGE_AGC, STAGE_FFTFILT, STAGE_NR, STAGE_SPEC256, STAGE_SPEC1024 = (1 << i for i in range(7))
 STAGE_ALL = 0x7F
 IO_DEVICE, IO_HOST = 0, 1
+AUDIO_STEREO, AUDIO_MONO = 0, 1
+GRAPH_AUTO, GRAPH_OFF = 0, 1
 TAPS_HILBERT_I, TAPS_HILBERT_Q, TAPS_BANDPASS = range(3)
 
 #: every symbol include/rdsp_gpu.h declares (tests check that the library exports all of them)
@@ -26,7 +28,7 @@ ABI_SYMBOLS = [
     "rdsp_gpu_set_mode", "rdsp_gpu_get_mode", "rdsp_gpu_process_block", "rdsp_gpu_process_blocks",
     "rdsp_gpu_synchronize", "rdsp_gpu_stream_join", "rdsp_gpu_set_stream", "rdsp_gpu_read_spectrum", "rdsp_gpu_read_audio_spectrum",
     "rdsp_gpu_read_panadapter", "rdsp_gpu_read_waterfall", "rdsp_gpu_set_taps", "rdsp_gpu_get_taps", "rdsp_gpu_design_bandpass", "rdsp_gpu_set_mask", "rdsp_gpu_get_mask",
-    "rdsp_gpu_read_debug_f32", "rdsp_gpu_kernel_launches", "rdsp_gpu_profile", "rdsp_gpu_profile_read",
+    "rdsp_gpu_read_debug_f32", "rdsp_gpu_kernel_launches", "rdsp_gpu_graph_replays", "rdsp_gpu_profile", "rdsp_gpu_profile_read",
     "rdsp_gpu_last_error", "rdsp_gpu_version",
 ]
 
@@ -44,6 +46,7 @@ class Config(C.Structure):
         ("async_", C.c_uint32), ("debug_f32", C.c_uint32), ("spec256_naverage", C.c_uint32),
         ("agc_target", C.c_float), ("agc_max_gain", C.c_float), ("agc_attack_ms", C.c_float),
         ("agc_decay_ms", C.c_float * 4), ("pipeline_chunks", C.c_uint32),
+        ("audio_layout", C.c_uint32), ("graph_mode", C.c_uint32),
     ]
 
 
@@ -98,6 +101,8 @@ def lib():
         L.rdsp_gpu_read_debug_f32.argtypes = [vp, u32, u32, u32, vp]
         L.rdsp_gpu_kernel_launches.argtypes = [vp]
         L.rdsp_gpu_kernel_launches.restype = C.c_uint64
+        L.rdsp_gpu_graph_replays.argtypes = [vp]
+        L.rdsp_gpu_graph_replays.restype = C.c_uint64
         L.rdsp_gpu_profile.argtypes = [vp, i32]
         L.rdsp_gpu_profile_read.argtypes = [vp, i32, vp, vp, vp]
         L.rdsp_gpu_last_error.argtypes = [vp]
@@ -266,6 +271,10 @@ class ReceiverBank:
     @property
     def kernel_launches(self) -> int:
         return int(lib().rdsp_gpu_kernel_launches(self._h))
+
+    @property
+    def graph_replays(self) -> int:
+        return int(lib().rdsp_gpu_graph_replays(self._h))
 
     def profile(self, enable: bool):
         self._ck(lib().rdsp_gpu_profile(self._h, 1 if enable else 0))

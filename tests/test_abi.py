@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(rd):
 
 def test_struct_layouts_match_header(rd):
     from radiodsp_sdr_rx_b200 import native
-    assert C.sizeof(native.Config) == 68 and C.sizeof(native.Params) == 60
+    assert C.sizeof(native.Config) == 76 and C.sizeof(native.Params) == 60
     cfg = rd.default_config()
     assert cfg.struct_size == C.sizeof(native.Config)
     assert (cfg.n_channels, cfg.stage_mask, cfg.spec256_naverage) == (1, rd.STAGE_ALL, 30)

@@ -510,9 +510,17 @@ def test_extreme_inputs(rd, po):
     # the stages in front of the collapse are unaffected: bit-exact / 1 LSB ...
     g2, _, o2, _, _, _ = run_both(rd, po, rd.STAGE_FRONTEND | rd.STAGE_NOTCH | rd.STAGE_AGC, params, iq, blocks_per_call=3)
     assert np.abs(g2.astype(np.int32) - o2).max() <= 1
-    # ... and so are K5 + K6 on identical inputs (the audio K4 produced) outside the collapse window
-    g3, _, o3, _, _, _ = run_both(rd, po, rd.STAGE_FFTFILT | rd.STAGE_NR, params, g2, blocks_per_call=3)
-    assert np.abs(g3.astype(np.int32) - o3)[keep].max() <= 1
+    # ... and so are K5, and K6 on identical inputs (the oracle's NLMS on the signal the GPU's K5 produced), outside the
+    # collapse window
+    g5, g5f, o5, _, _, _ = run_both(rd, po, rd.STAGE_FFTFILT, params, g2, blocks_per_call=3)
+    assert np.abs(g5.astype(np.int32) - o5).max() <= 1
+    g6, _, _, _, _, _ = run_both(rd, po, rd.STAGE_FFTFILT | rd.STAGE_NR, params, g2, blocks_per_call=3)
+    for c in range(4):
+        ch = po.OracleChan(po.default_config(stage_mask=po.STAGE_FFTFILT | po.STAGE_NR), params[c])
+        want = np.zeros((nb, 128), np.int16)
+        y = ch.dnr_f32(g5f[:, c, :, 0])
+        po.lib().arm_float_to_q15(y.ctypes.data, want.ctypes.data, y.size)
+        assert np.abs(g6[:, c, :, 0].astype(np.int32) - want)[keep].max() <= 1, c
 
 
 def test_level_collapse_with_a_noise_floor(rd, po):
@@ -636,3 +644,33 @@ def test_two_devices_in_one_process(rd, po):
             bank.set_mode(c, 1, rd.default_params(**bench.channel_params("cfg5", c)))
         outs.append(bank.process_host(iq))
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("T", [1, 8])
+def test_graph_replay_is_bit_identical(rd, po, T):
+    """A call shape seen twice is captured into a CUDA graph and replayed with one launch (rdsp_gpu.cu, run_call): same
+    bits as the kernel-by-kernel path — audio, both spectra, state carried over 40+ ticks, a parameter change in the middle
+    (tables change => the captured shapes are dropped and rebuilt)."""
+    import torch
+    nc, nb = 300, 48
+    iq = bench.make_inputs("cfg5", 0, nc, nb)
+    res = []
+    for mode in (rd.GRAPH_AUTO, rd.GRAPH_OFF):
+        cfg = rd.default_config(n_channels=nc, stage_mask=rd.STAGE_ALL, max_blocks_per_call=T, io_location=rd.IO_DEVICE, graph_mode=mode)
+        bank = rd.ReceiverBank(cfg)
+        for c in range(nc):
+            bank.set_mode(c, 1, rd.default_params(**bench.channel_params("cfg5", c)))
+        d_in = [torch.empty((T, nc, 128, 2), dtype=torch.int16, device="cuda") for _ in range(2)]   # two rotating input buffers
+        d_out = torch.zeros((T, nc, 128, 2), dtype=torch.int16, device="cuda")
+        outs = []
+        for k, b0 in enumerate(range(0, nb, T)):
+            if b0 == nb // 2:
+                bank.set_mode(5, 7, rd.default_params(demod=rd.DEMOD_USB, nr_kind=rd.NR_LMS, nr_level=40, notch_on=1))
+            d_in[k % 2].copy_(torch.from_numpy(iq[b0:b0 + T]))
+            bank.process_blocks(T, d_in[k % 2], d_out)
+            outs.append(d_out.cpu().numpy().copy())
+        res.append((np.concatenate(outs), bank.read_spectrum()[0], bank.read_audio_spectrum()[0], bank.graph_replays, bank.kernel_launches))
+    (a_out, a_s, a_as, a_rep, a_l), (b_out, b_s, b_as, b_rep, b_l) = res
+    assert np.array_equal(a_out, b_out) and np.array_equal(a_s, b_s) and np.array_equal(a_as, b_as)
+    assert b_rep == 0 and a_rep >= nb // T - 12, (a_rep, b_rep)      # 2 buffers x 2 phases, seen + captured, twice (tables changed once)
+    assert a_l == b_l                                                 # a replay accounts for the kernels it runs

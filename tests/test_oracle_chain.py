@@ -215,3 +215,20 @@ def test_waterfall_history(po):
         assert np.array_equal(rows[r], lines[3 - r])
     assert not rows[4:].any()
     assert col.max() <= 6 and ((rows >= 75) == (col == 6)).all() and ((rows < 5) == (col == 0)).all()
+
+
+def test_dnr_hook_equals_the_chain(po):
+    """rdsp_oracle_chan_dnr_f32 (K6 alone, used by the GPU tests to hand both sides identical inputs) is the DNR branch of
+    the chain: K5-only output pushed through it == the K5+K6 chain, bit for bit, through a level change"""
+    from radiodsp_sdr_rx_b200 import synth
+    iq = synth.synth_iq([3], 24, [0])[:, 0]
+    k5 = po.OracleChan(po.default_config(stage_mask=po.STAGE_FFTFILT))
+    _, f5 = k5.process(iq, True)
+    full = po.OracleChan(po.default_config(stage_mask=po.STAGE_FFTFILT | po.STAGE_NR))
+    hook = po.OracleChan(po.default_config(stage_mask=po.STAGE_FFTFILT | po.STAGE_NR))
+    for b0, lvl in ((0, 30), (12, 50)):
+        p = po.default_params(nr_kind=po.NR_LMS, nr_level=lvl)
+        full.set_mode(p); hook.set_mode(p)
+        _, f6 = full.process(iq[b0:b0 + 12], True)
+        y = hook.dnr_f32(f5[b0:b0 + 12, :, 0])
+        assert np.array_equal(y, f6[..., 0]) and np.array_equal(f6[..., 0], f6[..., 1])
