@@ -219,31 +219,19 @@ def max_over_ranks(ms: float, dist=None, device=None) -> float:
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_chain(workload: str, n_threads: int, ch_per_thread: int, n_blocks: int, reps: int = 1):
-    """The CPU oracle port on `n_threads` host threads (ctypes releases the GIL); returns (MS/s, seconds)."""
+def _timing_oracle():
+    """pyoracle bound to a build of the CPU port for THIS host: oracle/liboracle_native.so (-O3 -march=native, built here on
+    first use) — parity tests keep the portable x86-64-v3 build.  Returns (module, build name)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    native = os.path.join(ROOT, "oracle", "liboracle_native.so")
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "native"], capture_output=True, text=True)
+    name = "-O3 -march=native"
+    if r.returncode == 0 and os.path.exists(native):
+        os.environ["RDSP_ORACLE_LIB"] = native
+    else:
+        name = "-O3 -march=x86-64-v3 (native build failed)"
     import pyoracle as po
-    stage = WORKLOADS[workload][1]
-    nc = n_threads * ch_per_thread
-    iq = make_inputs(workload, 0, nc, n_blocks, unique=min(nc, 64))
-    out = np.zeros_like(iq)
-    cfg = po.default_config(stage_mask=stage)
-    chans = [po.OracleChan(cfg, po.default_params(**channel_params(workload, c))) for c in range(nc)]
-    arr = (C.c_void_p * nc)(*[c.handle for c in chans])
-    L = po.lib()
-
-    def work(i):
-        for _ in range(reps):
-            L.rdsp_oracle_bank_process(arr, i * ch_per_thread, ch_per_thread, nc, n_blocks, iq.ctypes.data, out.ctypes.data)
-
-    th = [threading.Thread(target=work, args=(i,)) for i in range(n_threads)]
-    t0 = time.perf_counter()
-    for t in th:
-        t.start()
-    for t in th:
-        t.join()
-    dt = time.perf_counter() - t0
-    return nc * n_blocks * reps * BLK / dt / 1e6, dt
+    return po, name
 
 
 def host_cores() -> int:
@@ -253,34 +241,100 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def cpu_chain(workload: str, n_channels: int, T: int, n_steps: int, n_warm: int = 1):
+    """The CPU oracle port on ALL host threads, the GPU arm's own shape: every step is one pass of `T` blocks over
+    `n_channels` channels (contiguous channel ranges per thread, ctypes releases the GIL; the state of all channels is
+    live, so it does not sit in L1 / L2 the way a one-channel loop would).  Returns (ms per step list, build name, cores)."""
+    po, build = _timing_oracle()
+    stage = WORKLOADS[workload][1]
+    iq = make_inputs(workload, 0, n_channels, T)
+    out = np.zeros_like(iq)
+    cfg = po.default_config(stage_mask=stage)
+    chans = [po.OracleChan(cfg, po.default_params(**channel_params(workload, c))) for c in range(n_channels)]
+    arr = (C.c_void_p * n_channels)(*[c.handle for c in chans])
+    L = po.lib()
+    cores = host_cores()
+    bounds = [n_channels * i // cores for i in range(cores + 1)]
+
+    def work(i):
+        if bounds[i + 1] > bounds[i]:
+            L.rdsp_oracle_bank_process(arr, bounds[i], bounds[i + 1] - bounds[i], n_channels, T, iq.ctypes.data, out.ctypes.data)
+
+    ms = []
+    for k in range(n_warm + n_steps):
+        th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if k >= n_warm:
+            ms.append((time.perf_counter() - t0) * 1e3)
+    return ms, build, cores
+
+
+def cpu_reference_stages(n_blocks: int = 2048):
+    """kind "reference": the stages whose sources ARE in the reference tree — doConvolutionalProcessing (K5 + K6 + K7, DNR
+    level 30) and AudioAnalyzeFFT256IQ::update (K9) — compiled unmodified (oracle/_ref, built in the build container: the
+    reference tree does not travel), one private copy of the library per host thread because its state is file-scope
+    globals.  Returns a cpu_baseline-style dict, or None when oracle/_ref is absent."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    if not po.ref_available():
+        return None
+    from radiodsp_sdr_rx_b200 import synth
+    cores = host_cores()
+    iq = synth.synth_iq(np.arange(cores), n_blocks, 0)
+    refs = [po.RefChannel() for _ in range(cores)]
+    ins = [np.ascontiguousarray(iq[:, i]) for i in range(cores)]
+    for r, x in zip(refs, ins):
+        r.run_blocks(x[:64], 30)                                  # warm the pages
+    th = [threading.Thread(target=r.run_blocks, args=(x, 30)) for r, x in zip(refs, ins)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    return {"value": cores * n_blocks * BLK / dt / 1e6, "unit": "MS/s", "cores": cores, "kind": "reference",
+            "stages": "K5 + K6 (DNR level 30) + K7 + K9 only: the stages whose sources are in the reference tree (AudioSDR is not)",
+            "sample": f"{cores} threads x 1 channel x {n_blocks} blocks ({dt:.1f} s), reference sources compiled unmodified "
+                      "(-O3 -march=x86-64-v3, built where /root/reference exists)"}
+
+
+def workload_config(wl: str, C_: int, world: int, T: int) -> dict:
+    """what both arms (this framework and --impl reference) are measured on: identical in both JSON lines"""
+    return {"workload": f"{wl}: {WORKLOADS[wl][0]}", "channels_per_gpu": C_, "channels_total": world * C_, "blocks_per_call": T,
+            "block_samples": BLK, "sample_rate_hz": FS, "sharding": "contiguous channel ranges, no collective on the hot path",
+            "l2": "GPU arm: 256 MiB memset between timed steps; per-step CUDA events summed"}
+
+
 def run_reference(args):
-    """--impl reference: the reference chain on the host cores (CPU oracle port; its in-tree stages are pinned
-    bit-exact to the reference's own sources compiled unmodified, oracle/_ref).  Rank 0 only."""
+    """--impl reference: the reference chain on the host cores, on the GPU arm's own config — every step is one pass of
+    blocks_per_call blocks over ALL channels_total channels (CPU oracle port; its in-tree stages are pinned bit-exact to the
+    reference's own sources compiled unmodified, oracle/_ref; AudioSDR does not exist in the reference tree, so the whole
+    chain cannot be kind "reference").  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = args.workload
-    cores = host_cores()
+    world = max(1, args.gpus)
     T = args.blocks_per_call
-    cpt = max(1, args.cpu_channels_per_thread)
-    nbc = args.cpu_blocks
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_chain(wl, cores, cpt, nbc)
-    vals, secs = [], []
-    for _ in range(args.steps):
-        v, dt = cpu_chain(wl, cores, cpt, nbc, reps=1)
-        vals.append(v); secs.append(dt)
-    v = float(np.mean(vals))
     C_ = args.channels or WORKLOADS[wl][2]
+    ms, build, cores = cpu_chain(wl, world * C_, T, args.steps, n_warm=max(1, min(args.warmup, 2)))
+    samples = world * C_ * T * BLK
+    v = samples * len(ms) / (sum(ms) * 1e-3) / 1e6
     line = {
         "impl": "reference", "metric": "aggregate MS/s (real-time 44.1 kS/s channels sustained = value / 0.0441)",
         "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "q15+f32", "data": "synthetic",
-        "config": {"workload": f"{wl}: {WORKLOADS[wl][0]}", "channels_per_gpu": C_, "blocks_per_call": T,
-                   "realtime_channels": v / 0.0441},
+        "config": workload_config(wl, C_, world, T),
+        "derived": {"realtime_channels": v / 0.0441},
         "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": "port",
-                         "sample": f"per step: {cores} threads x {cpt} channels x {nbc} blocks of the {wl} chain"},
+                         "sample": f"every step: {cores} threads x {world * C_} channels x {T} blocks of the {wl} chain (the GPU arm's step); "
+                                   f"oracle port built {build}"},
+        "cpu_baseline_reference": cpu_reference_stages(),
         "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

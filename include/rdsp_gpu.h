@@ -191,7 +191,7 @@ int  rdsp_gpu_get_mode(rdsp_gpu_t *h, uint32_t ch, rdsp_chan_params_t *p);
 
 /* One update() tick for every channel.
  *   iq_in     [n_channels][128][2] int16  (I,Q interleaved = I2S frame order)
- *   audio_out [n_channels][128][2] int16  (L,R interleaved)
+ *   audio_out [n_channels][128][2] int16  (L,R interleaved); [n_channels][128] (L) with cfg.audio_layout = RDSP_AUDIO_MONO
  * Both 16-byte aligned, on the device or on the host per cfg.io_location. */
 int  rdsp_gpu_process_block(rdsp_gpu_t *h, const int16_t *iq_in, int16_t *audio_out);
 

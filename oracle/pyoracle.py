@@ -281,6 +281,7 @@ class RefChannel:
         L.ref_lms_coeffs.argtypes = [C.c_void_p]
         L.ref_fft256_update.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_fft256_output.argtypes = [C.c_void_p]
+        L.ref_run_blocks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         self.L = L
         L.ref_setup(naverage)
 
@@ -322,6 +323,14 @@ class RefChannel:
             assert got == 1
             self.L.ref_conv_float_out(_ptr(fL[k]), _ptr(fR[k]))
         return outL, outR, fL, fR
+
+    def run_blocks(self, iq: np.ndarray, nr_level: int, with_fft: bool = True):
+        """iq int16 [n_blocks,128,2] -> audio [n_blocks,128,2]: the in-tree stages (K5+K6+K7, K9) in one C loop (bench timing)"""
+        iq = np.ascontiguousarray(iq, np.int16)
+        out = np.zeros_like(iq)
+        played = self.L.ref_run_blocks(iq.shape[0], _ptr(iq), _ptr(out), int(nr_level), int(with_fft))
+        assert played == iq.shape[0]
+        return out
 
     def lms_mu(self):
         return float(self.L.ref_lms_mu())

@@ -83,4 +83,30 @@ int ref_fft256_update(const int16_t *I, const int16_t *Q)
 }
 void ref_fft256_output(uint16_t *out) { memcpy(out, g_fft->output, sizeof(g_fft->output)); }
 
+/* Timing loop for bench.py's "reference"-kind CPU baseline: n_blocks ticks of the stages whose sources are in the reference
+ * tree — doConvolutionalProcessing (K5 + K6 + K7) in loop() and, with_fft, AudioAnalyzeFFT256IQ::update (K9) — on
+ * iq [n_blocks][128][2], audio [n_blocks][128][2].  Same call order as ref_conv_push / ref_conv_loop above (the gate at
+ * RDSP_convolutional.h:231 needs one block of look-ahead).  Returns the number of blocks played. */
+int ref_run_blocks(int n_blocks, const int16_t *iq, int16_t *audio, int nr_level, int with_fft)
+{
+    int16_t L[2][128], R[2][128], oL[128], oR[128];
+    int played = 0;
+    auto split = [&](int b, int s) { for (int i = 0; i < 128; i++) { L[s][i] = iq[(size_t)b * 256 + 2 * i]; R[s][i] = iq[(size_t)b * 256 + 2 * i + 1]; } };
+    split(0, 0);
+    Q_in_L.shim_push(L[0]); Q_in_R.shim_push(R[0]);
+    for (int b = 0; b < n_blocks; b++) {
+        const int cur = b & 1, nxt = cur ^ 1;
+        if (with_fft) { g_fft->shim_feed(0, L[cur]); g_fft->shim_feed(1, R[cur]); g_fft->update(); (void)g_fft->available(); }
+        if (b + 1 < n_blocks) split(b + 1, nxt); else { memset(L[nxt], 0, sizeof(L[nxt])); memset(R[nxt], 0, sizeof(R[nxt])); }
+        Q_in_L.shim_push(L[nxt]); Q_in_R.shim_push(R[nxt]);
+        doConvolutionalProcessing((float)nr_level, true, 300.0, 4000.0);
+        if (Q_out_L.shim_available() && Q_out_R.shim_available()) {
+            Q_out_L.shim_pop(oL); Q_out_R.shim_pop(oR);
+            for (int i = 0; i < 128; i++) { audio[(size_t)b * 256 + 2 * i] = oL[i]; audio[(size_t)b * 256 + 2 * i + 1] = oR[i]; }
+            played++;
+        }
+    }
+    return played;
+}
+
 }  /* extern "C" */

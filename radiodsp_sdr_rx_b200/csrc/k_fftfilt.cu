@@ -143,12 +143,17 @@ __global__ void __launch_bounds__(WARPS * 32, 3) k_fftfilt(FftFiltArgs a)
         if (to_dnr) {
             *reinterpret_cast<float4 *>(a.out_f32_L + cb * RDSP_BLK + 4 * lane) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
         } else {
-            int4 q;
-            q.x = (int)mk16(f32_to_q15(o[0].x), f32_to_q15(o[0].y));
-            q.y = (int)mk16(f32_to_q15(o[1].x), f32_to_q15(o[1].y));
-            q.z = (int)mk16(f32_to_q15(o[2].x), f32_to_q15(o[2].y));
-            q.w = (int)mk16(f32_to_q15(o[3].x), f32_to_q15(o[3].y));
-            st_stream16(a.out_stereo + cb * 2 * RDSP_BLK + lane * 8, q);
+            if (a.out_mono) {
+                st_stream8(a.out_mono + cb * RDSP_BLK + lane * 4,
+                           make_int2((int)mk16(f32_to_q15(o[0].x), f32_to_q15(o[1].x)), (int)mk16(f32_to_q15(o[2].x), f32_to_q15(o[3].x))));
+            } else {
+                int4 q;
+                q.x = (int)mk16(f32_to_q15(o[0].x), f32_to_q15(o[0].y));
+                q.y = (int)mk16(f32_to_q15(o[1].x), f32_to_q15(o[1].y));
+                q.z = (int)mk16(f32_to_q15(o[2].x), f32_to_q15(o[2].y));
+                q.w = (int)mk16(f32_to_q15(o[3].x), f32_to_q15(o[3].y));
+                st_stream16(a.out_stereo + cb * 2 * RDSP_BLK + lane * 8, q);
+            }
             if (a.dbg) {
                 float4 *dp = reinterpret_cast<float4 *>(a.dbg + cb * 2 * RDSP_BLK + lane * 8);
                 dp[0] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);

@@ -21,9 +21,14 @@
 //   * what remains sequential is a scalar chain of one subtract, one multiply and one FMA per sample;
 //   * the coefficient update c += sum_j g[j] x[n+j] is four independent FMAs per tap.
 //
-// G = 4 or 8 lanes per channel, W = 96/G taps per lane in registers together with a circular window of the
-// delayed input (static indices through unrolling); the block sits in shared memory with a row stride that
-// keeps every 16-byte access of a quarter-warp on distinct banks.
+// The 96 taps of a channel are cut into EIGHT segments of 12 ("virtual lanes"), each with a circular window of the
+// delayed input in registers (static indices through unrolling).  Two forms: G = 8 lanes per channel hold one segment
+// each; G = 4 lanes hold two (segments g and g + 4) and add their two partial sums first — which is exactly the first
+// stage (xor 4) of the 8-lane butterfly, so BOTH FORMS PERFORM THE SAME ROUNDINGS IN THE SAME ORDER and give the same
+// bits.  The launcher picks the form by list size for speed only (4 lanes: 30 % fewer instructions per sample, better
+// with many channels; 8 lanes: half the dependent chain per group, better with few); what a channel computes depends
+// neither on the form nor on the list it was launched in.  The block sits in shared memory with a row stride that keeps
+// every 16-byte access of a quarter-warp on distinct banks.
 //
 // Both tap-sized loops run on the packed f32x2 FMA of sm_100 (FFMA2 = two IEEE f32 FMAs in one issue slot): taps are
 // held as pairs (c[i+1], c[i]) and the window twice, as even pairs (w[2q], w[2q+1]) and as odd pairs (w[2q+1], w[2q+2]),
@@ -56,10 +61,11 @@ __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<floa
 template <int G, bool PACKED>
 __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32) k_nlms(NlmsArgs a)
 {
-    constexpr int W = RDSP_LMS_NTAPS / G;        // taps per lane (24 or 12)
-    constexpr int S = W + D;                     // circular window (slots = lane-relative sample index mod S)
+    constexpr int V = 8 / G;                     // virtual lanes (tap segments) per lane: 1 or 2
+    constexpr int W = RDSP_LMS_NTAPS / 8;        // taps per segment
+    constexpr int S = W + D;                     // circular window of a segment (slots = segment-relative sample index mod S)
     constexpr int CPW = 32 / G;                  // channels per warp
-    static_assert(W % 4 == 0, "taps per lane must be a multiple of 4");
+    static_assert(W % 4 == 0 && (G == 4 || G == 8) && !(PACKED && V != 1), "forms: 8 lanes (scalar or packed), 4 lanes (scalar)");
     constexpr int NWARPS = PACKED ? NWARPS_PACKED : NWARPS_SCALAR;
     __shared__ __align__(16) float s_x[NWARPS * CPW][XS];     // [0,128) previous block / outputs, [128,256) current
     __shared__ __align__(16) float s_x1[PACKED ? NWARPS * CPW : 1][XS];   // the same samples one to the left: s_x1[i] = x[i + 1]
@@ -73,10 +79,14 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
     float *xs = s_x1[PACKED ? warp * CPW + lane / G : 0];     // odd window pairs load from here as aligned 16-byte quads
 
     constexpr int HP = S / 2;                    // window pairs
-    float2 cp[W / 2];                            // (c[2r+1], c[2r])
-    float2 E[HP] = {}, O[HP] = {};                       // E[q] = (w[2q], w[2q+1]), O[q] = (w[2q+1], w[(2q+2) % S])
-    auto w1 = [&](int m) -> float { m = ((m % S) + S) % S; return (m & 1) ? E[m / 2].y : E[m / 2].x; };
+    float2 cpv[V][W / 2];                        // segment v: (c[2r+1], c[2r])
+    float2 Ev[V][HP] = {}, O[HP] = {};           // Ev[v][q] = (w[2q], w[2q+1]), O[q] = (w[2q+1], w[(2q+2) % S]) (packed form, one segment)
+    float2 (&cp)[W / 2] = cpv[0];
+    float2 (&E)[HP] = Ev[0];
+    auto wv = [&](int v, int m) -> float { m = ((m % S) + S) % S; return (m & 1) ? Ev[v][m / 2].y : Ev[v][m / 2].x; };
+    auto w1 = [&](int m) -> float { return wv(0, m); };
     auto w2 = [&](int m) -> float2 { m = ((m % S) + S) % S; return (m & 1) ? O[m / 2] : E[m / 2]; };      // (w[m], w[m+1])
+    auto seg = [&](int v) -> int { return g + G * v; };           // the virtual lane of segment v of this lane: delays W seg .. W seg + W - 1
     float energy = 0.0f, mu = 0.0f;
     bool first = false, peak = false;
     if (active) {
@@ -85,15 +95,19 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
         peak = !a.mode && p.als_peak != 0;                               // ALS "peak": the notch stage emits the estimate
         const float *cf = a.coeff + (size_t)ch * RDSP_LMS_NTAPS;
 #pragma unroll
-        for (int r = 0; r < W / 2; r++)                                // tap register i <-> delay W*g + i
-            cp[r] = *reinterpret_cast<const float2 *>(cf + 94 - W * g - 2 * r);
+        for (int v = 0; v < V; v++)
+#pragma unroll
+            for (int r = 0; r < W / 2; r++)                            // tap register i of segment v <-> delay W * seg(v) + i
+                cpv[v][r] = *reinterpret_cast<const float2 *>(cf + 94 - W * seg(v) - 2 * r);
         const float4 *pv = reinterpret_cast<const float4 *>(a.prev + (size_t)ch * RDSP_BLK);
         for (int i = g; i < 32; i += G) st4(xb + 4 * i, pv[i]);
         energy = a.energy[ch];
         first = a.first[ch] != 0;
     } else {
 #pragma unroll
-        for (int r = 0; r < W / 2; r++) cp[r] = make_float2(0.f, 0.f);
+        for (int v = 0; v < V; v++)
+#pragma unroll
+            for (int r = 0; r < W / 2; r++) cpv[v][r] = make_float2(0.f, 0.f);
         for (int i = g; i < 32; i += G) st4(xb + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     __syncwarp();
@@ -156,11 +170,14 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
         shift_copy(128);
         __syncwarp();
 
-        // ---- lane-relative window u[m] = x[m - W*g]; slots m mod S.  Before sample 0: m = -S .. -1 (all slots)
+        // ---- segment-relative window u[m] = x[m - W*seg]; slots m mod S.  Before sample 0: m = -S .. -1 (all slots)
 #pragma unroll
         for (int q = 0; q < S / 4; q++) {
-            const float4 v = ld4(xb + 128 - W * g - S + 4 * q);             // m = -S + 4q .. -S + 4q + 3
-            E[2 * q] = make_float2(v.x, v.y); E[2 * q + 1] = make_float2(v.z, v.w);
+#pragma unroll
+            for (int vv = 0; vv < V; vv++) {
+                const float4 v = ld4(xb + 128 - W * seg(vv) - S + 4 * q);   // m = -S + 4q .. -S + 4q + 3
+                Ev[vv][2 * q] = make_float2(v.x, v.y); Ev[vv][2 * q + 1] = make_float2(v.z, v.w);
+            }
             if (PACKED) {
                 const float4 o = ld4(xs + 128 - W * g - S + 4 * q);         // m + 1: the last one (slot 0) is sample 0 already
                 O[2 * q] = make_float2(o.x, o.y); O[2 * q + 1] = make_float2(o.z, o.w);
@@ -182,24 +199,33 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
                     // sum carried for long would lose all its digits when the signal drops by orders of magnitude
                     // inside the window, exactly where 1/(energy + eps) amplifies every error.
                     if (gq % ANCHOR == 0) {
-                        s1 = 0.f; s2 = 0.f; s3 = 0.f;
+                        float a1[V], a2[V], a3[V];
 #pragma unroll
-                        for (int i = 0; i < W; i++) {
-                            const float uk = w1(sb - 1 - i);
-                            s1 = fmaf(w1(sb - 2 - i), uk, s1);
-                            s2 = fmaf(w1(sb - 3 - i), uk, s2);
-                            s3 = fmaf(w1(sb - 4 - i), uk, s3);
+                        for (int v = 0; v < V; v++) {
+                            a1[v] = 0.f; a2[v] = 0.f; a3[v] = 0.f;
+#pragma unroll
+                            for (int i = 0; i < W; i++) {
+                                const float uk = wv(v, sb - 1 - i);
+                                a1[v] = fmaf(wv(v, sb - 2 - i), uk, a1[v]);
+                                a2[v] = fmaf(wv(v, sb - 3 - i), uk, a2[v]);
+                                a3[v] = fmaf(wv(v, sb - 4 - i), uk, a3[v]);
+                            }
                         }
+                        // two segments in one lane: their sum IS the xor-4 stage of the 8-lane butterfly
+                        s1 = V == 2 ? a1[0] + a1[V - 1] : a1[0]; s2 = V == 2 ? a2[0] + a2[V - 1] : a2[0]; s3 = V == 2 ? a3[0] + a3[V - 1] : a3[0];
 #pragma unroll
-                        for (int o = G / 2; o > 0; o >>= 1) {
+                        for (int o = G / 2 >= 4 ? 4 : 2; o > 0; o >>= 1) {
                             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
                             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                             s3 += __shfl_xor_sync(0xffffffffu, s3, o);
                         }
                     }
                     // ---- loads
-                    const float4 un = ld4(xb + 128 + n - W * g);
-                    E[sb / 2] = make_float2(un.x, un.y); E[sb / 2 + 1] = make_float2(un.z, un.w);
+#pragma unroll
+                    for (int v = 0; v < V; v++) {
+                        const float4 un = ld4(xb + 128 + n - W * seg(v));
+                        Ev[v][sb / 2] = make_float2(un.x, un.y); Ev[v][sb / 2 + 1] = make_float2(un.z, un.w);
+                    }
                     // odd pairs (w[sb+1], w[sb+2]), (w[sb+3], w[sb+4]): the slot of w[sb+4] held w[sb-W], which no pair needs any more
                     if (PACKED) {
                         const float4 uo = ld4(xs + 128 + n - W * g);
@@ -236,21 +262,27 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
                         }
                         p[0] = p01.x; p[1] = p01.y; p[2] = p23.x; p[3] = p23.y;
                     } else {
-                        float2 pa[4];                                       // .y: even taps, .x: odd taps
+                        float pv[V][4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) pa[j] = make_float2(0.f, 0.f);
+                        for (int v = 0; v < V; v++) {
+                            float2 pa[4];                                   // .y: even taps, .x: odd taps
 #pragma unroll
-                        for (int r = 0; r < W / 2; r++) {
+                            for (int j = 0; j < 4; j++) pa[j] = make_float2(0.f, 0.f);
 #pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                pa[j].y = fmaf(cp[r].y, w1(sb + j - 2 * r), pa[j].y);
-                                pa[j].x = fmaf(cp[r].x, w1(sb + j - 2 * r - 1), pa[j].x);
+                            for (int r = 0; r < W / 2; r++) {
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    pa[j].y = fmaf(cpv[v][r].y, wv(v, sb + j - 2 * r), pa[j].y);
+                                    pa[j].x = fmaf(cpv[v][r].x, wv(v, sb + j - 2 * r - 1), pa[j].x);
+                                }
                             }
+#pragma unroll
+                            for (int j = 0; j < 4; j++) pv[v][j] = pa[j].y + pa[j].x;
                         }
 #pragma unroll
-                        for (int j = 0; j < 4; j++) p[j] = pa[j].y + pa[j].x;
+                        for (int j = 0; j < 4; j++) p[j] = V == 2 ? pv[0][j] + pv[V - 1][j] : pv[0][j];      // = the xor-4 stage of the 8-lane form
 #pragma unroll
-                        for (int o = G / 2; o > 0; o >>= 1) {
+                        for (int o = G / 2 >= 4 ? 4 : 2; o > 0; o >>= 1) {
 #pragma unroll
                             for (int j = 0; j < 4; j++) p[j] += __shfl_xor_sync(0xffffffffu, p[j], o);
                         }
@@ -328,13 +360,16 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
 
                     // ---- coefficient update c += sum_j g[j] x[n+j]
 #pragma unroll
-                    for (int r = 0; r < W / 2; r++) {
+                    for (int v = 0; v < V; v++) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            if (PACKED) cp[r] = __ffma2_rn(make_float2(gj[j], gj[j]), w2(sb + j - 2 * r - 1), cp[r]);
-                            else {
-                                cp[r].y = fmaf(gj[j], w1(sb + j - 2 * r), cp[r].y);
-                                cp[r].x = fmaf(gj[j], w1(sb + j - 2 * r - 1), cp[r].x);
+                        for (int r = 0; r < W / 2; r++) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                if (PACKED) cp[r] = __ffma2_rn(make_float2(gj[j], gj[j]), w2(sb + j - 2 * r - 1), cp[r]);
+                                else {
+                                    cpv[v][r].y = fmaf(gj[j], wv(v, sb + j - 2 * r), cpv[v][r].y);
+                                    cpv[v][r].x = fmaf(gj[j], wv(v, sb + j - 2 * r - 1), cpv[v][r].x);
+                                }
                             }
                         }
                     }
@@ -352,13 +387,15 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
                 for (int i = g; i < 32; i += G) dst[i] = ld4(xb + 4 * i);
             } else {
                 int4 *dst = reinterpret_cast<int4 *>(a.out_stereo + cb * 2 * RDSP_BLK);
+                int2 *dst_mono = reinterpret_cast<int2 *>(a.out_mono + cb * RDSP_BLK);
                 float4 *dbg = a.dbg ? reinterpret_cast<float4 *>(a.dbg + cb * 2 * RDSP_BLK) : nullptr;
                 for (int i = g; i < 32; i += G) {
                     const float4 yv = ld4(xb + 4 * i);
                     const float f0 = (float)((double)yv.x * 1.1), f1 = (float)((double)yv.y * 1.1);
                     const float f2 = (float)((double)yv.z * 1.1), f3 = (float)((double)yv.w * 1.1);
                     const int32_t q0 = f32_to_q15(f0), q1 = f32_to_q15(f1), q2 = f32_to_q15(f2), q3 = f32_to_q15(f3);
-                    dst[i] = make_int4((int)mk16(q0, q0), (int)mk16(q1, q1), (int)mk16(q2, q2), (int)mk16(q3, q3));
+                    if (a.out_mono) dst_mono[i] = make_int2((int)mk16(q0, q1), (int)mk16(q2, q3));     // RDSP_AUDIO_MONO: L only
+                    else dst[i] = make_int4((int)mk16(q0, q0), (int)mk16(q1, q1), (int)mk16(q2, q2), (int)mk16(q3, q3));
                     if (dbg) {
                         dbg[2 * i] = make_float4(f0, f0, f1, f1);
                         dbg[2 * i + 1] = make_float4(f2, f2, f3, f3);
@@ -377,13 +414,17 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
         {
             float chk = energy;
 #pragma unroll
-            for (int r = 0; r < W / 2; r++) chk += cp[r].x + cp[r].y;
+            for (int v = 0; v < V; v++)
+#pragma unroll
+                for (int r = 0; r < W / 2; r++) chk += cpv[v][r].x + cpv[v][r].y;
             bool bad = !isfinite(chk);
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) bad |= (__shfl_xor_sync(0xffffffffu, (int)bad, o) != 0);
             if (bad) {
 #pragma unroll
-                for (int r = 0; r < W / 2; r++) cp[r] = make_float2(0.f, 0.f);
+                for (int v = 0; v < V; v++)
+#pragma unroll
+                    for (int r = 0; r < W / 2; r++) cpv[v][r] = make_float2(0.f, 0.f);
                 energy = 0.0f;
                 for (int i = g; i < 32; i += G) {                                                    // like Init_LMS_NR: history cleared too
                     st4(xb + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -397,7 +438,9 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
     if (active) {
         float *cf = a.coeff + (size_t)ch * RDSP_LMS_NTAPS;
 #pragma unroll
-        for (int r = 0; r < W / 2; r++) *reinterpret_cast<float2 *>(cf + 94 - W * g - 2 * r) = cp[r];
+        for (int v = 0; v < V; v++)
+#pragma unroll
+            for (int r = 0; r < W / 2; r++) *reinterpret_cast<float2 *>(cf + 94 - W * seg(v) - 2 * r) = cpv[v][r];
         float4 *pv = reinterpret_cast<float4 *>(a.prev + (size_t)ch * RDSP_BLK);
         for (int i = g; i < 32; i += G) pv[i] = ld4(xb + 4 * i);
         if (g == 0) {
@@ -419,15 +462,16 @@ void launch_nlms(const NlmsArgs &a, cudaStream_t st)
     // sample); 8 lanes halve the dependent chain of a group.  Measured alone (8 blocks per launch, us, G = 4 / G = 8):
     // 2048 channels 170 / 100, 6554 channels 167 / 165, 8192 channels 165 / 211, 16384 channels 324 / 336; inside the
     // cfg5 step (6554 DNR channels beside the other kernels) G = 8 is 4 % ahead, inside cfg4a (8192) G = 4 by 11 %.
-    // The two forms sum in different orders, so the switch sits above the per-GPU channel counts of the configs:
-    // a handle and its channel-range shards then run the same form and agree bit for bit (tests/test_gpu_parity.py).
-    int G = a.n_list >= 12288 ? 4 : 8;
+    // The two forms give the same bits (the 4-lane one adds its two segment sums first = the xor-4 stage of the 8-lane
+    // butterfly), so the switch is a pure speed choice and sits where the measurements cross.
+    int G = a.n_list >= 7168 ? 4 : 8;
     if (const char *env = getenv("RDSP_NLMS_LANES")) G = atoi(env) == 4 ? 4 : 8;       // experiments only
     // The packed f32x2 form issues half the tap FMAs (FFMA2) for the same FMA-pipe time and a second window copy.  It
     // wins where other kernels compete for the issue slots (cfg5: 0.585 -> 0.537 ms per step although the kernel alone
     // takes the same 145 us) and loses where the NLMS has the GPU to itself (cfg3, 8192 notch channels: 270 -> 315 us),
     // so the caller says which situation this is.  Both forms perform the same roundings per lane: bit-identical output.
-    bool packed = a.packed != 0;
+    // A handle with spectrum branches has other kernels competing for the issue slots while the NLMS runs.
+    bool packed = a.contended != 0;
     if (const char *env = getenv("RDSP_NLMS_PACKED")) packed = env[0] == '1';          // experiments only
     const int nw = (G == 8 && packed) ? NWARPS_PACKED : NWARPS_SCALAR;
     const int cpb = nw * (32 / G);

@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(NWARPS * 32) k_nlms_direct(NlmsArgs a)
                     const float f0 = (float)((double)y.x * 1.1), f1 = (float)((double)y.y * 1.1);
                     const float f2 = (float)((double)y.z * 1.1), f3 = (float)((double)y.w * 1.1);
                     const int32_t q0 = f32_to_q15(f0), q1 = f32_to_q15(f1), q2 = f32_to_q15(f2), q3 = f32_to_q15(f3);
-                    dst[i] = make_int4((int)mk16(q0, q0), (int)mk16(q1, q1), (int)mk16(q2, q2), (int)mk16(q3, q3));
+                    if (a.out_mono) reinterpret_cast<int2 *>(a.out_mono + cb * RDSP_BLK)[i] = make_int2((int)mk16(q0, q1), (int)mk16(q2, q3));
+                    else dst[i] = make_int4((int)mk16(q0, q0), (int)mk16(q1, q1), (int)mk16(q2, q2), (int)mk16(q3, q3));
                     if (dbg) {
                         dbg[2 * i] = make_float4(f0, f0, f1, f1);
                         dbg[2 * i + 1] = make_float4(f2, f2, f3, f3);

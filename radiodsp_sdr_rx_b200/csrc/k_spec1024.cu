@@ -97,10 +97,14 @@ __global__ void __launch_bounds__(NT) k_spec1024(Spec1024Args a)
     for (int t = 0; t < a.T; t++) {
         const unsigned long long tick = tick0 + t;
         const int slot = (int)(tick & 7ull);
-        if (tid < 32) {                                             // append L of this block: 4 frames (16 bytes) per lane
-            const int4 v = *reinterpret_cast<const int4 *>(a.audio + ((size_t)t * a.C + ch) * 2 * RDSP_BLK + tid * 8);
-            gring[slot * 32 + tid] = make_uint2(((uint32_t)v.x & 0xFFFFu) | ((uint32_t)v.y << 16),
-                                                ((uint32_t)v.z & 0xFFFFu) | ((uint32_t)v.w << 16));
+        if (tid < 32) {                                             // append L of this block: 4 frames per lane
+            if (a.audio_mono) {
+                gring[slot * 32 + tid] = *reinterpret_cast<const uint2 *>(a.audio + ((size_t)t * a.C + ch) * RDSP_BLK + tid * 4);
+            } else {
+                const int4 v = *reinterpret_cast<const int4 *>(a.audio + ((size_t)t * a.C + ch) * 2 * RDSP_BLK + tid * 8);
+                gring[slot * 32 + tid] = make_uint2(((uint32_t)v.x & 0xFFFFu) | ((uint32_t)v.y << 16),
+                                                    ((uint32_t)v.z & 0xFFFFu) | ((uint32_t)v.w << 16));
+            }
         }
         if (!(tick >= 7ull && ((tick - 7ull) & 3ull) == 0ull)) continue;       // uniform over the CTA
         __syncthreads();                                            // the appended block is visible to the whole CTA

@@ -63,7 +63,8 @@ struct NlmsArgs {
     const int16_t *in_q15;      // [T][C][128]  (notch) or nullptr
     const float *in_f32;        // [T][C][128]  (DNR)   or nullptr
     float *out_f32;             // [T][C][128]  error signal (notch)
-    int16_t *out_stereo;        // [T][C][128][2] 1.1*y, L = R (DNR)
+    int16_t *out_stereo;        // [T][C][128][2] 1.1*y, L = R (DNR) ...
+    int16_t *out_mono;          // ... or [T][C][128] (RDSP_AUDIO_MONO); exactly one is set in mode 1
     float *dbg;                 // [T][C][128][2] or nullptr
     float *coeff;               // [C][96] CMSIS order (index 0 multiplies the oldest sample)
     float *prev;                // [C][128] previous input block (= de-correlation ring + FIR history)
@@ -71,7 +72,7 @@ struct NlmsArgs {
     uint8_t *first;             // [C] 1 until the instance ran once (RDSP_noise_reduction.h:69 statics)
     const RdspChanParams *par;
     int mode;                   // 0 = notch (output error), 1 = DNR (output estimate)
-    int packed;                 // 1: other kernels run beside this one (spectrum branches): use the FFMA2 form
+    int contended;              // 1: other kernels run beside this one (spectrum branches): the FFMA2 form pays (fewer issue slots)
     int direct;                 // 1: the sample-by-sample cross-check kernel (k_nlms_direct.cu; RDSP_NLMS_IMPL=direct at create)
 };
 void launch_nlms(const NlmsArgs &a, cudaStream_t st);
@@ -98,7 +99,8 @@ void launch_agc(const AgcArgs &a, cudaStream_t st);
 struct FftFiltArgs {
     const int16_t *in_mono;     // [T][C][128]     (L = R) or nullptr
     const int16_t *in_stereo;   // [T][C][128][2]  or nullptr
-    int16_t *out_stereo;        // [T][C][128][2]
+    int16_t *out_stereo;        // [T][C][128][2] ...
+    int16_t *out_mono;          // ... or [T][C][128], L only (RDSP_AUDIO_MONO); exactly one is set
     float *out_f32_L;           // [T][C][128] for channels whose DNR follows
     float *dbg;                 // [T][C][128][2] or nullptr
     int16_t *last;              // [C][128][2] previous input block (q15, exact)
@@ -145,7 +147,8 @@ void launch_spec256(const Spec256Args &a, cudaStream_t st);
 
 // K10 -------------------------------------------------------------------------------------------
 struct Spec1024Args {
-    const int16_t *audio;       // [T][C][128][2] (L used)
+    const int16_t *audio;       // [T][C][128][2] (L used), or [T][C][128] when audio_mono
+    int audio_mono;
     int16_t *ring;              // [C][8][128] last blocks of L, slot = tick mod 8
     uint16_t *output;           // [C][512]
     int C, T;

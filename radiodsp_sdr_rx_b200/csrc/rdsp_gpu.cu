@@ -425,6 +425,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
     const bool fe = has(h, RDSP_STAGE_FRONTEND), notch = has(h, RDSP_STAGE_NOTCH), agc = has(h, RDSP_STAGE_AGC);
     const bool ff = has(h, RDSP_STAGE_FFTFILT), nr = has(h, RDSP_STAGE_NR);
     const int C = h->C;
+    const bool mono = h->cfg.audio_layout == RDSP_AUDIO_MONO;          // audio = [T][C][128] (L only) instead of [T][C][128][2]
     const RdspTick *tick_in = h->d_tick + par;
     RdspTick *tick_out = h->d_tick + (par ^ 1);
     int G = 1;
@@ -448,7 +449,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
         if (piped) CK(cudaStreamWaitEvent(s_front, h->ev_fork, 0));
         front_last = !(notch || agc || ff);
         FrontArgs a{};
-        a.iq = iq; a.out_mono = front_last ? nullptr : h->d_mid_a; a.out_stereo = front_last ? audio : nullptr;
+        a.iq = iq; a.out_mono = front_last ? (mono ? audio : nullptr) : h->d_mid_a; a.out_stereo = (front_last && !mono) ? audio : nullptr;
         a.dbg = front_last ? dbg : nullptr; a.par = h->d_par; a.taps = h->d_taps; a.C = C; a.T = T;
         Prof pr(h, KK_FRONT, s_front);
         if (h->front_tc) {
@@ -478,7 +479,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
     // With classes 1 and 2 on two streams the latency-bound notch -> AGC -> ... chain of the (few) notched channels runs
     // beside the wide kernels of the others instead of in front of them.
     // the spectrum branches keep the issue slots contended while the NLMS kernels run (k_nlms.cu, launch_nlms)
-    const int nlms_packed = (has(h, RDSP_STAGE_SPEC256) || has(h, RDSP_STAGE_SPEC1024)) ? 1 : 0;
+    const int nlms_contended = (has(h, RDSP_STAGE_SPEC256) || has(h, RDSP_STAGE_SPEC1024)) ? 1 : 0;
     auto run_chain = [&](cudaStream_t cs, int cls, int c0, int c1) -> int {
         const int nc = c1 - c0;
         int f_notch = 0, n_notch = 0, f_plain = 0, n_plain = 0;
@@ -491,7 +492,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
             mono = h->d_mid_a;
             if (notch || agc) {
                 AgcArgs ag{};
-                ag.out_mono = ff ? h->d_mid_b : nullptr; ag.out_stereo = ff ? nullptr : audio;
+                ag.out_mono = ff ? h->d_mid_b : (mono ? audio : nullptr); ag.out_stereo = (ff || mono) ? nullptr : audio;
                 ag.dbg = ff ? nullptr : dbg; ag.env = h->d_agc_env; ag.par = h->d_par; ag.C = C; ag.T = T;
                 ag.agc_stage = agc ? 1 : 0;
                 ag.target = h->cfg.agc_target; ag.max_gain = h->cfg.agc_max_gain; ag.alpha_a = h->agc_alpha_a;
@@ -506,7 +507,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
                     n.list = h->d_list_notch + f_notch; n.n_list = n_notch; n.C = C; n.T = T;
                     n.in_q15 = h->d_mid_a; n.out_f32 = h->d_scr;
                     n.coeff = h->d_nc_coeff; n.prev = h->d_nc_prev; n.energy = h->d_nc_energy; n.first = h->d_nc_first;
-                    n.par = h->d_par; n.mode = 0; n.packed = nlms_packed; n.direct = h->nlms_direct;
+                    n.par = h->d_par; n.mode = 0; n.contended = nlms_contended; n.direct = h->nlms_direct;
                     { Prof pr(h, KK_NOTCH, cs); launch_nlms(n, cs); }
                     // ... the others read the notch's f32 error signal
                     ag.list = h->d_list_notch + f_notch; ag.n_list = n_notch; ag.in_q15 = nullptr; ag.in_f32 = h->d_scr;
@@ -517,7 +518,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
         }
         if (ff) {
             FftFiltArgs f{};
-            f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq; f.out_stereo = audio; f.out_f32_L = h->d_scr;
+            f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq; f.out_stereo = mono ? nullptr : audio; f.out_mono = mono ? audio : nullptr; f.out_f32_L = h->d_scr;
             f.dbg = dbg; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256; f.sin512 = h->d_sin512;
             f.par = h->d_par; f.C = C; f.T = T; f.list = cls_list; f.ch0 = c0; f.n = cls_n; f.nr_stage = nr ? 1 : 0;
             { Prof pr(h, KK_FFTFILT, cs); launch_fftfilt(f, cs); }
@@ -529,16 +530,16 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
                 if (n_dnr > 0) {
                     NlmsArgs n{};
                     n.list = dl + f_dnr; n.n_list = n_dnr; n.C = C; n.T = T;
-                    n.in_f32 = h->d_scr; n.out_stereo = audio; n.dbg = dbg;
+                    n.in_f32 = h->d_scr; n.out_stereo = mono ? nullptr : audio; n.out_mono = mono ? audio : nullptr; n.dbg = dbg;
                     n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
-                    n.par = h->d_par; n.mode = 1; n.packed = nlms_packed; n.direct = h->nlms_direct;
+                    n.par = h->d_par; n.mode = 1; n.contended = nlms_contended; n.direct = h->nlms_direct;
                     { Prof pr(h, KK_DNR, cs); launch_nlms(n, cs); }
                 }
             }
         }
         if (has(h, RDSP_STAGE_SPEC1024)) {
             Spec1024Args s1{};
-            s1.audio = audio; s1.ring = h->d_ring; s1.output = h->d_spec1024_out; s1.C = C; s1.T = T;
+            s1.audio = audio; s1.audio_mono = mono ? 1 : 0; s1.ring = h->d_ring; s1.output = h->d_spec1024_out; s1.C = C; s1.T = T;
             s1.list = cls_list; s1.ch0 = c0; s1.n = cls_n;
             s1.tick_in = tick_in; s1.tick_out = tick_out; s1.tw = h->d_tw; s1.win = h->d_win1024;
             { Prof pr(h, KK_SPEC1024, cs); launch_spec1024(s1, cs); }
@@ -686,6 +687,23 @@ int run_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStream_t
         drop_graphs(h);
         return enqueue_call(h, T, iq, audio, st, piped, fe_cur, par);
     }
+    if (getenv("RDSP_GRAPH_DEBUG")) {
+        // development aid: what the capture recorded (node count, kernel priorities)
+        size_t nn = 0;
+        cudaGraphGetNodes(graph, nullptr, &nn);
+        std::vector<cudaGraphNode_t> nodes(nn);
+        cudaGraphGetNodes(graph, nodes.data(), &nn);
+        fprintf(stderr, "[rdsp graph] T=%d: %zu nodes, %llu kernels;", T, nn, (unsigned long long)n_launch);
+        for (auto nd : nodes) {
+            cudaGraphNodeType ty;
+            cudaGraphNodeGetType(nd, &ty);
+            if (ty != cudaGraphNodeTypeKernel) continue;
+            cudaLaunchAttributeValue v{};
+            if (cudaGraphKernelNodeGetAttribute(nd, cudaLaunchAttributePriority, &v) == cudaSuccess) fprintf(stderr, " prio %d", v.priority);
+        }
+        fprintf(stderr, "\n");
+        cudaGetLastError();
+    }
     cudaGraphExec_t exec = nullptr;
     const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
@@ -811,7 +829,8 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
         int prio_lo = 0, prio_hi = 0;
         CKC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         for (int s = 0; s < kStreams; s++) {
-            const bool critical = s < kMaxGroups || s >= 2 * kMaxGroups;      // main chains, notch-class chains, front end
+            static const bool no_prio = [] { const char *e = getenv("RDSP_NO_PRIO"); return e && e[0] == '1'; }();   // experiments
+            const bool critical = no_prio || s < kMaxGroups || s >= 2 * kMaxGroups;      // main chains, notch-class chains, front end
             CKC(cudaStreamCreateWithPriority(&h->stage_stream[s], cudaStreamNonBlocking, critical ? prio_hi : prio_lo));
         }
     }
@@ -1028,6 +1047,7 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
 
     const int C = h->C, T = (int)n_blocks;
     const size_t io_bytes = (size_t)T * C * 2 * RDSP_BLK * sizeof(int16_t);
+    const size_t out_bytes = h->cfg.audio_layout == RDSP_AUDIO_MONO ? io_bytes / 2 : io_bytes;
     const int16_t *iq = iq_in;
     int16_t *audio = audio_out;
     const bool host_io = h->cfg.io_location == RDSP_IO_HOST;
@@ -1052,7 +1072,7 @@ int rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq_
         CK(cudaEventRecord(h->ev_comp[hb], st));
         if (audio_path) {
             CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_comp[hb], 0));
-            CK(cudaMemcpyAsync(audio_out, h->d_out_stage2[hb], io_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
+            CK(cudaMemcpyAsync(audio_out, h->d_out_stage2[hb], out_bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
             CK(cudaEventRecord(h->ev_d2h[hb], h->d2h_stream));
         }
         h->host_calls++;

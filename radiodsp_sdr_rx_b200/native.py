@@ -217,7 +217,7 @@ class ReceiverBank:
         """Convenience for IO_HOST handles: numpy in, numpy out."""
         assert self.cfg.io_location == IO_HOST
         iq = np.ascontiguousarray(iq, np.int16)
-        out = np.zeros_like(iq)
+        out = np.zeros(iq.shape[:3], np.int16) if self.cfg.audio_layout == AUDIO_MONO else np.zeros_like(iq)
         self.process_blocks(iq.shape[0], iq, out)
         if self.cfg.async_:
             self.synchronize()

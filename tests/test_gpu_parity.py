@@ -403,23 +403,49 @@ def test_ten_seconds_no_drift(rd, po, stage):
     assert (errs[:, -3:].mean(axis=1) <= 0.5 * REL_RMS_TOL).all(), errs
 
 
-def test_nlms_packed_form_is_bit_identical(rd, po, monkeypatch):
-    """k_nlms runs its tap loops on the packed f32x2 FMA (FFMA2) when spectrum branches share the GPU and as scalar FMAs
-    otherwise; every lane of a pair performs the scalar FMA sequence, so both forms give the same bits (notch error
-    signal and DNR estimate, through AGC / FFT filter down to the q15 audio)"""
-    nc, nb = 40, 12
-    params, demod = _all_mode_params(po, nc)
-    iq = synth.synth_iq(np.arange(nc), nb, demod, interferer=True)
+def test_nlms_bits_do_not_depend_on_the_launch_list(rd, po):
+    """what a channel computes depends neither on the form the launcher picks nor on which other channels run the notch / the
+    DNR: toggling the neighbours' settings (=> other lists, other warps, other CTAs) leaves a channel's notch error
+    signal, DNR estimate and audio bit-identical"""
+    nc, nb = 41, 12
+    iq = bench.make_inputs("cfg5", 0, nc, nb)
+    keep = [2, 6, 10, 14, 17, 23, 38]                                       # CW channels with notch (+ DNR on most), and others
     outs = []
-    for packed in ("0", "1"):
+    for variant in range(3):
+        bank = make_bank(rd, nc, rd.STAGE_ALL, max_blocks=4)
+        for c in range(nc):
+            p = dict(bench.channel_params("cfg5", c))
+            if c not in keep and variant == 1:
+                p.update(notch_on=1 - p["notch_on"], nr_kind=1, nr_level=(30, 50)[c % 2])
+            if c not in keep and variant == 2:
+                p.update(notch_on=int(c % 3 == 0), nr_kind=0, nr_level=0)
+            bank.set_mode(c, 1, rd.default_params(**p))
+        o = np.concatenate([bank.process_host(iq[b:b + 4]) for b in range(0, nb, 4)])
+        outs.append((o[:, keep], bank.read_debug_f32(4)[:, keep], bank.read_audio_spectrum()[0][keep]))
+    for v in (1, 2):
+        for a, b in zip(outs[0], outs[v]):
+            assert np.array_equal(a, b)
+
+
+def test_nlms_forms_are_bit_identical(rd, po, monkeypatch):
+    """k_nlms has three forms — 8 lanes per channel with scalar FMAs, 8 lanes on the packed f32x2 FMA (FFMA2), and 4 lanes
+    that hold two tap segments each and add their partial sums first (= the xor-4 stage of the 8-lane butterfly).  Every
+    form performs the same roundings in the same order: notch error signal, DNR estimate, audio and audio spectrum are
+    the same bits, so the launcher is free to pick by list size (cfg3's 16 384 notch channels run the 4-lane form)."""
+    nc, nb = 40, 12
+    iq = bench.make_inputs("cfg5", 0, nc, nb)
+    outs = []
+    for lanes, packed in (("8", "0"), ("8", "1"), ("4", "0")):
+        monkeypatch.setenv("RDSP_NLMS_LANES", lanes)
         monkeypatch.setenv("RDSP_NLMS_PACKED", packed)
         bank = make_bank(rd, nc, rd.STAGE_ALL, max_blocks=4)
-        for c, p in enumerate(params):
-            bank.set_mode(c, 1, to_rd_params(rd, p))
+        for c in range(nc):
+            bank.set_mode(c, 1, rd.default_params(**bench.channel_params("cfg5", c)))
         o = [bank.process_host(iq[b:b + 4]) for b in range(0, nb, 4)]
         outs.append((np.concatenate(o), bank.read_debug_f32(4), bank.read_audio_spectrum()[0]))
-    for a, b in zip(outs[0], outs[1]):
-        assert np.array_equal(a, b)
+    for k in (1, 2):
+        for a, b in zip(outs[0], outs[k]):
+            assert np.array_equal(a, b), k
 
 
 def test_blocks_per_call_invariance(rd, po):
@@ -525,15 +551,16 @@ def test_extreme_inputs(rd, po):
 
 def test_level_collapse_with_a_noise_floor(rd, po):
     """keyed carrier over a noise floor (what CW does to the DNR all day).  At a 40 dB on/off ratio the conditioning of
-    the reference recurrence (gain mu / (energy + eps), energy kept as a running difference) already costs digits:
-    the oracle's sequential sums and ANY other f32 evaluation order agree to a few 1e-4 (the direct per-sample kernel,
-    RDSP_NLMS_IMPL=direct, gives the same figures as the grouped look-ahead one: tools/diag_collapse.py).  At 60 dB the
+    the reference recurrence (gain mu / (energy + eps), energy kept as a running difference) costs digits: the ORACLE
+    ITSELF moves by a few 1e-4 when its input moves by half an ulp.  The bar here is therefore the oracle's own
+    sensitivity: on identical inputs (the oracle's NLMS on the signal the GPU's K5 produced) the kernel stays within
+    1e-4 or within 4 x what a half-ulp input perturbation does to the oracle, whichever is larger.  At 60 dB the
     reference itself bursts above full scale and parity stops being defined; that case only has to stay finite."""
     nb, nc = 64, 4
     rng = np.random.default_rng(9)
     n = np.arange(nb * 128)
     key = ((n // 2646) % 2 == 0).astype(float)                              # 60 ms elements
-    for floor, tol, lsb in ((120.0, 5e-4, 32), (12.0, None, None)):
+    for floor, checked in ((120.0, True), (12.0, False)):
         iq = np.zeros((nb, nc, 128, 2), np.int16)
         for c in range(nc):
             amp = 12000.0 * key + floor
@@ -541,13 +568,20 @@ def test_level_collapse_with_a_noise_floor(rd, po):
             iq[:, c, :, 0] = np.rint(z.real).reshape(nb, 128)
             iq[:, c, :, 1] = np.rint(z.imag).reshape(nb, 128)
         params = [po.default_params(nr_kind=po.NR_LMS, nr_level=(20, 30, 40, 50)[c]) for c in range(nc)]
-        g_out, g_f32, o_out, o_f32, _, _ = run_both(rd, po, rd.STAGE_FFTFILT | rd.STAGE_NR, params, iq, blocks_per_call=8)
-        assert np.isfinite(g_f32[-8:]).all()                                # whatever happens in a burst, the channel recovers
-        if tol is not None:
-            assert np.isfinite(g_f32).all()
-            for c in range(nc):
-                assert rel_rms(g_f32[:, c, :, 0], o_f32[:, c, :, 0]) <= tol, (floor, c)
-            assert np.abs(g_out.astype(np.int32) - o_out).max() <= lsb
+        _, g_f5, _, _, _, _ = run_both(rd, po, rd.STAGE_FFTFILT, params, iq, blocks_per_call=8)
+        _, g_f6, _, _, _, _ = run_both(rd, po, rd.STAGE_FFTFILT | rd.STAGE_NR, params, iq, blocks_per_call=8)
+        assert np.isfinite(g_f6[-8:]).all()                                 # whatever happens in a burst, the channel recovers
+        if not checked:
+            continue
+        assert np.isfinite(g_f6).all()
+        for c in range(nc):
+            x = g_f5[:, c, :, 0]
+            mk = lambda: po.OracleChan(po.default_config(stage_mask=po.STAGE_FFTFILT | po.STAGE_NR), params[c])
+            want = mk().dnr_f32(x)
+            moved = mk().dnr_f32((x.astype(np.float64) * (1.0 + 2.0 ** -24 * rng.choice([-1.0, 1.0], x.shape))).astype(np.float32))
+            own = rel_rms(moved, want)                                      # the oracle against itself, input moved by half an ulp
+            err = rel_rms(g_f6[:, c, :, 0], want)
+            assert err <= max(REL_RMS_TOL, 4.0 * own), (c, err, own)
 
 
 def test_argument_errors_on_device(rd):
@@ -674,3 +708,26 @@ def test_graph_replay_is_bit_identical(rd, po, T):
     assert np.array_equal(a_out, b_out) and np.array_equal(a_s, b_s) and np.array_equal(a_as, b_as)
     assert b_rep == 0 and a_rep >= nb // T - 12, (a_rep, b_rep)      # 2 buffers x 2 phases, seen + captured, twice (tables changed once)
     assert a_l == b_l                                                 # a replay accounts for the kernels it runs
+
+
+@pytest.mark.parametrize("stage", ["fe", "fe_agc", "ff", "all"])
+def test_mono_layout_is_the_left_channel(rd, po, stage):
+    """cfg.audio_layout = RDSP_AUDIO_MONO: audio_out is [n_blocks][C][128] = L, bit for bit what the stereo layout puts into
+    its left channel — from every kernel that can end a chain (front end, AGC, FFT filter, DNR) — and the audio spectrum,
+    which reads the output rows, is unchanged.  Half the device-to-host bytes where L == R anyway."""
+    sm = {"fe": rd.STAGE_FRONTEND, "fe_agc": rd.STAGE_FRONTEND | rd.STAGE_NOTCH | rd.STAGE_AGC | rd.STAGE_SPEC1024,
+          "ff": rd.STAGE_FFTFILT | rd.STAGE_NR, "all": rd.STAGE_ALL}[stage]
+    nc, nb = 45, 16
+    iq = bench.make_inputs("cfg5", 0, nc, nb)
+    res = []
+    for layout in (rd.AUDIO_STEREO, rd.AUDIO_MONO):
+        cfg = rd.default_config(n_channels=nc, stage_mask=sm, max_blocks_per_call=8, io_location=rd.IO_HOST, audio_layout=layout)
+        bank = rd.ReceiverBank(cfg)
+        for c in range(nc):
+            bank.set_mode(c, 1, rd.default_params(**bench.channel_params("cfg5", c)))
+        out = np.concatenate([bank.process_host(iq[b:b + 8]) for b in range(0, nb, 8)])
+        res.append((out, bank.read_audio_spectrum()[0] if sm & rd.STAGE_SPEC1024 else None))
+    (st, st_spec), (mo, mo_spec) = res
+    assert mo.shape == (nb, nc, 128) and np.array_equal(mo, st[..., 0])
+    if st_spec is not None:
+        assert np.array_equal(st_spec, mo_spec) and st_spec.any()
