@@ -273,7 +273,7 @@ def cpu_chain(workload: str, n_channels: int, T: int, n_steps: int, n_warm: int 
     return ms, build, cores
 
 
-def cpu_reference_stages(n_blocks: int = 2048):
+def cpu_reference_stages(n_blocks: int = 16384):
     """kind "reference": the stages whose sources ARE in the reference tree — doConvolutionalProcessing (K5 + K6 + K7, DNR
     level 30) and AudioAnalyzeFFT256IQ::update (K9) — compiled unmodified (oracle/_ref, built in the build container: the
     reference tree does not travel), one private copy of the library per host thread because its state is file-scope
@@ -342,65 +342,64 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    import radiodsp_sdr_rx_b200 as rd
+class Gpu:
+    """one rank's device context: stream, barrier, max-over-ranks"""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback (use --impl reference for the CPU chain)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        # NCCL's banner ("NCCL version ...") goes to stdout by default: keep stdout to the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback (use --impl reference for the CPU chain)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            # NCCL's banner ("NCCL version ...") goes to stdout by default: keep stdout to the ONE JSON line
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+            dist.init_process_group("nccl", device_id=self.dev)
+        # a real (non-default) stream: the C ABI takes NULL to mean "the handle's own stream", and CUDA events must be
+        # recorded on the stream the kernels are launched on
+        self.stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.stream)
+        assert self.stream.cuda_stream != 0
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)      # > 126 MB L2
 
-    def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(device_ids=[self.local])
+        self.torch.cuda.synchronize()
 
-    wl = args.workload
-    desc, stage, c_default = WORKLOADS[wl]
-    C_ = args.channels or c_default
-    T = args.blocks_per_call
-    K, W = args.steps, args.warmup
-    ch0, _ = rank_channel_range(rank, C_)             # contiguous channel range of this rank
-    NB = args.input_batches
+    def max_ms(self, ms: float) -> float:
+        return max_over_ranks(ms, self.dist if self.world > 1 else None, self.dev)
 
-    iq_host = make_inputs(wl, ch0, C_, NB * T)        # [NB*T, C, 128, 2]
-    d_in = torch.from_numpy(iq_host).to(dev).view(NB, T, C_, BLK, 2)
-    d_out = torch.zeros((T, C_, BLK, 2), dtype=torch.int16, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)            # > 126 MB L2
 
-    def new_bank(io):
-        cfg = rd.default_config(n_channels=C_, device=local, stage_mask=stage, max_blocks_per_call=T, io_location=io,
-                                pipeline_chunks=args.pipeline_chunks)
-        cfg.async_ = 1
-        b = rd.ReceiverBank(cfg)
-        # runs of identical parameters -> one set_mode per run would be ideal; the configs cycle with small periods,
-        # so set one period and let the library dedupe masks
-        for c in range(C_):
-            b.set_mode(c, 1, rd.default_params(**channel_params(wl, ch0 + c)))
-        return b
+def new_bank(gpu, rd, wl, C_, T, io, ch0, layout=0, pipeline_chunks=0):
+    cfg = rd.default_config(n_channels=C_, device=gpu.local, stage_mask=WORKLOADS[wl][1], max_blocks_per_call=T, io_location=io,
+                            pipeline_chunks=pipeline_chunks, audio_layout=layout)
+    cfg.async_ = 1
+    b = rd.ReceiverBank(cfg)
+    for c in range(C_):                               # the library ignores repeats and de-duplicates masks
+        b.set_mode(c, 1, rd.default_params(**channel_params(wl, ch0 + c)))
+    b.set_stream(gpu.stream.cuda_stream)
+    return b
 
-    # a real (non-default) stream: the C ABI takes NULL to mean "the handle's own stream", and CUDA events must be
-    # recorded on the stream the kernels are launched on
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    bank = new_bank(rd.IO_DEVICE)
-    bank.set_stream(stream.cuda_stream)
+
+def measure_device(gpu, rd, wl, C_, T, K, W, NB, iq_host, sample_clocks=False, pipeline_chunks=0):
+    """device-resident throughput of one workload + per-kernel device times.  Inputs already in HBM, L2 flushed between
+    timed steps (outside the per-step events), CUDA events on the launching stream, max over ranks."""
+    torch = gpu.torch
+    ch0, _ = rank_channel_range(gpu.rank, C_)
+    d_in = torch.from_numpy(iq_host).to(gpu.dev).view(NB, T, C_, BLK, 2)
+    d_out = torch.zeros((T, C_, BLK, 2), dtype=torch.int16, device=gpu.dev)
+    bank = new_bank(gpu, rd, wl, C_, T, rd.IO_DEVICE, ch0, pipeline_chunks=pipeline_chunks)
 
     def step(i):
         bank.process_blocks(T, d_in[i % NB], d_out)
 
-    # ---- device-resident throughput ------------------------------------------------------------
-    sampler = ClockSampler(local)                      # nvidia-smi takes a moment to start: launch it before the warm-up
+    sampler = ClockSampler(gpu.local) if sample_clocks else None     # nvidia-smi takes a moment to start: launch it before the warm-up
     # initialisation, before the warm-up: the library captures a call shape (buffers x ping-pong phase) into a CUDA graph
     # the second time it sees it; let every shape of the rotation be seen twice so that the W warm-up steps and the K
     # timed steps all run the way steady state does (one cudaGraphLaunch per call)
@@ -409,139 +408,230 @@ def run_b200(args):
     torch.cuda.synchronize()
     for i in range(W):
         step(i)
-    barrier()
-    replays0 = bank.graph_replays
+    gpu.barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    launches0 = bank.kernel_launches
+    launches0, replays0 = bank.kernel_launches, bank.graph_replays
     t_wall0 = time.time()
     no_flush = bool(os.environ.get("RDSP_BENCH_NO_FLUSH"))      # experiments only (the reported numbers always flush)
     for i in range(K):
         if not no_flush:
-            flush.zero_()                              # L2 flush between timed iterations (outside the per-step events)
-        ev[i][0].record(stream)
+            gpu.flush.zero_()                          # L2 flush between timed iterations (outside the per-step events)
+        ev[i][0].record(gpu.stream)
         step(W + i)
-        ev[i][1].record(stream)
-    barrier()
+        ev[i][1].record(gpu.stream)
+    gpu.barrier()
     t_wall1 = time.time()
-    launches = bank.kernel_launches - launches0
-    graph_replays = bank.graph_replays - replays0
-    # the timed region of a short run can fall between two nvidia-smi samples (200 ms period; faster polling measurably slows kernel launches): keep the SAME load up,
-    # untimed, until at least three samples were taken under it, and report over [start of the timed region, end of load]
-    t_load1 = t_wall1
-    extended = 0
-    if sampler.proc is not None:
-        deadline = time.time() + 3.0
-        i = 0
-        while time.time() < deadline:
-            n_in = sum(1 for t, _ in sampler.rows if t_wall0 <= t <= time.time())
-            if n_in >= 3:
-                break
-            step(W + K + i); i += 1
-            if i % 8 == 0:
-                torch.cuda.synchronize()
-        torch.cuda.synchronize()
-        extended = i
-        if extended:
-            t_load1 = time.time()
-    clocks = sampler.stop(t_wall0, t_load1)
-    clocks["window"] = "timed region" if not extended else f"timed region + {extended} more of the same steps, untimed, until 3 samples"
+    res = {"launches": bank.kernel_launches - launches0, "graph_replays": bank.graph_replays - replays0}
+    if sampler is not None:
+        # the timed region of a short run can fall between two nvidia-smi samples (200 ms period; faster polling measurably
+        # slows kernel launches): keep the SAME load up, untimed, until at least three samples were taken under it, and
+        # report over [start of the timed region, end of load]
+        t_load1, extended = t_wall1, 0
+        if sampler.proc is not None:
+            deadline = time.time() + 3.0
+            i = 0
+            while time.time() < deadline:
+                if sum(1 for t, _ in sampler.rows if t_wall0 <= t <= time.time()) >= 3:
+                    break
+                step(W + K + i); i += 1
+                if i % 8 == 0:
+                    torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            extended = i
+            if extended:
+                t_load1 = time.time()
+        clocks = sampler.stop(t_wall0, t_load1)
+        clocks["window"] = "timed region" if not extended else f"timed region + {extended} more of the same steps, untimed, until 3 samples"
+        res["clocks"] = clocks
     ms_steps = [a.elapsed_time(b) for a, b in ev]
-    ms_total = float(sum(ms_steps))
-    ms_total_max = max_over_ranks(ms_total, dist if world > 1 else None, dev)
-    samples = world * C_ * T * BLK * K
-    value = samples / (ms_total_max * 1e-3) / 1e6      # MS/s
-
-    # ---- per-kernel device times (CUDA events on the launching stream, same steps, L2 flushed) ---
+    ms_total_max = gpu.max_ms(float(sum(ms_steps)))
+    res.update(ms_steps=ms_steps, ms_per_step=ms_total_max / K,
+               value=gpu.world * C_ * T * BLK * K / (ms_total_max * 1e-3) / 1e6)
+    # per-kernel device times (CUDA events on the launching stream, same steps, L2 flushed, kernel by kernel)
     bank.profile(True)
     for i in range(K):
-        flush.zero_()
+        gpu.flush.zero_()
         step(W + K + i)
     torch.cuda.synchronize()
-    prof = {k: v for k, v in bank.profile_read().items() if v["launches"] > 0}
+    res["prof"] = {k: v for k, v in bank.profile_read().items() if v["launches"] > 0}
     bank.profile(False)
+    bank.close()
+    return res
 
-    # ---- end to end through the C ABI with pinned host buffers ----------------------------------
-    e2e_bank = new_bank(rd.IO_HOST)
-    e2e_bank.set_stream(stream.cuda_stream)
+
+def measure_e2e(gpu, rd, wl, C_, T, K, W, NB, iq_host, layout):
+    """the same metric through the C-ABI call with pinned HOST buffers: H2D of the step's input and D2H of its audio inside
+    the timed region, every step"""
+    torch = gpu.torch
+    ch0, _ = rank_channel_range(gpu.rank, C_)
+    bank = new_bank(gpu, rd, wl, C_, T, rd.IO_HOST, ch0, layout=layout)
     h_in = torch.from_numpy(iq_host).view(NB, T, C_, BLK, 2).pin_memory()
-    h_out = torch.zeros((2, T, C_, BLK, 2), dtype=torch.int16).pin_memory()
-    for i in range(max(W, 1) + 8):                     # (+ 8: both staging buffers x both phases seen twice, see above)
-        e2e_bank.process_blocks(T, h_in[i % NB], h_out[i % 2])
-    barrier()
+    out_shape = (2, T, C_, BLK) if layout else (2, T, C_, BLK, 2)
+    h_out = torch.zeros(out_shape, dtype=torch.int16).pin_memory()
+    for i in range(max(W, 1) + 8):                     # (+ 8: both staging buffers x both phases seen twice: graphs captured)
+        bank.process_blocks(T, h_in[i % NB], h_out[i % 2])
+    bank.synchronize()
+    gpu.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    e0.record(gpu.stream)
     for i in range(K):
-        e2e_bank.process_blocks(T, h_in[(W + i) % NB], h_out[i % 2])
-    e2e_bank.stream_join()                             # the last device-to-host copies are part of the timed region
-    e1.record(stream)
-    e2e_bank.synchronize()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1), dist if world > 1 else None, dev)
-    e2e_value = samples / (e2e_ms * 1e-3) / 1e6
-    io_bytes = T * C_ * BLK * 2 * 2
+        bank.process_blocks(T, h_in[(W + i) % NB], h_out[i % 2])
+    bank.stream_join()                                 # the last device-to-host copies are part of the timed region
+    e1.record(gpu.stream)
+    bank.synchronize()
+    gpu.barrier()
+    ms = gpu.max_ms(e0.elapsed_time(e1))
+    in_bytes = T * C_ * BLK * 2 * 2
+    out_bytes = in_bytes // 2 if layout else in_bytes
+    bank.close()
+    # copy-only ceiling: the same pinned buffers and byte counts, H2D and D2H concurrently on two streams, every rank at once
+    d_a = torch.empty(in_bytes, dtype=torch.uint8, device=gpu.dev)
+    d_b = torch.empty(out_bytes, dtype=torch.uint8, device=gpu.dev)
+    s_in, s_out = torch.cuda.Stream(device=gpu.dev), torch.cuda.Stream(device=gpu.dev)
+    hv_in = h_in.view(torch.uint8).view(NB, -1)
+    hv_out = h_out.view(torch.uint8).view(2, -1)
+
+    def copies(n):
+        for i in range(n):
+            with torch.cuda.stream(s_in):
+                d_a.copy_(hv_in[i % NB], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hv_out[i % 2].copy_(d_b, non_blocking=True)
+
+    copies(3)
+    gpu.barrier()
+    c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    c0.record(gpu.stream)
+    s_in.wait_stream(gpu.stream); s_out.wait_stream(gpu.stream)
+    copies(K)
+    gpu.stream.wait_stream(s_in); gpu.stream.wait_stream(s_out)
+    c1.record(gpu.stream)
+    gpu.barrier()
+    ceil_ms = gpu.max_ms(c0.elapsed_time(c1))
+    samples = gpu.world * C_ * T * BLK * K
+    v, ceil_v = samples / (ms * 1e-3) / 1e6, samples / (ceil_ms * 1e-3) / 1e6
+    return {"value": v, "unit": "MS/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+            "audio_layout": "mono (L)" if layout else "stereo (L,R)",
+            "ceiling": {"value": ceil_v, "unit": "MS/s", "GB_s_each_way_all_ranks": [gpu.world * in_bytes * K / (ceil_ms * 1e-3) / 1e9, gpu.world * out_bytes * K / (ceil_ms * 1e-3) / 1e9],
+                        "what": "copy only: the same pinned buffers and byte counts per step, H2D and D2H concurrently on two streams, every rank at once, max over ranks"},
+            "frac_of_ceiling": v / ceil_v}
+
+
+def kernel_table(wl, C_, T, K, prof):
+    ab = algorithmic_bytes(wl, T)
+    tot = max(sum(v["ms"] for v in prof.values()), 1e-12)
+    kernels = {}
+    for kname, v in prof.items():
+        per_launch_ms = v["ms"] / v["launches"]
+        bytes_launch = ab.get(kname, 0.0) * C_ * T
+        kernels[kname] = {"ms_per_launch": per_launch_ms, "share": v["ms"] / tot,
+                          "alg_gb_s": bytes_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None}
+    return kernels, ab, (max(prof, key=lambda k: prof[k]["ms"]) if prof else None)
+
+
+def roofline_of(dom, wl, C_, T, prof, ab):
+    """the dominant kernel against the HBM roofline the contract asks for, and against the pipe that actually binds it:
+    the CUDA-core FMA pipe for the recurrences and FFTs, the int8 TENSOR pipe for the tcgen05 front end"""
+    peak, peak_src, sm_max = measured_peaks()
+    per_launch_ms = prof[dom]["ms"] / prof[dom]["launches"]
+    bytes_launch = ab.get(dom, 0.0) * C_ * T
+    achieved = bytes_launch / (per_launch_ms * 1e-3) / 1e9
+    frac_ch = {"k_nlms_notch": 0.25 if wl == "cfg5" else 1.0, "k_nlms_dnr": 0.8 if wl == "cfg5" else 1.0}.get(dom, 1.0)
+    if dom == "k_front":
+        # 4 byte-plane products per q15 product, K padded 129 -> 160: int8 MACs issued per channel-block; dense int8 peak = 2 x the
+        # measured bf16 burst (same tensor pipe, half the operand width)
+        ops = 3 * 128 * 160 * 4 * 2.0
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        pipe_peak = 2.0 * float(p.get("bf16_tflops", 1590.0)) * 1e12
+        pipe = {"pipe": "tensor (tcgen05 kind::i8)", "achieved_Tops": ops * C_ * T / (per_launch_ms * 1e-3) / 1e12, "peak_Tops": pipe_peak / 1e12,
+                "frac": ops * C_ * T / (per_launch_ms * 1e-3) / pipe_peak, "peak_source": "2 x measured bf16 burst (MEASURED_PEAKS.json)"}
+        binding = "tcgen05 kind::i8 tensor pipe at small N (per-instruction cost of N = 32 MMAs), not HBM — see DESIGN.md 4a"
+    else:
+        pipe_peak = 148 * 128 * sm_max * 1e6                     # lane-ops/s of the FP32/INT32 FMA pipe at max clock
+        pipe_ach = PIPE_OPS.get(dom, 0) * frac_ch * C_ * T / (per_launch_ms * 1e-3)
+        pipe = {"pipe": "fp32/int32 FMA (CUDA cores)", "achieved_Tlaneops": pipe_ach / 1e12, "peak_Tlaneops": pipe_peak / 1e12, "frac": pipe_ach / pipe_peak}
+        binding = "fp32/int32 pipe and recurrence latency (sequential NLMS / AGC, q15 FFTs), not HBM — see DESIGN.md"
+    return {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": ncu_traffic(dom, wl, C_, T), "peak_source": peak_src, "alg_bytes_per_channel_block": ab.get(dom),
+            "ms_per_launch": per_launch_ms, "binding": binding, "pipe": pipe}
+
+
+def run_b200(args):
+    import radiodsp_sdr_rx_b200 as rd
+    gpu = Gpu()
+    torch, world, rank = gpu.torch, gpu.world, gpu.rank
+    wl = args.workload
+    C_ = args.channels or WORKLOADS[wl][2]
+    T, K, W, NB = args.blocks_per_call, args.steps, args.warmup, args.input_batches
+    ch0, _ = rank_channel_range(rank, C_)             # contiguous channel range of this rank (SURVEY.md 8e)
+    iq_host = make_inputs(wl, ch0, C_, NB * T)        # [NB*T, C, 128, 2]
+
+    main = measure_device(gpu, rd, wl, C_, T, K, W, NB, iq_host, sample_clocks=True, pipeline_chunks=args.pipeline_chunks)
+    e2e = measure_e2e(gpu, rd, wl, C_, T, K, W, NB, iq_host, layout=0)
+    e2e_mono = measure_e2e(gpu, rd, wl, C_, T, K, W, NB, iq_host, layout=1)
+
+    # the other BASELINE configs, compact (N = 1 only: the scaling runs are about the default workload)
+    others = {}
+    if world == 1 and not args.no_other_configs:
+        for o in sorted(WORKLOADS):
+            if o == wl:
+                continue
+            oc = WORKLOADS[o][2]
+            r = measure_device(gpu, rd, o, oc, T, max(5, min(K, 10)), max(3, min(W, 5)), 2, make_inputs(o, 0, oc, 2 * T))
+            kern, ab_o, dom_o = kernel_table(o, oc, T, 0, r["prof"])
+            peak = measured_peaks()[0]
+            step_bytes = ab_o["_step"] * oc * T
+            others[o] = {"channels_per_gpu": oc, "blocks_per_call": T, "value": r["value"], "unit": "MS/s", "ms_per_step": r["ms_per_step"],
+                         "realtime_channels": r["value"] / 0.0441, "dominant_kernel": dom_o,
+                         "dominant_ms_per_launch": kern[dom_o]["ms_per_launch"] if dom_o else None,
+                         "dominant_hbm_frac": (kern[dom_o]["alg_gb_s"] or 0.0) / peak if dom_o else None,
+                         "step_hbm_frac": step_bytes / (r["ms_per_step"] * 1e-3) / 1e9 / peak,
+                         "kernels_us": {k: round(v["ms_per_launch"] * 1e3, 1) for k, v in kern.items()}}
 
     if rank == 0:
-        peak, peak_src, sm_max = measured_peaks()
-        ab = algorithmic_bytes(wl, T)
-        dom = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
-        roof = None
-        kernels = {}
-        step_ms_prof = sum(v["ms"] for v in prof.values()) / max(K, 1)
-        for kname, v in prof.items():
-            per_launch_ms = v["ms"] / v["launches"]
-            bytes_launch = ab.get(kname, 0.0) * C_ * T
-            kernels[kname] = {"ms_per_launch": per_launch_ms, "share": v["ms"] / max(sum(x["ms"] for x in prof.values()), 1e-12),
-                              "alg_gb_s": bytes_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None}
-        if dom:
-            per_launch_ms = prof[dom]["ms"] / prof[dom]["launches"]
-            bytes_launch = ab.get(dom, 0.0) * C_ * T
-            achieved = bytes_launch / (per_launch_ms * 1e-3) / 1e9
-            pipe_peak = 148 * 128 * sm_max * 1e6                     # lane-ops/s of the FP32/INT32 FMA pipe at max clock
-            frac_ch = {"k_nlms_notch": 0.25 if wl == "cfg5" else 1.0, "k_nlms_dnr": 0.8 if wl == "cfg5" else 1.0}.get(dom, 1.0)
-            pipe_ach = PIPE_OPS.get(dom, 0) * frac_ch * C_ * T / (per_launch_ms * 1e-3)
-            roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": ncu_traffic(dom, wl, C_, T), "peak_source": peak_src, "alg_bytes_per_channel_block": ab.get(dom),
-                    "ms_per_launch": per_launch_ms,
-                    "binding": ("tcgen05 kind::i8 tensor pipe fed from shared memory (operand fetch bound), not HBM — see DESIGN.md"
-                                if dom == "k_front" else "fp32/int32 pipe and recurrence latency (sequential NLMS / AGC, q15 FFTs), not HBM — see DESIGN.md"),
-                    "pipe": {"achieved_Tlaneops": pipe_ach / 1e12, "peak_Tlaneops": pipe_peak / 1e12, "frac": pipe_ach / pipe_peak}}
+        peak, peak_src, _ = measured_peaks()
+        prof = main["prof"]
+        kernels, ab, dom = kernel_table(wl, C_, T, K, prof)
+        value, ms_step = main["value"], main["ms_per_step"]
         step_bytes = ab["_step"] * C_ * T
         line = {
             "metric": "aggregate MS/s (real-time 44.1 kS/s channels sustained = value / 0.0441)",
             "value": value, "unit": "MS/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "q15+f32", "data": "synthetic",
-            "ms_step_min_median_max": [float(np.min(ms_steps)), float(np.median(ms_steps)), float(np.max(ms_steps))],
-            **({"ms_steps": [round(float(x), 3) for x in ms_steps]} if os.environ.get("RDSP_BENCH_STEPS") else {}),
-            "config": {"workload": f"{wl}: {desc}", "channels_per_gpu": C_, "channels_total": world * C_, "blocks_per_call": T, "pipeline_chunks": args.pipeline_chunks or "auto",
-                       "block_samples": BLK, "sample_rate_hz": FS, "sharding": "contiguous channel ranges, no collective on the hot path",
-                       "l2": "256 MiB memset between timed steps; per-step CUDA events summed",
-                       "realtime_channels": value / 0.0441, "realtime_channels_e2e": e2e_value / 0.0441,
-                       "realtime_margin_per_gpu": (value / world) / (C_ * 0.0441)},
-            "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes},
-            "gpu_launches": int(launches),
-            "graph_replays": int(graph_replays),       # timed calls that ran as one cudaGraphLaunch (the rest: kernel by kernel)
-            "clocks": clocks,
-            "roofline": roof,
-            "roofline_step": {"bound": "hbm", "achieved": step_bytes / (ms_total_max / K * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                              "frac": step_bytes / (ms_total_max / K * 1e-3) / 1e9 / peak, "alg_bytes_per_channel_block": ab["_step"]},
+            "ms_step_min_median_max": [float(np.min(main["ms_steps"])), float(np.median(main["ms_steps"])), float(np.max(main["ms_steps"]))],
+            **({"ms_steps": [round(float(x), 3) for x in main["ms_steps"]]} if os.environ.get("RDSP_BENCH_STEPS") else {}),
+            "config": workload_config(wl, C_, world, T),
+            "derived": {"realtime_channels": value / 0.0441, "realtime_channels_e2e": e2e["value"] / 0.0441,
+                        "realtime_margin_per_gpu": (value / world) / (C_ * 0.0441), "pipeline_chunks": args.pipeline_chunks or "library default (1 channel group)"},
+            "e2e": e2e,
+            "e2e_mono": e2e_mono,
+            "gpu_launches": int(main["launches"]),
+            "graph_replays": int(main["graph_replays"]),       # timed calls that ran as one cudaGraphLaunch (the rest: kernel by kernel)
+            "clocks": main["clocks"],
+            "roofline": roofline_of(dom, wl, C_, T, prof, ab) if dom else None,
+            "roofline_step": {"bound": "hbm", "achieved": step_bytes / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak, "alg_bytes_per_channel_block": ab["_step"]},
             "kernels": kernels,
-            "profiled_step_ms": step_ms_prof,
+            "profiled_step_ms": sum(v["ms"] for v in prof.values()) / max(K, 1),
+            "other_configs": others,
         }
         if world == 1 and not args.no_cpu:
-            cores = host_cores()
-            cpt = max(1, args.cpu_channels_per_thread)
-            cpu_chain(wl, cores, cpt, 4)                             # warm the pages
-            v, dt = cpu_chain(wl, cores, cpt, args.cpu_blocks, reps=args.cpu_reps)
+            # a bounded sample of the SAME step shape (all channels x T blocks), about 10 - 20 s of CPU work
+            ms1, build, cores = cpu_chain(wl, C_, T, 1, n_warm=1)
+            n = int(max(3, min(60, 12e3 / max(ms1[0], 1.0))))
+            ms, build, cores = cpu_chain(wl, C_, T, n, n_warm=0)
+            v = C_ * T * BLK * len(ms) / (sum(ms) * 1e-3) / 1e6
             line["cpu_baseline"] = {"value": v, "unit": "MS/s", "cores": cores, "kind": "port",
-                                    "sample": f"{cores} threads x {cpt} channels x {args.cpu_blocks} blocks x {args.cpu_reps} reps ({dt:.1f} s); "
-                                              "single-channel state sits in L1/L2, which flatters the CPU"}
+                                    "sample": f"{len(ms)} steps of the GPU arm's shape: {cores} threads x {C_} channels x {T} blocks of the {wl} chain "
+                                              f"({sum(ms) * 1e-3:.1f} s); oracle port built {build}"}
+            line["cpu_baseline_reference"] = cpu_reference_stages()
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier(device_ids=[local])
-        dist.destroy_process_group()
+        gpu.dist.barrier(device_ids=[gpu.local])
+        gpu.dist.destroy_process_group()
 
 
 def main():
@@ -555,10 +645,8 @@ def main():
     ap.add_argument("--blocks-per-call", type=int, default=8)
     ap.add_argument("--input-batches", type=int, default=4)
     ap.add_argument("--pipeline-chunks", type=int, default=0, help="wavefront chunks per call (0 = library default)")
-    ap.add_argument("--cpu-channels-per-thread", type=int, default=32)
-    ap.add_argument("--cpu-blocks", type=int, default=64)
-    ap.add_argument("--cpu-reps", type=int, default=96, help="repetitions of the CPU sample (default: about 12 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the compact runs of the other BASELINE configs (N = 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

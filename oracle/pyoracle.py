@@ -18,7 +18,8 @@ import tempfile
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liboracle.so")
+# RDSP_ORACLE_LIB: another build of the same sources (bench.py times a -march=native one; parity always uses the portable build)
+LIB_PATH = os.environ.get("RDSP_ORACLE_LIB") or os.path.join(HERE, "liboracle.so")
 REF_PATH = os.path.join(HERE, "_ref", "librdsp_ref.so")
 
 BLK = 128

@@ -425,7 +425,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
     const bool fe = has(h, RDSP_STAGE_FRONTEND), notch = has(h, RDSP_STAGE_NOTCH), agc = has(h, RDSP_STAGE_AGC);
     const bool ff = has(h, RDSP_STAGE_FFTFILT), nr = has(h, RDSP_STAGE_NR);
     const int C = h->C;
-    const bool mono = h->cfg.audio_layout == RDSP_AUDIO_MONO;          // audio = [T][C][128] (L only) instead of [T][C][128][2]
+    const bool mono_out = h->cfg.audio_layout == RDSP_AUDIO_MONO;      // audio = [T][C][128] (L only) instead of [T][C][128][2]
     const RdspTick *tick_in = h->d_tick + par;
     RdspTick *tick_out = h->d_tick + (par ^ 1);
     int G = 1;
@@ -449,7 +449,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
         if (piped) CK(cudaStreamWaitEvent(s_front, h->ev_fork, 0));
         front_last = !(notch || agc || ff);
         FrontArgs a{};
-        a.iq = iq; a.out_mono = front_last ? (mono ? audio : nullptr) : h->d_mid_a; a.out_stereo = (front_last && !mono) ? audio : nullptr;
+        a.iq = iq; a.out_mono = front_last ? (mono_out ? audio : nullptr) : h->d_mid_a; a.out_stereo = (front_last && !mono_out) ? audio : nullptr;
         a.dbg = front_last ? dbg : nullptr; a.par = h->d_par; a.taps = h->d_taps; a.C = C; a.T = T;
         Prof pr(h, KK_FRONT, s_front);
         if (h->front_tc) {
@@ -492,7 +492,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
             mono = h->d_mid_a;
             if (notch || agc) {
                 AgcArgs ag{};
-                ag.out_mono = ff ? h->d_mid_b : (mono ? audio : nullptr); ag.out_stereo = (ff || mono) ? nullptr : audio;
+                ag.out_mono = ff ? h->d_mid_b : (mono_out ? audio : nullptr); ag.out_stereo = (ff || mono_out) ? nullptr : audio;
                 ag.dbg = ff ? nullptr : dbg; ag.env = h->d_agc_env; ag.par = h->d_par; ag.C = C; ag.T = T;
                 ag.agc_stage = agc ? 1 : 0;
                 ag.target = h->cfg.agc_target; ag.max_gain = h->cfg.agc_max_gain; ag.alpha_a = h->agc_alpha_a;
@@ -518,7 +518,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
         }
         if (ff) {
             FftFiltArgs f{};
-            f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq; f.out_stereo = mono ? nullptr : audio; f.out_mono = mono ? audio : nullptr; f.out_f32_L = h->d_scr;
+            f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq; f.out_stereo = mono_out ? nullptr : audio; f.out_mono = mono_out ? audio : nullptr; f.out_f32_L = h->d_scr;
             f.dbg = dbg; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256; f.sin512 = h->d_sin512;
             f.par = h->d_par; f.C = C; f.T = T; f.list = cls_list; f.ch0 = c0; f.n = cls_n; f.nr_stage = nr ? 1 : 0;
             { Prof pr(h, KK_FFTFILT, cs); launch_fftfilt(f, cs); }
@@ -530,7 +530,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
                 if (n_dnr > 0) {
                     NlmsArgs n{};
                     n.list = dl + f_dnr; n.n_list = n_dnr; n.C = C; n.T = T;
-                    n.in_f32 = h->d_scr; n.out_stereo = mono ? nullptr : audio; n.out_mono = mono ? audio : nullptr; n.dbg = dbg;
+                    n.in_f32 = h->d_scr; n.out_stereo = mono_out ? nullptr : audio; n.out_mono = mono_out ? audio : nullptr; n.dbg = dbg;
                     n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
                     n.par = h->d_par; n.mode = 1; n.contended = nlms_contended; n.direct = h->nlms_direct;
                     { Prof pr(h, KK_DNR, cs); launch_nlms(n, cs); }
@@ -539,7 +539,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
         }
         if (has(h, RDSP_STAGE_SPEC1024)) {
             Spec1024Args s1{};
-            s1.audio = audio; s1.audio_mono = mono ? 1 : 0; s1.ring = h->d_ring; s1.output = h->d_spec1024_out; s1.C = C; s1.T = T;
+            s1.audio = audio; s1.audio_mono = mono_out ? 1 : 0; s1.ring = h->d_ring; s1.output = h->d_spec1024_out; s1.C = C; s1.T = T;
             s1.list = cls_list; s1.ch0 = c0; s1.n = cls_n;
             s1.tick_in = tick_in; s1.tick_out = tick_out; s1.tw = h->d_tw; s1.win = h->d_win1024;
             { Prof pr(h, KK_SPEC1024, cs); launch_spec1024(s1, cs); }
