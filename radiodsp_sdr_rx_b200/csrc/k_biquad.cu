@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(32) k_biquad(BiquadArgs a)
         bprev = (uint32_t)st[0]; aprev = (uint32_t)st[1]; sum = st[2];
     }
     const int32_t b0 = a.b0, b1 = a.b1, b2 = a.b2, a1 = a.a1, a2 = a.a2;
+    const int32_t a1h = a1 >> 16, a1l = a1 & 0xFFFF;       // a1 = 65536 a1h + a1l, a1l unsigned
     const unsigned sh = iq ? 0u : 16u;                      // brings this stream's half-word to the top
 
     auto issue_load = [&](int t, int buf) {
@@ -82,18 +83,19 @@ __global__ void __launch_bounds__(32) k_biquad(BiquadArgs a)
                 for (int h = 0; h < 2; h++) {
                     const uint32_t x0 = (w[2 * h] << sh) & 0xFFFF0000u;        // earlier sample, in the top half
                     const uint32_t x1 = (w[2 * h + 1] << sh) & 0xFFFF0000u;    // later sample
-                    sum = mlaw(b0, x0, sum);
-                    sum = mlaw(b1, bprev & 0xFFFF0000u, sum);
-                    sum = mlaw(b2, bprev << 16, sum);
-                    sum = mlaw(a1, aprev & 0xFFFF0000u, sum);
-                    sum = mlaw(a2, aprev << 16, sum);
+                    // The accumulator wraps mod 2^32, so the ten MACs of a sample pair may be added in any order: everything
+                    // that does not depend on the newest output is summed OFF the recurrence (pre0, pre1), and what stays
+                    // on it per sample is a1 * (previous output) -> add -> >> 14 -> saturate.  That one product is done as
+                    // two full-rate IMADs ((a1 o) >> 16 = a1h o + ((a1l o) >> 16), exact) instead of a quarter-rate IMAD.HI.
+                    const uint32_t pre0 = (uint32_t)__mulhi(b0, (int32_t)x0) + (uint32_t)__mulhi(b1, (int32_t)(bprev & 0xFFFF0000u)) +
+                                          (uint32_t)__mulhi(b2, (int32_t)(bprev << 16)) + (uint32_t)__mulhi(a2, (int32_t)(aprev << 16));
+                    const uint32_t pre1 = (uint32_t)__mulhi(b0, (int32_t)x1) + (uint32_t)__mulhi(b1, (int32_t)x0) +
+                                          (uint32_t)__mulhi(b2, (int32_t)(bprev & 0xFFFF0000u)) + (uint32_t)__mulhi(a2, (int32_t)(aprev & 0xFFFF0000u));
+                    const int32_t o_prev = (int32_t)aprev >> 16;               // the newest output so far
+                    sum = (int32_t)((uint32_t)sum + pre0 + (uint32_t)(a1h * o_prev + ((a1l * o_prev) >> 16)));
                     const int32_t o_lo = sat16(sum >> 14);
                     sum &= 0x3FFF;
-                    sum = mlaw(b0, x1, sum);
-                    sum = mlaw(b1, x0, sum);
-                    sum = mlaw(b2, bprev & 0xFFFF0000u, sum);
-                    sum = mlaw(a1, (uint32_t)o_lo << 16, sum);
-                    sum = mlaw(a2, aprev & 0xFFFF0000u, sum);
+                    sum = (int32_t)((uint32_t)sum + pre1 + (uint32_t)(a1h * o_lo + ((a1l * o_lo) >> 16)));
                     const int32_t o_hi = sat16(sum >> 14);
                     sum &= 0x3FFF;
                     bprev = (x0 >> 16) | x1;

@@ -74,7 +74,8 @@ constexpr int TM_RING = 0, TM_PLANE = 48;
 constexpr int TM_ACC1B = 192, TM_ACC2P = 384;
 
 // mbarriers (index = chunk parity unless single):
-constexpr int B_IN_FULL = 0, B_M1_DONE = 2, B_E1_DONE = 4, B_M2_DONE = 6, B_E2_DONE = 8;
+constexpr int B_IN_FULL = 0, B_M1_DONE = 2, B_E1_DONE = 4, B_M2_DONE = 6, B_E2_DONE = 8, B_TAPS = 9;
+constexpr int TOEP_ROW_B = 256, TOEP_ROWS_PER_SET = TOEP_SET_B / TOEP_ROW_B;   // the table as a 2-D byte tensor for TMA
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 @4, a_format @7, b_format @10 (1 = signed),
 // K-major A and B, N >> 3 @17, M >> 4 @24
@@ -118,6 +119,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
                  "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+// bounded wait for the one-shot barriers of the prologue: a descriptor or byte-count mistake must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity)
+{
+    for (uint32_t spin = 0; spin < (1u << 24); spin++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+// TMA: one box of a 2-D tensor, global -> shared, completion on an mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -451,7 +473,7 @@ __device__ unsigned long long g_tc_cta[4096][2];
 // WITH_SAM: the instantiation that carries the SAM detector (atan2f and the loop state cost 15 registers and a stack
 // frame; with them in the common kernel every step of cfg5 was 17 % slower although no channel used SAM).
 template <bool WITH_SAM>
-__global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTables tb)
+__global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, const __grid_constant__ FrontTcTables tb)
 {
     extern __shared__ __align__(128) uint8_t s_raw[];
     TcSmem s{s_raw};
@@ -489,13 +511,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
         s.nb_thr()[row] = (nbm && nbr > 0) ? (uint32_t)(((uint32_t)nbr * nbm) >> 8) : 0xFFFFFFFFu;
         s.nb_sum()[row] = 0u;
     }
-#pragma unroll 1
-    for (int k = 0; k < 3; k++) {
-        const int set = k == 0 ? rows.x : (k == 1 ? rows.y : rows.z);
-        const int4 *src = reinterpret_cast<const int4 *>(tb.toep + (size_t)set * TOEP_SET_B);
-        int4 *dst = reinterpret_cast<int4 *>(s.taps(k, 0));
-        for (int i = threadIdx.x; i < TOEP_SET_B / 16; i += NTHREADS) dst[i] = src[i];
-    }
     const uint32_t bar0 = smem_u32(s.bars());
     auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     if (threadIdx.x == 0) {
@@ -504,7 +519,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
         mbar_init(bar(B_E1_DONE), 2 * ROWS); mbar_init(bar(B_E1_DONE + 1), 2 * ROWS);     // both epilogue-1 groups arrive
         mbar_init(bar(B_M2_DONE), RDSP_TC_A_TMEM ? 1 : 2); mbar_init(bar(B_M2_DONE + 1), RDSP_TC_A_TMEM ? 1 : 2);
         mbar_init(bar(B_E2_DONE), ROWS);
+        mbar_init(bar(B_TAPS), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the three Toeplitz images of this tile (I', Q', band-pass: 2 byte planes each, 30 KB) arrive by TMA — three
+        // cp.async.bulk.tensor boxes issued by this one thread, completion counted in bytes on B_TAPS — while the other 703
+        // threads load row parameters and delay-line state; only the MMA issuers wait for them
+        mbar_expect_tx(bar(B_TAPS), 3 * TOEP_SET_B);
+        tma_load_2d(smem_u32(s.taps(0, 0)), &tb.toep_map, 0, rows.x * TOEP_ROWS_PER_SET, bar(B_TAPS));
+        tma_load_2d(smem_u32(s.taps(1, 0)), &tb.toep_map, 0, rows.y * TOEP_ROWS_PER_SET, bar(B_TAPS));
+        tma_load_2d(smem_u32(s.taps(2, 0)), &tb.toep_map, 0, rows.z * TOEP_ROWS_PER_SET, bar(B_TAPS));
     }
     __syncthreads();                                                       // row parameters visible
     if (seg == 0) {
@@ -598,6 +621,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
             const uint32_t rD0 = smem_u32(s.ring(2, 0)), rD1 = smem_u32(s.ring(2, 1));
             const uint32_t tA0 = smem_u32(s.taps(0, 0)), tA1 = smem_u32(s.taps(0, 1)), tB0 = smem_u32(s.taps(1, 0)), tB1 = smem_u32(s.taps(1, 1));
             const uint32_t tM0 = smem_u32(s.taps(2, 0)), tM1 = smem_u32(s.taps(2, 1));
+            mbar_wait_bounded(bar(B_TAPS), 0);                             // the Toeplitz images have landed (TMA)
             TCP_BEGIN;
 #pragma unroll 1
             for (int c = 0; c <= nch; c++) {
@@ -647,6 +671,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, FrontTcTa
             const uint32_t tB0 = smem_u32(s.taps(1, 0)), tB1 = smem_u32(s.taps(1, 1));
             const uint32_t rD0 = smem_u32(s.ring(2, 0)), rD1 = smem_u32(s.ring(2, 1));
             const uint32_t tM0 = smem_u32(s.taps(2, 0)), tM1 = smem_u32(s.taps(2, 1));
+            mbar_wait_bounded(bar(B_TAPS), 0);
 #pragma unroll 1
             for (int c = 0; c <= nch; c++) {
                 if (c < nch) {
@@ -803,6 +828,26 @@ void front_tc_read_cta(unsigned long long *out) { cudaMemcpyFromSymbol(out, g_tc
 #endif
 
 size_t front_tc_toeplitz_bytes() { return (size_t)15 * TOEP_SET_B; }
+
+// The Toeplitz table as a 2-D byte tensor [15 * 40 rows][256 bytes]; one box = 40 rows = the two planes of one tap row,
+// dense in shared memory (no swizzle, no interleave) = the layout the UMMA descriptors of issue_fir expect.
+int front_tc_make_tensor_map(const uint8_t *d_toep, CUtensorMap *map)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
+    const cuuint64_t dims[2] = {(cuuint64_t)TOEP_ROW_B, (cuuint64_t)15 * TOEP_ROWS_PER_SET};
+    const cuuint64_t strides[1] = {(cuuint64_t)TOEP_ROW_B};
+    const cuuint32_t box[2] = {(cuuint32_t)TOEP_ROW_B, (cuuint32_t)TOEP_ROWS_PER_SET};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = ((EncodeFn)fn)(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(d_toep), dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
 
 // Segments: with fewer tiles than SMs the T blocks of a tile are cut into up to 8 time segments, one CTA each.  A later
 // segment pays about 1.25 blocks of warm-up (one block of loads, one of Hilbert MMAs), so the cut points balance

@@ -1,5 +1,6 @@
 // kernels.h — argument blocks and launchers of the sm_100a kernels (internal to librdsp_gpu.so).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <vector>
@@ -44,6 +45,8 @@ struct FrontTcTables {
     const int *tile_ch;         // [n_tiles][128] channel of every MMA row, -1 = padding
     const int4 *tile_rows;      // [n_tiles] Toeplitz image index of the I', Q' and band-pass taps; w = 0 sideband sum, 1 AM envelope, 2 SAM
     const uint8_t *toep;        // [15][2][5120] banded Toeplitz byte planes of the tap rows (front_tc_build_toeplitz)
+    CUtensorMap toep_map;       // TMA descriptor of `toep` as a 2-D byte tensor [15 * 40 rows][256]: one box = one tap row's
+                                // two planes (front_tc_make_tensor_map); the kernel loads its three images with it
     int n_tiles;
     int seg_bounds[9];          // filled by launch_front_tc: block range of every time segment
     int sam_tiles;              // a SAM tile exists: launch the instantiation that carries the SAM detector
@@ -51,6 +54,7 @@ struct FrontTcTables {
 };
 void launch_front_tc(const FrontArgs &a, const FrontTcTables &tb, cudaStream_t st);
 size_t front_tc_toeplitz_bytes();
+int front_tc_make_tensor_map(const uint8_t *d_toep, CUtensorMap *map);   // 0 = ok (cuTensorMapEncodeTiled through the runtime's driver entry point)
 void front_tc_build_toeplitz(const int16_t *taps, int stride, uint8_t *out);
 int front_tc_build_tiles(const RdspChanParams *par, int C, const int16_t *taps, int stride,
                          std::vector<int> &tile_ch, std::vector<int4> &tile_rows);

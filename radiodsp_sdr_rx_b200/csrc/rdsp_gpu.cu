@@ -53,6 +53,7 @@ struct rdsp_gpu {
     // one stream per stage of the graph + one event per (stage, chunk): the wavefront of process_blocks
     cudaStream_t stage_stream[kStreams] = {nullptr};
     cudaEvent_t ev_group[kMaxGroups][3] = {{nullptr}};
+    cudaEvent_t ev_mark[kMaxGroups][4] = {{nullptr}};      // after the notch / AGC / FFT filter / DNR of the chain that runs the notch
     cudaEvent_t ev_fork = nullptr, ev_front = nullptr;
     // IO_HOST: copies run on their own streams over double-buffered staging, so that the H2D of call n+1 and the
     // D2H of call n-1 overlap the kernels of call n (async handles)
@@ -101,8 +102,10 @@ struct rdsp_gpu {
     int16_t *d_fe_hist2 = nullptr;             // buffers so that a call's blocks can run as concurrent time segments
     int fe_hist_cur = 0;
     bool front_tc = true;                      // RDSP_FRONT_IMPL=cuda-core selects k_front.cu (cross-check)
+    int spec_after = 1;                        // where the spectrum branch starts (enqueue_call); RDSP_SPEC_AFTER=0..5, experiments
     bool nlms_direct = false;                  // RDSP_NLMS_IMPL=direct selects k_nlms_direct.cu (cross-check); read at create
     uint8_t *d_toep = nullptr;                 // Toeplitz byte planes of the 15 tap rows
+    CUtensorMap toep_map;                      // TMA descriptor of d_toep (k_front_tc loads its three images with it)
     float *d_sam_state = nullptr;              // [C][4] SAM carrier loop
     int32_t *d_nb_ref = nullptr;               // [C] noise blanker running magnitude
     int any_sam = 0, sam_tiles = 0;
@@ -398,6 +401,8 @@ void free_all(rdsp_gpu *h)
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (int g = 0; g < kMaxGroups; g++)
         for (int k = 0; k < 3; k++) if (h->ev_group[g][k]) cudaEventDestroy(h->ev_group[g][k]);
+    for (int g = 0; g < kMaxGroups; g++)
+        for (int k = 0; k < 4; k++) if (h->ev_mark[g][k]) cudaEventDestroy(h->ev_mark[g][k]);
     if (h->ev_front) cudaEventDestroy(h->ev_front);
     for (int s = 0; s < kStreams; s++) {
         if (h->stage_stream[s]) cudaStreamDestroy(h->stage_stream[s]);
@@ -456,7 +461,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
             a.hist = fe_cur ? h->d_fe_hist2 : h->d_fe_hist;
             a.hist_out = fe_cur ? h->d_fe_hist : h->d_fe_hist2;
             FrontTcTables tb{};
-            tb.tile_ch = h->d_tile_ch; tb.tile_rows = h->d_tile_rows; tb.toep = h->d_toep; tb.n_tiles = h->n_tiles;
+            tb.tile_ch = h->d_tile_ch; tb.tile_rows = h->d_tile_rows; tb.toep = h->d_toep; tb.toep_map = h->toep_map; tb.n_tiles = h->n_tiles;
             tb.any_sam = h->any_sam; tb.sam_tiles = h->sam_tiles;
             a.sam_state = h->d_sam_state; a.nb_ref = h->d_nb_ref;
             launch_front_tc(a, tb, s_front);
@@ -480,7 +485,8 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
     // beside the wide kernels of the others instead of in front of them.
     // the spectrum branches keep the issue slots contended while the NLMS kernels run (k_nlms.cu, launch_nlms)
     const int nlms_contended = (has(h, RDSP_STAGE_SPEC256) || has(h, RDSP_STAGE_SPEC1024)) ? 1 : 0;
-    auto run_chain = [&](cudaStream_t cs, int cls, int c0, int c1) -> int {
+    auto run_chain = [&](cudaStream_t cs, int cls, int c0, int c1, cudaEvent_t *marks, int *n_marks) -> int {
+        auto mark = [&](int k) { if (marks && piped) { cudaEventRecord(marks[k], cs); if (*n_marks < k + 1) *n_marks = k + 1; } };
         const int nc = c1 - c0;
         int f_notch = 0, n_notch = 0, f_plain = 0, n_plain = 0;
         if (notch) { sub(h->l_notch, c0, c1, f_notch, n_notch); sub(h->l_plain, c0, c1, f_plain, n_plain); }
@@ -509,9 +515,11 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
                     n.coeff = h->d_nc_coeff; n.prev = h->d_nc_prev; n.energy = h->d_nc_energy; n.first = h->d_nc_first;
                     n.par = h->d_par; n.mode = 0; n.contended = nlms_contended; n.direct = h->nlms_direct;
                     { Prof pr(h, KK_NOTCH, cs); launch_nlms(n, cs); }
+                    mark(0);
                     // ... the others read the notch's f32 error signal
                     ag.list = h->d_list_notch + f_notch; ag.n_list = n_notch; ag.in_q15 = nullptr; ag.in_f32 = h->d_scr;
                     { Prof pr(h, KK_AGC, cs); launch_agc(ag, cs); }
+                    mark(1);
                 }
                 mono = h->d_mid_b;
             }
@@ -522,6 +530,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
             f.dbg = dbg; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256; f.sin512 = h->d_sin512;
             f.par = h->d_par; f.C = C; f.T = T; f.list = cls_list; f.ch0 = c0; f.n = cls_n; f.nr_stage = nr ? 1 : 0;
             { Prof pr(h, KK_FFTFILT, cs); launch_fftfilt(f, cs); }
+            if (cls != 1 && notch) mark(2);
             if (nr) {
                 const std::vector<int> &ld = cls == 1 ? h->l_dnr_p : (cls == 2 ? h->l_dnr_n : h->l_dnr);
                 const int *dl = cls == 1 ? h->d_list_dnr_p : (cls == 2 ? h->d_list_dnr_n : h->d_list_dnr);
@@ -534,6 +543,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
                     n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
                     n.par = h->d_par; n.mode = 1; n.contended = nlms_contended; n.direct = h->nlms_direct;
                     { Prof pr(h, KK_DNR, cs); launch_nlms(n, cs); }
+                    if (cls != 1 && notch) mark(3);
                 }
             }
         }
@@ -552,15 +562,38 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
         cudaStream_t s_main = piped ? h->stage_stream[g] : st;
         cudaStream_t s_spec = piped ? h->stage_stream[kMaxGroups + g] : st;
         cudaStream_t s_side = piped ? h->stage_stream[2 * kMaxGroups + g] : st;
-        if (piped) {
-            // the spectrum branch needs only the input, but it starts behind the front end: beside it, it slowed the
-            // kernel everything else waits for (0.67 ms per step against 0.61; RDSP_SPEC_WITH_FRONT=1 restores that order)
-            static const bool spec_with_front = [] { const char *e = getenv("RDSP_SPEC_WITH_FRONT"); return e && e[0] == '1'; }();
-            CK(cudaStreamWaitEvent(s_main, fe ? h->ev_front : h->ev_fork, 0));
-            CK(cudaStreamWaitEvent(s_spec, (fe && !spec_with_front) ? h->ev_front : h->ev_fork, 0));
+        if (piped) CK(cudaStreamWaitEvent(s_main, fe ? h->ev_front : h->ev_fork, 0));
+
+        // the channels whose notch runs form their own chain on the side stream (when both classes exist)
+        int fn = 0, nn = 0, fp = 0, np = 0;
+        if (fe && notch) { sub(h->l_notch, c0, c1, fn, nn); sub(h->l_plain, c0, c1, fp, np); }
+        static const bool no_split = [] { const char *e = getenv("RDSP_NO_SPLIT"); return e && e[0] == '1'; }();   // experiments
+        const bool split = piped && fe && notch && nn > 0 && np > 0 && !no_split;
+        int n_marks = 0;
+        if (split) {
+            CK(cudaStreamWaitEvent(s_side, h->ev_front, 0));
+            int rc2 = run_chain(s_side, 2, c0, c1, h->ev_mark[g], &n_marks);
+            if (rc2 != RDSP_OK) return rc2;
+            rc2 = run_chain(s_main, 1, c0, c1, nullptr, nullptr);
+            if (rc2 != RDSP_OK) return rc2;
+            CK(cudaEventRecord(h->ev_group[g][2], s_side));
+            CK(cudaStreamWaitEvent(st, h->ev_group[g][2], 0));
+        } else {
+            const int rc2 = run_chain(s_main, 0, c0, c1, h->ev_mark[g], &n_marks);
+            if (rc2 != RDSP_OK) return rc2;
         }
 
+        // The spectrum branch (high-pass biquads -> IQ spectrum) needs only the input and nobody waits for it, so WHEN it
+        // starts is a pure scheduling choice.  spec_after: 0 = with the front end, 1 = behind the front end, 2.. = behind
+        // the notch / AGC / FFT filter / DNR of the chain that runs the notch (the longest dependent chain of the call: its
+        // latency-bound kernels stretch in proportion to what shares their SMs — tools/diag_timeline.py).
         if (has(h, RDSP_STAGE_SPEC256)) {
+            if (piped) {
+                cudaEvent_t after = fe ? h->ev_front : h->ev_fork;
+                if (h->spec_after == 0) after = h->ev_fork;
+                else if (h->spec_after >= 2 && n_marks > 0) after = h->ev_mark[g][std::min(h->spec_after - 2, n_marks - 1)];
+                CK(cudaStreamWaitEvent(s_spec, after, 0));
+            }
             BiquadArgs b{};
             b.iq = iq; b.out = h->d_hp_iq; b.state = h->d_bq_state; b.C = C; b.T = T; b.ch0 = c0; b.n = nc;
             b.b0 = h->bq[0]; b.b1 = h->bq[1]; b.b2 = h->bq[2]; b.a1 = h->bq[3]; b.a2 = h->bq[4];
@@ -572,24 +605,8 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
             a.div_magic = ((1ull << a.div_shift) + h->cfg.spec256_naverage - 1) / h->cfg.spec256_naverage;
             a.tw = h->d_tw; a.win = h->d_win256;
             { Prof pr(h, KK_SPEC256, s_spec); launch_spec256(a, s_spec); }
-        }
-
-        // the channels whose notch runs form their own chain on the side stream (when both classes exist)
-        int fn = 0, nn = 0, fp = 0, np = 0;
-        if (fe && notch) { sub(h->l_notch, c0, c1, fn, nn); sub(h->l_plain, c0, c1, fp, np); }
-        static const bool no_split = [] { const char *e = getenv("RDSP_NO_SPLIT"); return e && e[0] == '1'; }();   // experiments
-        const bool split = piped && fe && notch && nn > 0 && np > 0 && !no_split;
-        if (split) {
-            CK(cudaStreamWaitEvent(s_side, h->ev_front, 0));
-            int rc2 = run_chain(s_side, 2, c0, c1);
-            if (rc2 != RDSP_OK) return rc2;
-            rc2 = run_chain(s_main, 1, c0, c1);
-            if (rc2 != RDSP_OK) return rc2;
-            CK(cudaEventRecord(h->ev_group[g][2], s_side));
-            CK(cudaStreamWaitEvent(st, h->ev_group[g][2], 0));
-        } else {
-            const int rc2 = run_chain(s_main, 0, c0, c1);
-            if (rc2 != RDSP_OK) return rc2;
+        } else if (piped) {
+            CK(cudaStreamWaitEvent(s_spec, h->ev_fork, 0));
         }
         if (piped) {
             // join: the call is complete on the handle's stream when every group has finished all of its streams
@@ -823,6 +840,8 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     CKC(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
     for (int g = 0; g < kMaxGroups; g++)
         for (int k = 0; k < 3; k++) CKC(cudaEventCreateWithFlags(&h->ev_group[g][k], cudaEventDisableTiming));
+    for (int g = 0; g < kMaxGroups; g++)
+        for (int k = 0; k < 4; k++) CKC(cudaEventCreateWithFlags(&h->ev_mark[g][k], cudaEventDisableTiming));
     {
         // the main chain (and the front end it waits for) outranks the spectrum and side branches: when an SM slot frees
         // up, a block of the latency-critical notch / DNR launch goes first, the wide FFT grids fill what is left
@@ -863,12 +882,15 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
         CKC(dalloc(&h->d_fe_hist, C * 3 * RDSP_BLK));
         CKC(dalloc(&h->d_fe_hist2, C * 3 * RDSP_BLK));
         CKC(dalloc(&h->d_toep, front_tc_toeplitz_bytes()));
+        if (front_tc_make_tensor_map(h->d_toep, &h->toep_map) != 0) return fail(cudaErrorUnknown, "cuTensorMapEncodeTiled (TMA descriptor of the Toeplitz table)");
         CKC(dalloc(&h->d_sam_state, C * 4));
         CKC(dalloc(&h->d_nb_ref, C));
         if (const char *e = getenv("RDSP_FRONT_IMPL")) h->front_tc = !(e[0] == 'c' || e[0] == 'C');
         if (const char *e = getenv("RDSP_TIMELINE")) h->timeline = e[0] == '1';
     }
     if (const char *e = getenv("RDSP_NLMS_IMPL")) h->nlms_direct = e[0] == 'd';
+    if (const char *e = getenv("RDSP_SPEC_AFTER")) h->spec_after = std::max(0, std::min(5, atoi(e)));
+    if (const char *e = getenv("RDSP_SPEC_WITH_FRONT")) { if (e[0] == '1') h->spec_after = 0; }
     if (sm & RDSP_STAGE_FRONTEND) {
         CKC(dalloc(&h->d_mid_a, T * C * RDSP_BLK));
     }

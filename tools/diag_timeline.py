@@ -9,9 +9,10 @@ import bench
 import radiodsp_sdr_rx_b200 as rd
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg5"
-chunks = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+chunks = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+T_ARG = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 desc, stage, C_ = bench.WORKLOADS[wl]
-T = 8
+T = T_ARG
 dev = torch.device("cuda", 0)
 iq = bench.make_inputs(wl, 0, C_, T)
 d_in = torch.from_numpy(iq).to(dev)

@@ -79,7 +79,9 @@ int main(int argc, char **argv)
 
     FrontArgs a{};
     a.iq = d_iq; a.par = d_par; a.taps = d_taps; a.C = C; a.T = T;
-    FrontTcTables tb{d_tile_ch, d_tile_rows, d_toep, n_tiles};
+    FrontTcTables tb{};
+    tb.tile_ch = d_tile_ch; tb.tile_rows = d_tile_rows; tb.toep = d_toep; tb.n_tiles = n_tiles;
+    if (front_tc_make_tensor_map(d_toep, &tb.toep_map) != 0) { printf("tensor map failed\n"); return 1; }
 
     int bad = 0;
     for (int pass = 0; pass < 2; pass++) {          // pass 0: mono output, pass 1: stereo output (state carries over)
