@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) k_fftfilt(FftFiltArgs a)
     __shared__ float2 s_tw[256];
     __shared__ __align__(16) float2 s_buf[WARPS][FFT256_BUF];
     __shared__ float s_sin[513];
+    pdl_release_successor();
 
     for (int i = threadIdx.x; i < 256; i += WARPS * 32) s_tw[i] = a.tw256[i];
     if (a.nr_stage)
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) k_fftfilt(FftFiltArgs a)
     }
     float nfloor = a.nfloor[ch];
 
+    pdl_wait_predecessor();                            // tables, mask, previous block are loaded; the rows are the predecessor's output
     for (int t = 0; t < a.T; t++) {
         const size_t cb = (size_t)t * a.C + ch;
         uint32_t cw[4];
@@ -175,5 +177,5 @@ __global__ void __launch_bounds__(WARPS * 32, 3) k_fftfilt(FftFiltArgs a)
 void launch_fftfilt(const FftFiltArgs &a, cudaStream_t st)
 {
     RDSP_CARVEOUT_ONCE(k_fftfilt);
-    if (a.n > 0) k_fftfilt<<<(a.n + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(a);
+    if (a.n > 0) rdsp_launch(k_fftfilt, (a.n + WARPS - 1) / WARPS, WARPS * 32, 0, st, a.pdl != 0, a);
 }

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
     __shared__ __align__(16) float s_x[NWARPS * CPW][XS];     // [0,128) previous block / outputs, [128,256) current
     __shared__ __align__(16) float s_x1[PACKED ? NWARPS * CPW : 1][XS];   // the same samples one to the left: s_x1[i] = x[i + 1]
 
+    pdl_release_successor();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane % G;                      // lane within the channel group
     const int li = (blockIdx.x * NWARPS + warp) * CPW + lane / G;
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
             for (int k = 0; k < NPF / 2; k++) nx[k] = src[g + G * k];
         }
     };
+    pdl_wait_predecessor();                      // own state is loaded; from here on: the predecessor's output
     fetch(0);
 
     for (int t = 0; t < a.T; t++) {
@@ -478,7 +480,7 @@ void launch_nlms(const NlmsArgs &a, cudaStream_t st)
     const int grid = (a.n_list + cpb - 1) / cpb;
     RDSP_CARVEOUT_ONCE((k_nlms<4, false>)); RDSP_CARVEOUT_ONCE((k_nlms<8, false>)); RDSP_CARVEOUT_ONCE((k_nlms<8, true>));
     // (G = 4 packed measured slower than G = 4 scalar everywhere: cfg5 0.565 vs 0.530 ms for G = 8 packed, cfg4a 0.381 vs 0.333)
-    if (G == 4) k_nlms<4, false><<<grid, nw * 32, 0, st>>>(a);
-    else if (packed) k_nlms<8, true><<<grid, nw * 32, 0, st>>>(a);
-    else k_nlms<8, false><<<grid, nw * 32, 0, st>>>(a);
+    if (G == 4) rdsp_launch(k_nlms<4, false>, grid, nw * 32, 0, st, a.pdl != 0, a);
+    else if (packed) rdsp_launch(k_nlms<8, true>, grid, nw * 32, 0, st, a.pdl != 0, a);
+    else rdsp_launch(k_nlms<8, false>, grid, nw * 32, 0, st, a.pdl != 0, a);
 }

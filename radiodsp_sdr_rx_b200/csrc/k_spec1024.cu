@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(NT) k_spec1024(Spec1024Args a)
 
     const unsigned long long tick0 = a.tick_in->tick;
     if (blockIdx.x == 0 && tid == 0) a.tick_out->tick = tick0 + (unsigned long long)a.T;
+    pdl_wait_predecessor();                                       // the audio rows are the predecessor's output
     for (int t = 0; t < a.T; t++) {
         const unsigned long long tick = tick0 + t;
         const int slot = (int)(tick & 7ull);
@@ -154,5 +155,5 @@ __global__ void __launch_bounds__(NT) k_spec1024(Spec1024Args a)
 void launch_spec1024(const Spec1024Args &a, cudaStream_t st)
 {
     RDSP_CARVEOUT_ONCE(k_spec1024);
-    if (a.n > 0) k_spec1024<<<a.n, NT, 0, st>>>(a);
+    if (a.n > 0) rdsp_launch(k_spec1024, a.n, NT, 0, st, a.pdl != 0, a);
 }

@@ -23,6 +23,29 @@ inline int rdsp_current_device() { int d = 0; cudaGetDevice(&d); return (d >= 0 
 #define RDSP_CARVEOUT_ONCE(kernel) do { static std::atomic<bool> done_[RDSP_MAX_DEVICES]; const int d_ = rdsp_current_device(); \
         if (!done_[d_].load(std::memory_order_acquire)) { rdsp_uniform_carveout(kernel); done_[d_].store(true, std::memory_order_release); } } while (0)
 
+// Programmatic dependent launch for the kernels of one dependent chain (notch -> AGC -> FFT filter -> DNR -> audio spectrum on
+// one stream).  A kernel launched with `pdl` may start while its predecessor still runs: it loads ITS OWN per-channel state
+// (written by its previous launch, one call ago), then executes griddepcontrol.wait, which returns when the predecessor has
+// completed and its stores are visible, and only then touches the predecessor's output.  Every chain kernel releases its
+// successor at its first instruction.  What it buys is the launch latency and the state prologue of each stage — which is most
+// of a call that covers a single 128-sample block (the sketch's calling pattern); with many blocks per call the early CTAs
+// only take slots from the running stage (measured in r01: 0.67 -> 0.79 ms at 8 blocks), so the host enables it for short calls.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_release_successor() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_predecessor() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename A>
+inline void rdsp_launch(void (*kernel)(A), int grid, int block, size_t smem, cudaStream_t st, bool pdl, const A &args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kernel, args);
+}
+#endif
+
 // K0+K1+K2 -----------------------------------------------------------------------------------
 struct FrontArgs {
     const int16_t *iq;          // [T][C][128][2]
@@ -78,6 +101,7 @@ struct NlmsArgs {
     int mode;                   // 0 = notch (output error), 1 = DNR (output estimate)
     int contended;              // 1: other kernels run beside this one (spectrum branches): the FFMA2 form pays (fewer issue slots)
     int direct;                 // 1: the sample-by-sample cross-check kernel (k_nlms_direct.cu; RDSP_NLMS_IMPL=direct at create)
+    int pdl;                    // launched as a programmatic dependent of the kernel before it on the stream
 };
 void launch_nlms(const NlmsArgs &a, cudaStream_t st);
 
@@ -96,6 +120,7 @@ struct AgcArgs {
     int C, T;
     int agc_stage;              // 0: only quantise (notch without AGC stage)
     float target, max_gain, alpha_a;
+    int pdl;                    // launched as a programmatic dependent of the kernel before it on the stream
 };
 void launch_agc(const AgcArgs &a, cudaStream_t st);
 
@@ -117,6 +142,7 @@ struct FftFiltArgs {
     const int *list;            // channels of this launch (n entries), or nullptr: [ch0, ch0 + n)
     int ch0, n;
     int nr_stage;               // RDSP_STAGE_NR present
+    int pdl;                    // launched as a programmatic dependent of the kernel before it on the stream
 };
 void launch_fftfilt(const FftFiltArgs &a, cudaStream_t st);
 
@@ -162,6 +188,7 @@ struct Spec1024Args {
     RdspTick *tick_out;         // ... and where tick + T goes (the other copy)
     const int2 *tw;             // [3072]
     const int16_t *win;         // [1024] Hann
+    int pdl;                    // launched as a programmatic dependent of the kernel before it on the stream
 };
 void launch_spec1024(const Spec1024Args &a, cudaStream_t st);
 

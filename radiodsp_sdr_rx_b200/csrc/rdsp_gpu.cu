@@ -102,6 +102,7 @@ struct rdsp_gpu {
     int16_t *d_fe_hist2 = nullptr;             // buffers so that a call's blocks can run as concurrent time segments
     int fe_hist_cur = 0;
     bool front_tc = true;                      // RDSP_FRONT_IMPL=cuda-core selects k_front.cu (cross-check)
+    int pdl_max_T = 2;                         // calls of up to this many blocks chain their kernels by programmatic dependent launch (RDSP_PDL_MAX_T)
     int spec_after = 1;                        // where the spectrum branch starts (enqueue_call); RDSP_SPEC_AFTER=0..5, experiments
     bool nlms_direct = false;                  // RDSP_NLMS_IMPL=direct selects k_nlms_direct.cu (cross-check); read at create
     uint8_t *d_toep = nullptr;                 // Toeplitz byte planes of the 15 tap rows
@@ -485,8 +486,13 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
     // beside the wide kernels of the others instead of in front of them.
     // the spectrum branches keep the issue slots contended while the NLMS kernels run (k_nlms.cu, launch_nlms)
     const int nlms_contended = (has(h, RDSP_STAGE_SPEC256) || has(h, RDSP_STAGE_SPEC1024)) ? 1 : 0;
+    // short calls: every kernel of a chain is a programmatic dependent of the one before it (kernels.h); `first` marks the kernel
+    // that follows an event wait (no kernel in front of it on its stream)
+    const int pdl = (piped && T <= h->pdl_max_T) ? 1 : 0;
     auto run_chain = [&](cudaStream_t cs, int cls, int c0, int c1, cudaEvent_t *marks, int *n_marks) -> int {
-        auto mark = [&](int k) { if (marks && piped) { cudaEventRecord(marks[k], cs); if (*n_marks < k + 1) *n_marks = k + 1; } };
+        auto mark = [&](int k) { if (marks && piped && h->spec_after >= 2) { cudaEventRecord(marks[k], cs); if (*n_marks < k + 1) *n_marks = k + 1; } };
+        bool first = true;                                   // the chain's first kernel has no kernel before it on `cs`
+        auto dep = [&]() { const int d = (pdl && !first) ? 1 : 0; first = false; return d; };
         const int nc = c1 - c0;
         int f_notch = 0, n_notch = 0, f_plain = 0, n_plain = 0;
         if (notch) { sub(h->l_notch, c0, c1, f_notch, n_notch); sub(h->l_plain, c0, c1, f_plain, n_plain); }
@@ -506,18 +512,18 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
                     // channels that bypass the notch read the front end's q15 rows ...
                     ag.list = notch ? h->d_list_plain + f_plain : nullptr; ag.n_list = notch ? n_plain : nc; ag.ch0 = c0;
                     ag.in_q15 = h->d_mid_a; ag.in_f32 = nullptr;
-                    if (ag.n_list > 0) { Prof pr(h, KK_AGC, cs); launch_agc(ag, cs); }
+                    if (ag.n_list > 0) { ag.pdl = dep(); Prof pr(h, KK_AGC, cs); launch_agc(ag, cs); }
                 }
                 if (cls != 1 && notch && n_notch > 0) {
                     NlmsArgs n{};
                     n.list = h->d_list_notch + f_notch; n.n_list = n_notch; n.C = C; n.T = T;
                     n.in_q15 = h->d_mid_a; n.out_f32 = h->d_scr;
                     n.coeff = h->d_nc_coeff; n.prev = h->d_nc_prev; n.energy = h->d_nc_energy; n.first = h->d_nc_first;
-                    n.par = h->d_par; n.mode = 0; n.contended = nlms_contended; n.direct = h->nlms_direct;
+                    n.par = h->d_par; n.mode = 0; n.contended = nlms_contended; n.direct = h->nlms_direct; n.pdl = dep();
                     { Prof pr(h, KK_NOTCH, cs); launch_nlms(n, cs); }
                     mark(0);
                     // ... the others read the notch's f32 error signal
-                    ag.list = h->d_list_notch + f_notch; ag.n_list = n_notch; ag.in_q15 = nullptr; ag.in_f32 = h->d_scr;
+                    ag.list = h->d_list_notch + f_notch; ag.n_list = n_notch; ag.in_q15 = nullptr; ag.in_f32 = h->d_scr; ag.pdl = dep();
                     { Prof pr(h, KK_AGC, cs); launch_agc(ag, cs); }
                     mark(1);
                 }
@@ -528,7 +534,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
             FftFiltArgs f{};
             f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq; f.out_stereo = mono_out ? nullptr : audio; f.out_mono = mono_out ? audio : nullptr; f.out_f32_L = h->d_scr;
             f.dbg = dbg; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256; f.sin512 = h->d_sin512;
-            f.par = h->d_par; f.C = C; f.T = T; f.list = cls_list; f.ch0 = c0; f.n = cls_n; f.nr_stage = nr ? 1 : 0;
+            f.par = h->d_par; f.C = C; f.T = T; f.list = cls_list; f.ch0 = c0; f.n = cls_n; f.nr_stage = nr ? 1 : 0; f.pdl = dep();
             { Prof pr(h, KK_FFTFILT, cs); launch_fftfilt(f, cs); }
             if (cls != 1 && notch) mark(2);
             if (nr) {
@@ -541,7 +547,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
                     n.list = dl + f_dnr; n.n_list = n_dnr; n.C = C; n.T = T;
                     n.in_f32 = h->d_scr; n.out_stereo = mono_out ? nullptr : audio; n.out_mono = mono_out ? audio : nullptr; n.dbg = dbg;
                     n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
-                    n.par = h->d_par; n.mode = 1; n.contended = nlms_contended; n.direct = h->nlms_direct;
+                    n.par = h->d_par; n.mode = 1; n.contended = nlms_contended; n.direct = h->nlms_direct; n.pdl = dep();
                     { Prof pr(h, KK_DNR, cs); launch_nlms(n, cs); }
                     if (cls != 1 && notch) mark(3);
                 }
@@ -551,7 +557,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
             Spec1024Args s1{};
             s1.audio = audio; s1.audio_mono = mono_out ? 1 : 0; s1.ring = h->d_ring; s1.output = h->d_spec1024_out; s1.C = C; s1.T = T;
             s1.list = cls_list; s1.ch0 = c0; s1.n = cls_n;
-            s1.tick_in = tick_in; s1.tick_out = tick_out; s1.tw = h->d_tw; s1.win = h->d_win1024;
+            s1.tick_in = tick_in; s1.tick_out = tick_out; s1.tw = h->d_tw; s1.win = h->d_win1024; s1.pdl = dep();
             { Prof pr(h, KK_SPEC1024, cs); launch_spec1024(s1, cs); }
         }
         return RDSP_OK;
@@ -889,6 +895,7 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
         if (const char *e = getenv("RDSP_TIMELINE")) h->timeline = e[0] == '1';
     }
     if (const char *e = getenv("RDSP_NLMS_IMPL")) h->nlms_direct = e[0] == 'd';
+    if (const char *e = getenv("RDSP_PDL_MAX_T")) h->pdl_max_T = atoi(e);
     if (const char *e = getenv("RDSP_SPEC_AFTER")) h->spec_after = std::max(0, std::min(5, atoi(e)));
     if (const char *e = getenv("RDSP_SPEC_WITH_FRONT")) { if (e[0] == '1') h->spec_after = 0; }
     if (sm & RDSP_STAGE_FRONTEND) {
