@@ -121,12 +121,14 @@ def ncu_traffic(kernel: str, workload: str, C_: int, T: int):
     def rows_of(prefix):
         return [r for name, rows in k.items() if name.split("<")[0] == prefix for r in rows]
     if kernel in ("k_nlms_notch", "k_nlms_dnr"):
-        # rows are in launch order: the notch (first kernel of the notched channels' chain), then the DNR of that class
-        # and the DNR of the channels that bypass the notch
+        # three k_nlms launches per step: the notch of the CW channels (a quarter of the channels, 16 per CTA) and the DNR of the
+        # two channel classes; the notch is the one whose grid matches its list
         rows = rows_of("k_nlms")
-        if len(rows) < 2:
+        notch_grid = (C_ // 4 + 15) // 16
+        notch = [r for r in rows if r["grid"] == notch_grid][:1]
+        rows = notch if kernel == "k_nlms_notch" else [r for r in rows if r["grid"] != notch_grid]
+        if not rows:
             return None
-        rows = rows[:1] if kernel == "k_nlms_notch" else rows[1:]
     elif kernel == "k_front":
         rows = rows_of("k_front_tc") or rows_of("k_front")
     elif kernel == "k_agc":

@@ -15,6 +15,10 @@ COLS = [
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma pipe %"),
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu pipe %"),
+    ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active %"),
+    ("sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active", "imma inst %"),
+    ("sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "tmem inst %"),
+    ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active", "TMA (mem tensor) %"),
     ("smsp__inst_executed.sum", "warp inst"),
     ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
