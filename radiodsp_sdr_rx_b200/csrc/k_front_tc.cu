@@ -13,6 +13,14 @@
 //         x h = 65536 xh hh + 256 (xh hl + xl hh) + xl hl
 //     Three TMEM accumulators (ll, mid, hh), four MMAs per 32-byte K step with the four signedness combinations of
 //     kind::i8.  No partial sum exceeds 2^24, the recombination wraps in 32-bit registers like the CMSIS accumulator.
+//   * r02, "paired" images: with the taps split into SIGNED digits (h = 256 hh + hl, hl in [-128, 127]; possible for every
+//     tap below 32640) the two digit planes of a tap row have the same signedness and sit side by side as ONE B operand of
+//     N = 64 columns [hl | hh].  A K step is then two MMAs instead of four — xl x [hl | hh] into the columns [ll | mid] and
+//     xh x [hl | hh] into the columns [mid | hh], the second one simply 32 columns further right, so that its hl half
+//     accumulates onto the lh half of the first — 11 MMAs per FIR and chunk instead of 20, and 12 KB instead of 20 KB of
+//     operand fetch per K step (the kernel is bound by the per-instruction cost and the shared-memory operand traffic of
+//     its small MMAs).  Accumulator columns, epilogues and results are unchanged.  A tile whose tap rows
+//     hold a tap >= 32640 keeps the classic four-product path (both images of every row are in the table).
 //   * delay lines live in shared memory as two byte planes per line (I', Q', demodulated), each a ring of six
 //     32-sample slices in the canonical no-swizzle K-major core-matrix layout (8 rows x 16 bytes): slice =
 //     [2 k-groups][128 rows][16 B].  An MMA K step reads one slice, so the ring never moves data: chunk c reads slices
@@ -79,11 +87,16 @@ constexpr int TOEP_ROW_B = 256, TOEP_ROWS_PER_SET = TOEP_SET_B / TOEP_ROW_B;   /
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 @4, a_format @7, b_format @10 (1 = signed),
 // K-major A and B, N >> 3 @17, M >> 4 @24
-constexpr uint32_t IDESC_BASE = (2u << 4) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
-constexpr uint32_t IDESC_UU = IDESC_BASE;
-constexpr uint32_t IDESC_SU = IDESC_BASE | (1u << 7);
-constexpr uint32_t IDESC_US = IDESC_BASE | (1u << 10);
-constexpr uint32_t IDESC_SS = IDESC_BASE | (1u << 7) | (1u << 10);
+constexpr uint32_t idesc(int n, bool a_signed, bool b_signed)
+{
+    return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24) | (a_signed ? (1u << 7) : 0u) | (b_signed ? (1u << 10) : 0u);
+}
+constexpr uint32_t IDESC_UU = idesc(NOUT, false, false);
+constexpr uint32_t IDESC_SU = idesc(NOUT, true, false);
+constexpr uint32_t IDESC_US = idesc(NOUT, false, true);
+constexpr uint32_t IDESC_SS = idesc(NOUT, true, true);
+// paired images: B = [hl | hh], both signed, N = 64 (or one half of it, N = 32)
+constexpr uint32_t IDESC_P_US64 = idesc(2 * NOUT, false, true), IDESC_P_SS64 = idesc(2 * NOUT, true, true), IDESC_P_SS32 = idesc(NOUT, true, true);
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -338,6 +351,30 @@ __device__ __forceinline__ void issue_fir(uint32_t ring_lo, uint32_t ring_hi, ui
     }
 }
 
+// the same FIR from a PAIRED image (taps = [10 k-groups][64 columns: hl of output n | hh of output n][16 B], signed digits):
+// two N = 64 MMAs per K step; the first K step clears the accumulators with three (the hh columns are cleared by an N = 32
+// MMA of their own, because the N = 64 MMA that covers them must accumulate onto mid)
+__device__ __forceinline__ void issue_fir_paired(uint32_t ring_lo, uint32_t ring_hi, uint32_t taps, uint32_t tmem_d, int c)
+{
+    int sl = c % SLICES;
+#pragma unroll 1
+    for (int ks = 0; ks < KSTEPS; ks++) {
+        const uint32_t so = (uint32_t)(sl * SLICE_B);
+        const uint64_t a_lo = make_desc(ring_lo + so, ROWS * 16), a_hi = make_desc(ring_hi + so, ROWS * 16);
+        const uint32_t tb = taps + ks * 2 * (2 * NOUT) * 16;
+        const uint64_t b_all = make_desc(tb, 2 * NOUT * 16);
+        if (ks == 0) {
+            mma_i8(tmem_d + 0 * NOUT, a_lo, b_all, IDESC_P_US64, 0);                                   // [ll | mid] = xl x [hl | hh]
+            mma_i8(tmem_d + 2 * NOUT, a_hi, make_desc(tb + NOUT * 16, 2 * NOUT * 16), IDESC_P_SS32, 0);   // hh = xh x hh
+            mma_i8(tmem_d + 1 * NOUT, a_hi, b_all, IDESC_P_SS32, 1);                                   // mid += xh x hl
+        } else {
+            mma_i8(tmem_d + 0 * NOUT, a_lo, b_all, IDESC_P_US64, 1);
+            mma_i8(tmem_d + 1 * NOUT, a_hi, b_all, IDESC_P_SS64, 1);                                   // [mid | hh] += xh x [hl | hh]
+        }
+        sl = sl + 1 == SLICES ? 0 : sl + 1;
+    }
+}
+
 // the same FIR with the delay-line planes as TMEM A operand: ring_lo / ring_hi = TMEM column of slice 0 of the plane
 __device__ __forceinline__ void issue_fir_ts(uint32_t ring_lo, uint32_t ring_hi, uint32_t taps_lo, uint32_t taps_hi, uint32_t tmem_d, int c)
 {
@@ -480,7 +517,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, const __g
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x, seg = blockIdx.y;
     const int4 rows = tb.tile_rows[tile];                                 // x, y, z = Toeplitz images; w = AM flag
-    const int dmode = rows.w;                                             // 0 sideband sum, 1 AM envelope, 2 SAM
+    const int dmode = rows.w & 0xFF;                                      // 0 sideband sum, 1 AM envelope, 2 SAM
+    const bool paired = (rows.w >> 8) & 1;                                // the tile's three tap rows have paired images (CTA-uniform)
 #ifdef RDSP_TC_PROF
     unsigned long long gt0_;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0_));
@@ -517,7 +555,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, const __g
         mbar_init(bar(B_IN_FULL), NLD * 32); mbar_init(bar(B_IN_FULL + 1), NLD * 32);
         mbar_init(bar(B_M1_DONE), RDSP_TC_A_TMEM ? 1 : 2); mbar_init(bar(B_M1_DONE + 1), RDSP_TC_A_TMEM ? 1 : 2);   // two issuing threads commit (I' FIR, Q' FIR)
         mbar_init(bar(B_E1_DONE), 2 * ROWS); mbar_init(bar(B_E1_DONE + 1), 2 * ROWS);     // both epilogue-1 groups arrive
-        mbar_init(bar(B_M2_DONE), RDSP_TC_A_TMEM ? 1 : 2); mbar_init(bar(B_M2_DONE + 1), RDSP_TC_A_TMEM ? 1 : 2);
+        // classic images: both issuers own accumulators of the band-pass FIR; paired: one issuer per chunk (they alternate)
+        mbar_init(bar(B_M2_DONE), (RDSP_TC_A_TMEM || paired) ? 1 : 2); mbar_init(bar(B_M2_DONE + 1), (RDSP_TC_A_TMEM || paired) ? 1 : 2);
         mbar_init(bar(B_E2_DONE), ROWS);
         mbar_init(bar(B_TAPS), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -525,9 +564,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, const __g
         // cp.async.bulk.tensor boxes issued by this one thread, completion counted in bytes on B_TAPS — while the other 703
         // threads load row parameters and delay-line state; only the MMA issuers wait for them
         mbar_expect_tx(bar(B_TAPS), 3 * TOEP_SET_B);
-        tma_load_2d(smem_u32(s.taps(0, 0)), &tb.toep_map, 0, rows.x * TOEP_ROWS_PER_SET, bar(B_TAPS));
-        tma_load_2d(smem_u32(s.taps(1, 0)), &tb.toep_map, 0, rows.y * TOEP_ROWS_PER_SET, bar(B_TAPS));
-        tma_load_2d(smem_u32(s.taps(2, 0)), &tb.toep_map, 0, rows.z * TOEP_ROWS_PER_SET, bar(B_TAPS));
+        const int img = paired ? 1 : 0;                                    // the table holds both images of every tap row
+        tma_load_2d(smem_u32(s.taps(0, 0)), &tb.toep_map, 0, (rows.x * 2 + img) * TOEP_ROWS_PER_SET, bar(B_TAPS));
+        tma_load_2d(smem_u32(s.taps(1, 0)), &tb.toep_map, 0, (rows.y * 2 + img) * TOEP_ROWS_PER_SET, bar(B_TAPS));
+        tma_load_2d(smem_u32(s.taps(2, 0)), &tb.toep_map, 0, (rows.z * 2 + img) * TOEP_ROWS_PER_SET, bar(B_TAPS));
     }
     __syncthreads();                                                       // row parameters visible
     if (seg == 0) {
@@ -640,12 +680,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, const __g
                     TCP(3);
                     tc_fence_after();
                     const uint32_t acc1 = tmem + (c & 1) * TM_ACC1B;
-                    issue_fir<0>(rI0, rI1, tA0, tA1, acc1, c);              // the Q' FIR is issued by the second issuer warp
+                    if (paired) issue_fir_paired(rI0, rI1, tA0, acc1, c);
+                    else issue_fir<0>(rI0, rI1, tA0, tA1, acc1, c);         // the Q' FIR is issued by the second issuer warp
 #endif
                     mma_commit(bar(B_M1_DONE + (c & 1)));
                     TCP(4);
                 }
                 if (c >= 1) {
+                    // Both issuers wait for EVERY chunk's barriers, also for the chunks whose band-pass FIR the other one issues
+                    // (paired images: they alternate): a parity wait only tells the phase before the current one from the
+                    // current one — a thread that skipped a phase of e2_done would read "complete" one chunk too early.
                     const int cc = c - 1;
                     mbar_wait(bar(B_E1_DONE + (cc & 1)), (cc >> 1) & 1);
                     TCP(5);
@@ -654,10 +698,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, const __g
                     tc_fence_after();
 #if RDSP_TC_A_TMEM
                     issue_fir<0>(rD0, rD1, tM0, tM1, tmem + TM_ACC2P, cc);
-#else
-                    issue_fir<1>(rD0, rD1, tM0, tM1, tmem + TM_ACC2P, cc);         // ll, hh here; mid by the second issuer
-#endif
                     mma_commit(bar(B_M2_DONE + (cc & 1)));
+#else
+                    if (!paired) {
+                        issue_fir<1>(rD0, rD1, tM0, tM1, tmem + TM_ACC2P, cc);    // ll, hh here; mid by the second issuer
+                        mma_commit(bar(B_M2_DONE + (cc & 1)));
+                    } else if ((cc & 1) == 0) {                                   // paired: the even chunks here, the odd ones there
+                        issue_fir_paired(rD0, rD1, tM0, tmem + TM_ACC2P, cc);
+                        mma_commit(bar(B_M2_DONE + (cc & 1)));
+                    }
+#endif
                     TCP(7);
                 }
             }
@@ -678,16 +728,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, const __g
                     mbar_wait(bar(B_IN_FULL + (c & 1)), (c >> 1) & 1);
                     if (c >= 2) mbar_wait(bar(B_E1_DONE + (c & 1)), ((c - 2) >> 1) & 1);
                     tc_fence_after();
-                    issue_fir<0>(rQ0, rQ1, tB0, tB1, tmem + (c & 1) * TM_ACC1B + 3 * NOUT, c);
+                    if (paired) issue_fir_paired(rQ0, rQ1, tB0, tmem + (c & 1) * TM_ACC1B + 3 * NOUT, c);
+                    else issue_fir<0>(rQ0, rQ1, tB0, tB1, tmem + (c & 1) * TM_ACC1B + 3 * NOUT, c);
                     mma_commit(bar(B_M1_DONE + (c & 1)));
                 }
                 if (c >= 1) {
-                    const int cc = c - 1;                                  // the mid accumulator of the band-pass FIR
+                    const int cc = c - 1;
                     mbar_wait(bar(B_E1_DONE + (cc & 1)), (cc >> 1) & 1);
                     if (cc >= 1) mbar_wait(bar(B_E2_DONE), (cc - 1) & 1);
                     tc_fence_after();
-                    issue_fir<2>(rD0, rD1, tM0, tM1, tmem + TM_ACC2P, cc);
-                    mma_commit(bar(B_M2_DONE + (cc & 1)));
+                    if (!paired) {
+                        issue_fir<2>(rD0, rD1, tM0, tM1, tmem + TM_ACC2P, cc);     // classic: the mid accumulator of the band-pass FIR
+                        mma_commit(bar(B_M2_DONE + (cc & 1)));
+                    } else if ((cc & 1) == 1) {                                    // paired: the band-pass FIR of the odd chunks
+                        issue_fir_paired(rD0, rD1, tM0, tmem + TM_ACC2P, cc);
+                        mma_commit(bar(B_M2_DONE + (cc & 1)));
+                    }
                 }
             }
         }
@@ -770,21 +826,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, const __g
 
 // ---- host side: Toeplitz images and the tile table ---------------------------------------------------------------
 
-void front_tc_build_toeplitz(const int16_t *taps /*[15][stride]*/, int stride, uint8_t *out /*[15][TOEP_SET_B]*/)
+// every tap of the row has signed digits (hh = (h - (int8)h) / 256 fits int8): a paired image exists
+static bool row_pairable(const int16_t *row)
 {
-    for (int r = 0; r < 15; r++)
-        for (int plane = 0; plane < 2; plane++)
-            for (int kg = 0; kg < 10; kg++)
-                for (int n = 0; n < NOUT; n++)
-                    for (int b = 0; b < 16; b++) {
-                        const int k = kg * 16 + b, tap = 128 + n - k;
-                        uint8_t v = 0;
-                        if (tap >= 0 && tap <= 128) {
-                            const uint16_t h = (uint16_t)taps[(size_t)r * stride + tap];
-                            v = plane ? (uint8_t)(h >> 8) : (uint8_t)(h & 0xFF);
-                        }
-                        out[(size_t)r * TOEP_SET_B + plane * TOEP_PLANE_B + (kg * NOUT + n) * 16 + b] = v;
-                    }
+    for (int k = 0; k < RDSP_NTAPS; k++) if (row[k] >= 32640) return false;
+    return true;
+}
+
+// Two images per tap row, [15][2][TOEP_SET_B]:
+//   image 0 (classic)  [plane: low byte (unsigned) | high byte (signed)][10 k-groups][32 outputs][16 B]
+//   image 1 (paired)   [10 k-groups][64 columns: signed low digit of output n | high digit of output n][16 B]
+void front_tc_build_toeplitz(const int16_t *taps /*[15][stride]*/, int stride, uint8_t *out /*[15][2][TOEP_SET_B]*/)
+{
+    for (int r = 0; r < 15; r++) {
+        uint8_t *classic = out + (size_t)(2 * r) * TOEP_SET_B, *pairimg = out + (size_t)(2 * r + 1) * TOEP_SET_B;
+        const bool ok = row_pairable(taps + (size_t)r * stride);
+        for (int kg = 0; kg < 10; kg++)
+            for (int n = 0; n < NOUT; n++)
+                for (int b = 0; b < 16; b++) {
+                    const int k = kg * 16 + b, tap = 128 + n - k;
+                    const int h = (tap >= 0 && tap <= 128) ? taps[(size_t)r * stride + tap] : 0;
+                    classic[0 * TOEP_PLANE_B + (kg * NOUT + n) * 16 + b] = (uint8_t)((uint16_t)h & 0xFF);
+                    classic[1 * TOEP_PLANE_B + (kg * NOUT + n) * 16 + b] = (uint8_t)((uint16_t)h >> 8);
+                    const int hl = (int8_t)((uint16_t)h & 0xFF), hh = (h - hl) / 256;        // h = 256 hh + hl, hl in [-128, 127]
+                    pairimg[(kg * 2 * NOUT + n) * 16 + b] = ok ? (uint8_t)(int8_t)hl : 0;
+                    pairimg[(kg * 2 * NOUT + NOUT + n) * 16 + b] = ok ? (uint8_t)(int8_t)hh : 0;
+                }
+    }
 }
 
 // Channels that share their three tap rows (by content) and the detector (sideband sum / envelope / SAM) form a class;
@@ -811,7 +879,11 @@ int front_tc_build_tiles(const RdspChanParams *par, int C, const int16_t *taps, 
     for (auto &kv : classes) {
         const std::vector<int> &v = kv.second;
         for (size_t i = 0; i < v.size(); i += ROWS) {
-            tile_rows.push_back(make_int4(kv.first[0], kv.first[1], kv.first[2], kv.first[3]));
+            // w = detector kind | paired-image flag << 8 (all three tap rows must have one; RDSP_FRONT_PAIRED=0 forces the classic path)
+            static const bool allow = [] { const char *e = getenv("RDSP_FRONT_PAIRED"); return !(e && e[0] == '0'); }();
+            const bool pr = allow && row_pairable(taps + (size_t)kv.first[0] * stride) && row_pairable(taps + (size_t)kv.first[1] * stride) &&
+                            row_pairable(taps + (size_t)kv.first[2] * stride);
+            tile_rows.push_back(make_int4(kv.first[0], kv.first[1], kv.first[2], kv.first[3] | (pr ? 256 : 0)));
             for (int r = 0; r < ROWS; r++) tile_ch.push_back(i + r < v.size() ? v[i + r] : -1);
         }
     }
@@ -827,9 +899,9 @@ void front_tc_read_prof(unsigned long long *out, bool reset)
 void front_tc_read_cta(unsigned long long *out) { cudaMemcpyFromSymbol(out, g_tc_cta, sizeof(g_tc_cta)); }
 #endif
 
-size_t front_tc_toeplitz_bytes() { return (size_t)15 * TOEP_SET_B; }
+size_t front_tc_toeplitz_bytes() { return (size_t)15 * 2 * TOEP_SET_B; }
 
-// The Toeplitz table as a 2-D byte tensor [15 * 40 rows][256 bytes]; one box = 40 rows = the two planes of one tap row,
+// The Toeplitz table as a 2-D byte tensor [15 * 2 * 40 rows][256 bytes]; one box = 40 rows = one image of one tap row,
 // dense in shared memory (no swizzle, no interleave) = the layout the UMMA descriptors of issue_fir expect.
 int front_tc_make_tensor_map(const uint8_t *d_toep, CUtensorMap *map)
 {
@@ -839,7 +911,7 @@ int front_tc_make_tensor_map(const uint8_t *d_toep, CUtensorMap *map)
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
-    const cuuint64_t dims[2] = {(cuuint64_t)TOEP_ROW_B, (cuuint64_t)15 * TOEP_ROWS_PER_SET};
+    const cuuint64_t dims[2] = {(cuuint64_t)TOEP_ROW_B, (cuuint64_t)15 * 2 * TOEP_ROWS_PER_SET};
     const cuuint64_t strides[1] = {(cuuint64_t)TOEP_ROW_B};
     const cuuint32_t box[2] = {(cuuint32_t)TOEP_ROW_B, (cuuint32_t)TOEP_ROWS_PER_SET};
     const cuuint32_t estr[2] = {1, 1};

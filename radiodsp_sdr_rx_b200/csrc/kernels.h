@@ -66,8 +66,9 @@ void launch_front(const FrontArgs &a, cudaStream_t st);
 // K0+K1+K2 on tcgen05 (k_front_tc.cu): channels grouped into tiles of 128 that share their tap rows
 struct FrontTcTables {
     const int *tile_ch;         // [n_tiles][128] channel of every MMA row, -1 = padding
-    const int4 *tile_rows;      // [n_tiles] Toeplitz image index of the I', Q' and band-pass taps; w = 0 sideband sum, 1 AM envelope, 2 SAM
-    const uint8_t *toep;        // [15][2][5120] banded Toeplitz byte planes of the tap rows (front_tc_build_toeplitz)
+    const int4 *tile_rows;      // [n_tiles] tap row of the I', Q' and band-pass FIR; w = detector (0 sideband sum, 1 AM envelope, 2 SAM)
+                                // | 256 if the tile runs from the paired images of its rows
+    const uint8_t *toep;        // [15][2 images][10240] banded Toeplitz byte images of the tap rows (front_tc_build_toeplitz)
     CUtensorMap toep_map;       // TMA descriptor of `toep` as a 2-D byte tensor [15 * 40 rows][256]: one box = one tap row's
                                 // two planes (front_tc_make_tensor_map); the kernel loads its three images with it
     int n_tiles;

@@ -315,7 +315,7 @@ int sync_tables(rdsp_gpu *h)
         // k_front_tc: channels that share their tap rows, in tiles of 128 MMA rows
         h->n_tiles = front_tc_build_tiles(h->dpar.data(), h->C, &h->taps[0][0], RDSP_FIR_TAPS, tile_ch, tile_rows);
         h->any_sam = 0; h->sam_tiles = 0;
-        for (const int4 &r : tile_rows) if (r.w == 2) { h->any_sam = 1; h->sam_tiles = 1; }
+        for (const int4 &r : tile_rows) if ((r.w & 0xFF) == 2) { h->any_sam = 1; h->sam_tiles = 1; }
         for (int ch = 0; ch < h->C; ch++) if (h->dpar[ch].nb_mult_q8) h->any_sam = 1;   // blanker state is sequential too
         if (h->n_tiles > h->tile_cap) {
             if (h->d_tile_ch) cudaFree(h->d_tile_ch);
