@@ -57,7 +57,7 @@ constexpr int TOEP_SET_B = 2 * TOEP_PLANE_B;  // lo plane, hi plane
 constexpr int NLD = RDSP_TC_A_TMEM_EARLY ? 4 : 8;             // loader warps (the TMEM-operand variant maps them on lane quadrants)
 constexpr int ITEMS = 32 / NLD;                               // (row group, k-group) items per loader warp and chunk
 // warps 0-3: epilogue 1, outputs 0..15 of a chunk; W_E1B..+3: epilogue 1, outputs 16..31 (same TMEM lane quadrants)
-constexpr int W_E2 = 4, W_LD = 8, W_E1B = W_LD + NLD, W_MMA = W_E1B + 4, W_MMA2 = W_MMA + 1, NWARPS = W_MMA2 + 1;
+constexpr int W_E2 = 4, W_LD = 8, W_E1B = W_LD + NLD, W_MMA = W_E1B + 4, W_MMA2 = W_MMA + 1, W_MMA3 = W_MMA2 + 1, NWARPS = W_MMA3 + 1;
 static_assert(W_E1B % 4 == 0, "the second epilogue-1 group must sit on the lane quadrants of its warp indices");
 constexpr int NTHREADS = NWARPS * 32;
 
@@ -500,13 +500,13 @@ __device__ unsigned long long g_tc_cta[4096][2];
 
 // ---- the kernel: warp-specialised pipeline over the chunks of one tile -----------------------------------------------
 //   warps 0-3, 16-19  epilogue 1 (TMEM lane quadrant = warp % 4) warps 8-15  loader (HBM -> gain -> byte planes)
-//   warps 4-7         epilogue 2 (quadrant = warp - 4)           warps 20,21 MMA issue (one lane each)
+//   warps 4-7         epilogue 2 (quadrant = warp - 4)           warps 20-22 MMA issue (one lane each: I' FIR, Q' FIR, band-pass FIR)
 //   in_full[2]   loader -> MMA      chunk c's I'/Q' slice is in shared memory                      (128 arrivals)
 //   m1_done[2]   MMA -> E1, loader  Hilbert-pair MMAs of chunk c retired: acc1[c&1] valid, slice c%6 free (commit)
 //   e1_done[2]   E1 -> MMA          acc1[c&1] drained and the D slice of chunk c written           (256 arrivals)
 //   m2_done[2]   MMA -> E2, E1      band-pass MMAs of chunk c retired: acc2 valid, D slice c%6 free     (commit)
 //   e2_done      E2 -> MMA          acc2 drained                                                    (128 arrivals)
-// The band-pass MMAs of chunk c-1 are issued after the Hilbert MMAs of chunk c, so epilogue 1 overlaps tensor work.
+// Each FIR has an issuing thread of its own: the band-pass MMAs of chunk c run beside the Hilbert MMAs of chunk c + 1.
 // WITH_SAM: the instantiation that carries the SAM detector (atan2f and the loop state cost 15 registers and a stack
 // frame; with them in the common kernel every step of cfg5 was 17 % slower although no channel used SAM).
 template <bool WITH_SAM>
@@ -555,8 +555,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, const __g
         mbar_init(bar(B_IN_FULL), NLD * 32); mbar_init(bar(B_IN_FULL + 1), NLD * 32);
         mbar_init(bar(B_M1_DONE), RDSP_TC_A_TMEM ? 1 : 2); mbar_init(bar(B_M1_DONE + 1), RDSP_TC_A_TMEM ? 1 : 2);   // two issuing threads commit (I' FIR, Q' FIR)
         mbar_init(bar(B_E1_DONE), 2 * ROWS); mbar_init(bar(B_E1_DONE + 1), 2 * ROWS);     // both epilogue-1 groups arrive
-        // classic images: both issuers own accumulators of the band-pass FIR; paired: one issuer per chunk (they alternate)
-        mbar_init(bar(B_M2_DONE), (RDSP_TC_A_TMEM || paired) ? 1 : 2); mbar_init(bar(B_M2_DONE + 1), (RDSP_TC_A_TMEM || paired) ? 1 : 2);
+        mbar_init(bar(B_M2_DONE), 1); mbar_init(bar(B_M2_DONE + 1), 1);                   // the band-pass FIR has an issuer of its own
         mbar_init(bar(B_E2_DONE), ROWS);
         mbar_init(bar(B_TAPS), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -664,8 +663,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, const __g
             mbar_wait_bounded(bar(B_TAPS), 0);                             // the Toeplitz images have landed (TMA)
             TCP_BEGIN;
 #pragma unroll 1
-            for (int c = 0; c <= nch; c++) {
-                if (c < nch) {
+            for (int c = 0; c < nch; c++) {
+                {
                     mbar_wait(bar(B_IN_FULL + (c & 1)), (c >> 1) & 1);
                     TCP(2);
 #if RDSP_TC_A_TMEM
@@ -686,65 +685,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, const __g
                     mma_commit(bar(B_M1_DONE + (c & 1)));
                     TCP(4);
                 }
-                if (c >= 1) {
-                    // Both issuers wait for EVERY chunk's barriers, also for the chunks whose band-pass FIR the other one issues
-                    // (paired images: they alternate): a parity wait only tells the phase before the current one from the
-                    // current one — a thread that skipped a phase of e2_done would read "complete" one chunk too early.
-                    const int cc = c - 1;
-                    mbar_wait(bar(B_E1_DONE + (cc & 1)), (cc >> 1) & 1);
-                    TCP(5);
-                    if (cc >= 1) mbar_wait(bar(B_E2_DONE), (cc - 1) & 1);
-                    TCP(6);
-                    tc_fence_after();
-#if RDSP_TC_A_TMEM
-                    issue_fir<0>(rD0, rD1, tM0, tM1, tmem + TM_ACC2P, cc);
-                    mma_commit(bar(B_M2_DONE + (cc & 1)));
-#else
-                    if (!paired) {
-                        issue_fir<1>(rD0, rD1, tM0, tM1, tmem + TM_ACC2P, cc);    // ll, hh here; mid by the second issuer
-                        mma_commit(bar(B_M2_DONE + (cc & 1)));
-                    } else if ((cc & 1) == 0) {                                   // paired: the even chunks here, the odd ones there
-                        issue_fir_paired(rD0, rD1, tM0, tmem + TM_ACC2P, cc);
-                        mma_commit(bar(B_M2_DONE + (cc & 1)));
-                    }
-#endif
-                    TCP(7);
-                }
             }
         }
         __syncwarp();
     } else if (warp == W_MMA2) {
-        // ===== second MMA issuer: the Q' FIR of every chunk (two issuing threads keep the tensor pipe at ~40 clk per
-        // MMA instead of ~52, tools/ubench_umma.cu); same waits as the first issuer, own commit on m1_done =====
+        // ===== second MMA issuer: the Q' FIR of every chunk (several issuing threads keep more MMAs in flight: ~40 clk per
+        // N = 32 MMA instead of ~52, tools/ubench_umma.cu); same waits as the first issuer, own commit on m1_done =====
         if (lane == 0 && !RDSP_TC_A_TMEM) {
             const uint32_t rQ0 = smem_u32(s.ring(1, 0)), rQ1 = smem_u32(s.ring(1, 1));
             const uint32_t tB0 = smem_u32(s.taps(1, 0)), tB1 = smem_u32(s.taps(1, 1));
+            mbar_wait_bounded(bar(B_TAPS), 0);
+#pragma unroll 1
+            for (int c = 0; c < nch; c++) {
+                mbar_wait(bar(B_IN_FULL + (c & 1)), (c >> 1) & 1);
+                if (c >= 2) mbar_wait(bar(B_E1_DONE + (c & 1)), ((c - 2) >> 1) & 1);
+                tc_fence_after();
+                if (paired) issue_fir_paired(rQ0, rQ1, tB0, tmem + (c & 1) * TM_ACC1B + 3 * NOUT, c);
+                else issue_fir<0>(rQ0, rQ1, tB0, tB1, tmem + (c & 1) * TM_ACC1B + 3 * NOUT, c);
+                mma_commit(bar(B_M1_DONE + (c & 1)));
+            }
+        }
+        __syncwarp();
+    } else if (warp == W_MMA3) {
+        // ===== third MMA issuer (r02): the band-pass FIR of every chunk.  The phase timers showed the two Hilbert issuers
+        // blocked ~170 clk per MMA inside their own issue (the instruction waits for a slot in the tensor queue) and then
+        // again on e1_done / e2_done before they could issue the band-pass FIR of the chunk before — one thread cannot do
+        // both without serialising them.  With its own issuer the band-pass FIR of chunk c runs beside the Hilbert FIRs of
+        // chunk c + 1, and the Hilbert issuers never wait for an epilogue of the other stage. =====
+        if (lane == 0) {
             const uint32_t rD0 = smem_u32(s.ring(2, 0)), rD1 = smem_u32(s.ring(2, 1));
             const uint32_t tM0 = smem_u32(s.taps(2, 0)), tM1 = smem_u32(s.taps(2, 1));
             mbar_wait_bounded(bar(B_TAPS), 0);
+            TCP_BEGIN;
 #pragma unroll 1
-            for (int c = 0; c <= nch; c++) {
-                if (c < nch) {
-                    mbar_wait(bar(B_IN_FULL + (c & 1)), (c >> 1) & 1);
-                    if (c >= 2) mbar_wait(bar(B_E1_DONE + (c & 1)), ((c - 2) >> 1) & 1);
-                    tc_fence_after();
-                    if (paired) issue_fir_paired(rQ0, rQ1, tB0, tmem + (c & 1) * TM_ACC1B + 3 * NOUT, c);
-                    else issue_fir<0>(rQ0, rQ1, tB0, tB1, tmem + (c & 1) * TM_ACC1B + 3 * NOUT, c);
-                    mma_commit(bar(B_M1_DONE + (c & 1)));
-                }
-                if (c >= 1) {
-                    const int cc = c - 1;
-                    mbar_wait(bar(B_E1_DONE + (cc & 1)), (cc >> 1) & 1);
-                    if (cc >= 1) mbar_wait(bar(B_E2_DONE), (cc - 1) & 1);
-                    tc_fence_after();
-                    if (!paired) {
-                        issue_fir<2>(rD0, rD1, tM0, tM1, tmem + TM_ACC2P, cc);     // classic: the mid accumulator of the band-pass FIR
-                        mma_commit(bar(B_M2_DONE + (cc & 1)));
-                    } else if ((cc & 1) == 1) {                                    // paired: the band-pass FIR of the odd chunks
-                        issue_fir_paired(rD0, rD1, tM0, tmem + TM_ACC2P, cc);
-                        mma_commit(bar(B_M2_DONE + (cc & 1)));
-                    }
-                }
+            for (int cc = 0; cc < nch; cc++) {
+                mbar_wait(bar(B_E1_DONE + (cc & 1)), (cc >> 1) & 1);       // the D slice of chunk cc is written
+                TCP(5);
+                if (cc >= 1) mbar_wait(bar(B_E2_DONE), (cc - 1) & 1);      // the one band-pass accumulator set is drained
+                TCP(6);
+                tc_fence_after();
+                if (paired) issue_fir_paired(rD0, rD1, tM0, tmem + TM_ACC2P, cc);
+                else issue_fir<0>(rD0, rD1, tM0, tM1, tmem + TM_ACC2P, cc);
+                mma_commit(bar(B_M2_DONE + (cc & 1)));
+                TCP(7);
             }
         }
         __syncwarp();
