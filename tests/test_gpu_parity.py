@@ -731,3 +731,31 @@ def test_mono_layout_is_the_left_channel(rd, po, stage):
     assert mo.shape == (nb, nc, 128) and np.array_equal(mo, st[..., 0])
     if st_spec is not None:
         assert np.array_equal(st_spec, mo_spec) and st_spec.any()
+
+
+def test_installed_mask_survives_set_mode_until_the_pbt_changes(rd, po):
+    """rdsp_gpu_set_mask installs a mask as data; the sketch-style setters re-send the whole parameter block (get_mode ->
+    set_mode), which must not silently drop it — only a change of the PBT cut-offs redesigns the mask (reInitializeFilter,
+    RDSP_convolutional.h:209-224).  Identical masks are stored once; re-sending unchanged parameters rebuilds nothing."""
+    rng = np.random.default_rng(4)
+    mask = rng.normal(0, 0.5, 512).astype(np.float32)
+    bank = make_bank(rd, 3, rd.STAGE_FFTFILT)
+    designed = bank.get_mask(0).copy()
+    bank.set_mask(0, 2, mask)
+    bank.set_mask(2, 1, mask)                                   # same table again: shared row
+    p = bank.get_mode(0); p.nr_level = 30; p.nr_kind = rd.NR_LMS
+    bank.set_mode(0, 1, p)                                      # unrelated setting: the installed mask stays
+    assert np.array_equal(bank.get_mask(0), mask) and np.array_equal(bank.get_mask(1), mask) and np.array_equal(bank.get_mask(2), mask)
+    iq = synth.synth_iq([1, 2, 3], 4, [0, 0, 0])
+    g = bank.process_host(iq)
+    ch = po.OracleChan(po.default_config(stage_mask=po.STAGE_FFTFILT)); ch.set_mask(mask)
+    assert np.abs(g[:, 1].astype(np.int32) - ch.process(iq[:, 1])).max() <= 1
+    n0 = bank.kernel_launches
+    bank.set_mode(0, 1, p)                                      # re-sent unchanged: nothing to rebuild
+    bank.process_host(iq)
+    assert bank.kernel_launches - n0 == 1
+    p.pbt_hi_hz = 2500.0
+    bank.set_mode(0, 1, p)                                      # PBT moved: the mask is designed again
+    assert not np.array_equal(bank.get_mask(0), mask) and not np.array_equal(bank.get_mask(0), designed)
+    assert np.abs(bank.get_mask(0) - po.design_mask(300.0, 2500.0)).max() < 2e-6
+    assert np.array_equal(bank.get_mask(1), mask)
