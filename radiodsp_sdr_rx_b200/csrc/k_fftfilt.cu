@@ -40,7 +40,10 @@ __device__ __forceinline__ float arm_trig_f32(float x, bool cosine, const float 
     return __fadd_rn(__fmul_rn(__fsub_rn(1.0f, fract), a), __fmul_rn(fract, b));
 }
 
-__global__ void __launch_bounds__(WARPS * 32, 3) k_fftfilt(FftFiltArgs a)
+#ifndef RDSP_FFTFILT_MINB
+#define RDSP_FFTFILT_MINB 3
+#endif
+__global__ void __launch_bounds__(WARPS * 32, RDSP_FFTFILT_MINB) k_fftfilt(FftFiltArgs a)
 {
     __shared__ float2 s_tw[256];
     __shared__ __align__(16) float2 s_buf[WARPS][FFT256_BUF];

@@ -80,7 +80,10 @@ __device__ __forceinline__ void fft1024_passes(int2 (&x)[4][4], int2 *s_fft, con
     }
 }
 
-__global__ void __launch_bounds__(NT) k_spec1024(Spec1024Args a)
+#ifndef RDSP_SPEC1024_MINB
+#define RDSP_SPEC1024_MINB 12    // 80 registers, no spills (10 = what 96 registers allowed; 12 / 14: 495.6 / 499.6 us per step with k_spec256 at 4)
+#endif
+__global__ void __launch_bounds__(NT, RDSP_SPEC1024_MINB) k_spec1024(Spec1024Args a)
 {
     __shared__ __align__(16) int2 s_fft[1024 + 64];               // unpacked (re, im), element i at PP(i)
     __shared__ uint16_t s_guess[34];

@@ -26,7 +26,10 @@ constexpr int XBUF = 256 + 32;                // int2 per channel in the exchang
 
 __device__ __forceinline__ int PX(int e) { return e + 2 * (e >> 4); }
 
-__global__ void __launch_bounds__(WARPS * 32, 3) k_spec256(Spec256Args a)
+#ifndef RDSP_SPEC256_MINB
+#define RDSP_SPEC256_MINB 4      // 128 registers (112 B of spills): 71 -> 74.5 us alone, but the STEP gains 2.6 % — a fourth CTA per SM is co-residency for the kernels running beside it (r02 A/B, 3 / 4 / 5: 510.6 / 497.5 / 510.5 us per step)
+#endif
+__global__ void __launch_bounds__(WARPS * 32, RDSP_SPEC256_MINB) k_spec256(Spec256Args a)
 {
     __shared__ __align__(16) int2 s_x[WARPS * 2][XBUF];
     __shared__ int16_t s_win[256];
