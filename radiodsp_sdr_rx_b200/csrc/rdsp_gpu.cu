@@ -21,7 +21,7 @@
 #include <utility>
 #include <vector>
 
-#define RDSP_VERSION "rdsp-b200 0.1 (sm_100a)"
+#define RDSP_VERSION "rdsp-b200 0.2 (sm_100a)"
 
 namespace {
 
