@@ -453,35 +453,48 @@ __device__ __forceinline__ void epilogue1(const TcSmem &s, uint32_t tmem_row, in
     }
 }
 
-// epilogue 2: band-pass accumulators -> q15 -> audio rows
-__device__ __forceinline__ void epilogue2(const FrontArgs &a, uint32_t tmem_row, int ch, int t, int cq)
+// epilogue 2: band-pass accumulators -> q15 -> audio rows.  The one band-pass accumulator set is the shortest cycle of the
+// chunk pipeline (band-pass MMAs of chunk c+1 wait for this drain; phase timers r02: issue 1.6 k + drain-and-store 2.0 k clk of a
+// 3.9 k clk chunk period), so the drain is separated from the stores: both halves of the 32 outputs are pulled out of TMEM with
+// six loads in flight each and recombined into 16 packed registers, the accumulators are handed back (e2_done), and only then
+// do the global stores go out.
+__device__ __forceinline__ void epilogue2(const FrontArgs &a, uint32_t tmem_row, int ch, int t, int cq, uint32_t bar_e2_done)
 {
-    const size_t cb = (size_t)t * a.C + (ch >= 0 ? ch : 0);
-#pragma unroll 1
-    for (int h8 = 0; h8 < 4; h8++) {
-        uint32_t v[3][8];
+    uint32_t pk[NOUT / 2];                                                   // outputs 2i, 2i+1 as a q15 pair
 #pragma unroll
-        for (int k = 0; k < 3; k++) tmem_ld8(tmem_row + k * NOUT + h8 * 8, v[k]);
-        tmem_ld_wait();
-        int32_t m[8];
+    for (int half = 0; half < 2; half++) {
+        uint32_t v[3][16];
 #pragma unroll
-        for (int j = 0; j < 8; j++) m[j] = recombine(v[0][j], v[1][j], v[2][j]);
-        if (ch < 0) continue;
-        const size_t n0 = cb * RDSP_BLK + cq * NOUT + h8 * 8;
-        if (a.out_mono)
-            st_stream16(a.out_mono + n0, make_int4((int)mk16(m[0], m[1]), (int)mk16(m[2], m[3]), (int)mk16(m[4], m[5]), (int)mk16(m[6], m[7])));
-        if (a.out_stereo) {
-            int16_t *dst = a.out_stereo + n0 * 2;
-            st_stream16(dst, make_int4((int)mk16(m[0], m[0]), (int)mk16(m[1], m[1]), (int)mk16(m[2], m[2]), (int)mk16(m[3], m[3])));
-            st_stream16(dst + 8, make_int4((int)mk16(m[4], m[4]), (int)mk16(m[5], m[5]), (int)mk16(m[6], m[6]), (int)mk16(m[7], m[7])));
+        for (int k = 0; k < 3; k++) {
+            tmem_ld8(tmem_row + k * NOUT + half * 16, v[k]);
+            tmem_ld8(tmem_row + k * NOUT + half * 16 + 8, v[k] + 8);
         }
-        if (a.dbg) {
-            float4 *dp = reinterpret_cast<float4 *>(a.dbg + n0 * 2);
+        tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const float f0 = (float)m[2 * q] / 32768.0f, f1 = (float)m[2 * q + 1] / 32768.0f;
-                dp[q] = make_float4(f0, f0, f1, f1);
-            }
+        for (int j = 0; j < 8; j++)
+            pk[half * 8 + j] = mk16(recombine(v[0][2 * j], v[1][2 * j], v[2][2 * j]), recombine(v[0][2 * j + 1], v[1][2 * j + 1], v[2][2 * j + 1]));
+    }
+    tc_fence_before();
+    mbar_arrive(bar_e2_done);                                                // acc2 is free: the stores below no longer hold the tensor core up
+    if (ch < 0) return;
+    const size_t n0 = ((size_t)t * a.C + ch) * RDSP_BLK + cq * NOUT;
+    if (a.out_mono) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) st_stream16(a.out_mono + n0 + 8 * q, make_int4((int)pk[4 * q], (int)pk[4 * q + 1], (int)pk[4 * q + 2], (int)pk[4 * q + 3]));
+    }
+    if (a.out_stereo) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {                                        // 4 frames (L = R) per 16-byte store
+            const uint32_t p0 = pk[2 * q], p1 = pk[2 * q + 1];
+            st_stream16(a.out_stereo + (n0 + 4 * q) * 2, make_int4((int)prmt(p0, p0, 0x1010), (int)prmt(p0, p0, 0x3232), (int)prmt(p1, p1, 0x1010), (int)prmt(p1, p1, 0x3232)));
+        }
+    }
+    if (a.dbg) {
+        float4 *dp = reinterpret_cast<float4 *>(a.dbg + n0 * 2);
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const float f0 = (float)lo16(pk[q]) / 32768.0f, f1 = (float)hi16(pk[q]) / 32768.0f;
+            dp[q] = make_float4(f0, f0, f1, f1);
         }
     }
 }
@@ -778,9 +791,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, const __g
             mbar_wait(bar(B_M2_DONE + (c & 1)), (c >> 1) & 1);
             if (warp == W_E2) TCP(11);
             tc_fence_after();
-            epilogue2(a, tmem_row, t >= t_store ? ch : -1, t, c & 3);
-            tc_fence_before();
-            mbar_arrive(bar(B_E2_DONE));
+            epilogue2(a, tmem_row, t >= t_store ? ch : -1, t, c & 3, bar(B_E2_DONE));
             if (warp == W_E2) TCP(12);
         }
     }
