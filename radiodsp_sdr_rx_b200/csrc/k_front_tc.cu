@@ -540,7 +540,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, const __g
 
     // this CTA's share of the T blocks: outputs of blocks [t_store, t_end); a later segment first rebuilds its
     // delay lines from the input itself (block t0-1 as I'/Q' history, block t0 = t_store-1 as warm-up for the D line)
-    const int t_store = tb.seg_bounds[seg], t_end = tb.seg_bounds[seg + 1];
+    const int kind_seg = dmode == 1 ? 1 : 0;                              // AM tiles are cut into more segments (launch_front_tc)
+    const int n_seg = tb.n_seg[kind_seg];
+    if (seg >= n_seg) return;                                              // (whole CTA, before any barrier exists)
+    const int t_store = tb.seg_bounds[kind_seg][seg], t_end = tb.seg_bounds[kind_seg][seg + 1];
     const int t0 = seg ? t_store - 1 : 0;
     const int nch = 4 * (t_end - t0);
 
@@ -800,7 +803,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_front_tc(FrontArgs a, const __g
     tc_fence_before();
     __syncthreads();
     TCQ(14);
-    if (seg == (int)gridDim.y - 1) state_io<true>(s, a.hist_out, nch % SLICES, warp, lane);
+    if (seg == n_seg - 1) state_io<true>(s, a.hist_out, nch % SLICES, warp, lane);
     if (warp == W_MMA) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TM_COLS) : "memory");
@@ -917,10 +920,9 @@ int front_tc_make_tensor_map(const uint8_t *d_toep, CUtensorMap *map)
 
 // Segments: with fewer tiles than SMs the T blocks of a tile are cut into up to 8 time segments, one CTA each.  A later
 // segment pays about 1.25 blocks of warm-up (one block of loads, one of Hilbert MMAs), so the cut points balance
-// n_0 against n_s + 1.25.
-void front_tc_plan_segments(int n_tiles, int T, int n_sm, int *bounds, int *n_seg)
+// n_0 against n_s + 1.25.  S = wanted number of segments; fewer are planned when T is too short.
+void front_tc_plan_segments(int S, int T, int *bounds, int *n_seg)
 {
-    int S = n_tiles > 0 ? n_sm / n_tiles : 1;
     if (S > 8) S = 8;
     while (S > 1) {
         // segment s > 0 must start at block >= 2 and hold at least one block
@@ -943,6 +945,24 @@ void front_tc_plan_segments(int n_tiles, int T, int n_sm, int *bounds, int *n_se
     *n_seg = S;
 }
 
+// How many segments for the sideband tiles and for the AM tiles?  An AM tile's chunk takes about 1.5 x as long (its epilogue 1
+// computes the integer square root of the envelope; phase timers), so with one segment count for all the AM tiles finish last
+// (cfg5: 48 + 16 tiles x 2 segments = 128 CTAs, 20 SMs idle, and the 16 AM tiles set the kernel's time).  Pick the pair that
+// minimises the slowest CTA while everything still runs as one wave.
+static void front_tc_choose_segments(int n_sum, int n_am, int T, int n_sm, int *s_sum, int *s_am)
+{
+    auto cost = [&](double w, int n, int S) { return n ? w * (T + 1.25 * (S - 1)) / S : 0.0; };
+    double best = 1e30;
+    *s_sum = 1; *s_am = 1;
+    for (int a = 1; a <= 8; a++)
+        for (int b = 1; b <= 8; b++) {
+            if (n_sum * a + n_am * b > n_sm && !(a == 1 && b == 1)) continue;
+            if ((!n_sum && a > 1) || (!n_am && b > 1)) continue;
+            const double c = std::max(cost(1.0, n_sum, a), cost(1.5, n_am, b)) + 1e-3 * (a + b);   // ties: fewer CTAs
+            if (c < best) { best = c; *s_sum = a; *s_am = b; }
+        }
+}
+
 void launch_front_tc(const FrontArgs &a_in, const FrontTcTables &tb_in, cudaStream_t st)
 {
     // the opt-in to > 48 KB of dynamic shared memory is per (kernel, device): a process with one handle per GPU needs it on each
@@ -958,9 +978,14 @@ void launch_front_tc(const FrontArgs &a_in, const FrontTcTables &tb_in, cudaStre
     FrontArgs a = a_in;
     FrontTcTables tb = tb_in;
     if (!a.hist_out) a.hist_out = a.hist;
+    int want[2] = {1, 1};                                                   // per detector kind: 0 sideband sum (and SAM), 1 AM envelope
+    if (a.hist_out != a.hist && !tb.any_sam)                                // in-place state / SAM loop / noise blanker: one segment
+        front_tc_choose_segments(tb.n_tiles - tb.n_am_tiles, tb.n_am_tiles, a.T, n_sm, &want[0], &want[1]);
     int S = 1;
-    front_tc_plan_segments(tb.n_tiles, a.T, n_sm, tb.seg_bounds, &S);
-    if (S > 1 && (a.hist_out == a.hist || tb.any_sam)) { S = 1; tb.seg_bounds[0] = 0; tb.seg_bounds[1] = a.T; }   // in-place state / SAM loop: one segment
+    for (int k = 0; k < 2; k++) {
+        front_tc_plan_segments(want[k], a.T, tb.seg_bounds[k], &tb.n_seg[k]);
+        if (tb.n_seg[k] > S && (k == 0 ? tb.n_tiles > tb.n_am_tiles : tb.n_am_tiles > 0)) S = tb.n_seg[k];
+    }
     if (tb.sam_tiles) k_front_tc<true><<<dim3(tb.n_tiles, S), NTHREADS, SMEM_B, st>>>(a, tb);
     else k_front_tc<false><<<dim3(tb.n_tiles, S), NTHREADS, SMEM_B, st>>>(a, tb);
 }

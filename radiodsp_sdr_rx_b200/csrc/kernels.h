@@ -72,7 +72,9 @@ struct FrontTcTables {
     CUtensorMap toep_map;       // TMA descriptor of `toep` as a 2-D byte tensor [15 * 40 rows][256]: one box = one tap row's
                                 // two planes (front_tc_make_tensor_map); the kernel loads its three images with it
     int n_tiles;
-    int seg_bounds[9];          // filled by launch_front_tc: block range of every time segment
+    int n_am_tiles;             // how many of them are AM-envelope tiles (their chunks take ~1.5 x as long: more time segments)
+    int seg_bounds[2][9];       // filled by launch_front_tc: block range of every time segment, per kind (0 sideband / SAM, 1 AM)
+    int n_seg[2];
     int sam_tiles;              // a SAM tile exists: launch the instantiation that carries the SAM detector
     int any_sam;                // a SAM tile or a noise-blanked channel exists: their state is sequential over the whole call, one segment
 };

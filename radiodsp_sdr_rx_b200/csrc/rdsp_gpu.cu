@@ -109,7 +109,7 @@ struct rdsp_gpu {
     CUtensorMap toep_map;                      // TMA descriptor of d_toep (k_front_tc loads its three images with it)
     float *d_sam_state = nullptr;              // [C][4] SAM carrier loop
     int32_t *d_nb_ref = nullptr;               // [C] noise blanker running magnitude
-    int any_sam = 0, sam_tiles = 0;
+    int any_sam = 0, sam_tiles = 0, n_am_tiles = 0;
     int *d_tile_ch = nullptr; int4 *d_tile_rows = nullptr; int n_tiles = 0, tile_cap = 0;
     float *d_nc_coeff = nullptr, *d_nc_prev = nullptr, *d_nc_energy = nullptr; uint8_t *d_nc_first = nullptr;
     float *d_dn_coeff = nullptr, *d_dn_prev = nullptr, *d_dn_energy = nullptr; uint8_t *d_dn_first = nullptr;
@@ -314,8 +314,9 @@ int sync_tables(rdsp_gpu *h)
     if (has(h, RDSP_STAGE_FRONTEND)) {
         // k_front_tc: channels that share their tap rows, in tiles of 128 MMA rows
         h->n_tiles = front_tc_build_tiles(h->dpar.data(), h->C, &h->taps[0][0], RDSP_FIR_TAPS, tile_ch, tile_rows);
-        h->any_sam = 0; h->sam_tiles = 0;
+        h->any_sam = 0; h->sam_tiles = 0; h->n_am_tiles = 0;
         for (const int4 &r : tile_rows) if ((r.w & 0xFF) == 2) { h->any_sam = 1; h->sam_tiles = 1; }
+        for (const int4 &r : tile_rows) if ((r.w & 0xFF) == 1) h->n_am_tiles++;
         for (int ch = 0; ch < h->C; ch++) if (h->dpar[ch].nb_mult_q8) h->any_sam = 1;   // blanker state is sequential too
         if (h->n_tiles > h->tile_cap) {
             if (h->d_tile_ch) cudaFree(h->d_tile_ch);
@@ -463,7 +464,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
             a.hist_out = fe_cur ? h->d_fe_hist : h->d_fe_hist2;
             FrontTcTables tb{};
             tb.tile_ch = h->d_tile_ch; tb.tile_rows = h->d_tile_rows; tb.toep = h->d_toep; tb.toep_map = h->toep_map; tb.n_tiles = h->n_tiles;
-            tb.any_sam = h->any_sam; tb.sam_tiles = h->sam_tiles;
+            tb.any_sam = h->any_sam; tb.sam_tiles = h->sam_tiles; tb.n_am_tiles = h->n_am_tiles;
             a.sam_state = h->d_sam_state; a.nb_ref = h->d_nb_ref;
             launch_front_tc(a, tb, s_front);
         } else {

@@ -82,6 +82,7 @@ int main(int argc, char **argv)
     FrontTcTables tb{};
     tb.tile_ch = d_tile_ch; tb.tile_rows = d_tile_rows; tb.toep = d_toep; tb.n_tiles = n_tiles;
     if (front_tc_make_tensor_map(d_toep, &tb.toep_map) != 0) { printf("tensor map failed\n"); return 1; }
+    for (const int4 &r : tile_rows) if ((r.w & 0xFF) == 1) tb.n_am_tiles++;
 
     int bad = 0;
     for (int pass = 0; pass < 2; pass++) {          // pass 0: mono output, pass 1: stereo output (state carries over)
