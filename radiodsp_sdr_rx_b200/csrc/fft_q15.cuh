@@ -32,6 +32,23 @@ QHD int s16(int v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 : v); }
 // SAT = false: the caller has PROVED that no sum of this frame can leave int16 (see no_saturation_bound below), so
 // QADD16 / QSUB16 are plain adds.  The saturating min / max pairs are a quarter of a butterfly's ALU-pipe work.
 template <bool SAT> QHD int s16c(int v) { return SAT ? s16(v) : v; }
+// QADD16 / QSUB16 of one half-word pair on 32-bit lanes.  On the device the clamp is written in PTX: left to the compiler,
+// min(max(a + b)) of two values it has proved to be int16 becomes a 16-bit saturating add that it then expands into
+// ~8 compare / select / permute instructions; ptxas turns this form into VIADDMNMX + VIMNMX.
+template <bool SAT> QHD int qadd(int a, int b)
+{
+#ifdef __CUDA_ARCH__
+    if (SAT) { int r; asm("{.reg .s32 t;\n\tadd.s32 t, %1, %2;\n\tmax.s32 t, t, -32768;\n\tmin.s32 %0, t, 32767;}" : "=r"(r) : "r"(a), "r"(b)); return r; }
+#endif
+    return s16c<SAT>(a + b);
+}
+template <bool SAT> QHD int qsub(int a, int b)
+{
+#ifdef __CUDA_ARCH__
+    if (SAT) { int r; asm("{.reg .s32 t;\n\tsub.s32 t, %1, %2;\n\tmax.s32 t, t, -32768;\n\tmin.s32 %0, t, 32767;}" : "=r"(r) : "r"(a), "r"(b)); return r; }
+#endif
+    return s16c<SAT>(a - b);
+}
 
 // A frame whose windowed input components are all <= this bound in magnitude cannot saturate in any stage of the
 // 256- or 1024-point transform.  With input bound m0: stage 1 works on x >> 2 (<= a0 = m0/4 + 1), forms sums <= 4 a0 and
@@ -87,8 +104,8 @@ QHD void middle(int2 *src, const int2 *tw, int n1, int n2, int mod, int b)
     const int j = b % n2, grp = b / n2, ic = j * mod, i0 = j + grp * n1;
     int2 *p0 = src + P(i0), *p1 = src + P(i0 + n2), *p2 = src + P(i0 + 2 * n2), *p3 = src + P(i0 + 3 * n2);
     const int2 xa = *p0, xb = *p1, xc = *p2, xd = *p3;
-    const int Rx = s16c<SAT>(xa.x + xc.x), Ry = s16c<SAT>(xa.y + xc.y), Sx = s16c<SAT>(xa.x - xc.x), Sy = s16c<SAT>(xa.y - xc.y);
-    const int Tx = s16c<SAT>(xb.x + xd.x), Ty = s16c<SAT>(xb.y + xd.y), Ux = s16c<SAT>(xb.x - xd.x), Uy = s16c<SAT>(xb.y - xd.y);
+    const int Rx = qadd<SAT>(xa.x, xc.x), Ry = qadd<SAT>(xa.y, xc.y), Sx = qsub<SAT>(xa.x, xc.x), Sy = qsub<SAT>(xa.y, xc.y);
+    const int Tx = qadd<SAT>(xb.x, xd.x), Ty = qadd<SAT>(xb.y, xd.y), Ux = qsub<SAT>(xb.x, xd.x), Uy = qsub<SAT>(xb.y, xd.y);
     *p0 = make_int2(((Rx + Tx) >> 1) >> 1, ((Ry + Ty) >> 1) >> 1);
     *p1 = cmul(tw[2 * ic], make_int2((Rx - Tx) >> 1, (Ry - Ty) >> 1));
     *p2 = cmul(tw[ic], make_int2((Sx + Uy) >> 1, (Sy - Ux) >> 1));        // SHSAX(S, T)
@@ -101,8 +118,8 @@ QHD void last(int2 *src, int b)
 {
     int2 *w = src + P(4 * b);                                  // 4b..4b+3 never straddle a skew boundary
     const int2 xa = w[0], xb = w[1], xc = w[2], xd = w[3];
-    const int Rx = s16c<SAT>(xa.x + xc.x), Ry = s16c<SAT>(xa.y + xc.y), Sx = s16c<SAT>(xa.x - xc.x), Sy = s16c<SAT>(xa.y - xc.y);
-    const int Tx = s16c<SAT>(xb.x + xd.x), Ty = s16c<SAT>(xb.y + xd.y), Ux = s16c<SAT>(xb.x - xd.x), Uy = s16c<SAT>(xb.y - xd.y);
+    const int Rx = qadd<SAT>(xa.x, xc.x), Ry = qadd<SAT>(xa.y, xc.y), Sx = qsub<SAT>(xa.x, xc.x), Sy = qsub<SAT>(xa.y, xc.y);
+    const int Tx = qadd<SAT>(xb.x, xd.x), Ty = qadd<SAT>(xb.y, xd.y), Ux = qsub<SAT>(xb.x, xd.x), Uy = qsub<SAT>(xb.y, xd.y);
     w[0] = make_int2((Rx + Tx) >> 1, (Ry + Ty) >> 1);
     w[1] = make_int2((Rx - Tx) >> 1, (Ry - Ty) >> 1);
     w[2] = make_int2((Sx + Uy) >> 1, (Sy - Ux) >> 1);          // SHSAX(S, U)
@@ -135,8 +152,8 @@ template <bool SAT = true>
 QHD void middle_r(int2 &x0, int2 &x1, int2 &x2, int2 &x3, int2 t1, int2 t2, int2 t3)
 {
     const int2 xa = x0, xb = x1, xc = x2, xd = x3;
-    const int Rx = s16c<SAT>(xa.x + xc.x), Ry = s16c<SAT>(xa.y + xc.y), Sx = s16c<SAT>(xa.x - xc.x), Sy = s16c<SAT>(xa.y - xc.y);
-    const int Tx = s16c<SAT>(xb.x + xd.x), Ty = s16c<SAT>(xb.y + xd.y), Ux = s16c<SAT>(xb.x - xd.x), Uy = s16c<SAT>(xb.y - xd.y);
+    const int Rx = qadd<SAT>(xa.x, xc.x), Ry = qadd<SAT>(xa.y, xc.y), Sx = qsub<SAT>(xa.x, xc.x), Sy = qsub<SAT>(xa.y, xc.y);
+    const int Tx = qadd<SAT>(xb.x, xd.x), Ty = qadd<SAT>(xb.y, xd.y), Ux = qsub<SAT>(xb.x, xd.x), Uy = qsub<SAT>(xb.y, xd.y);
     x0 = make_int2(((Rx + Tx) >> 1) >> 1, ((Ry + Ty) >> 1) >> 1);
     x1 = cmul(t2, make_int2((Rx - Tx) >> 1, (Ry - Ty) >> 1));
     x2 = cmul(t1, make_int2((Sx + Uy) >> 1, (Sy - Ux) >> 1));
@@ -146,8 +163,8 @@ template <bool SAT = true>
 QHD void last_r(int2 &x0, int2 &x1, int2 &x2, int2 &x3)
 {
     const int2 xa = x0, xb = x1, xc = x2, xd = x3;
-    const int Rx = s16c<SAT>(xa.x + xc.x), Ry = s16c<SAT>(xa.y + xc.y), Sx = s16c<SAT>(xa.x - xc.x), Sy = s16c<SAT>(xa.y - xc.y);
-    const int Tx = s16c<SAT>(xb.x + xd.x), Ty = s16c<SAT>(xb.y + xd.y), Ux = s16c<SAT>(xb.x - xd.x), Uy = s16c<SAT>(xb.y - xd.y);
+    const int Rx = qadd<SAT>(xa.x, xc.x), Ry = qadd<SAT>(xa.y, xc.y), Sx = qsub<SAT>(xa.x, xc.x), Sy = qsub<SAT>(xa.y, xc.y);
+    const int Tx = qadd<SAT>(xb.x, xd.x), Ty = qadd<SAT>(xb.y, xd.y), Ux = qsub<SAT>(xb.x, xd.x), Uy = qsub<SAT>(xb.y, xd.y);
     x0 = make_int2((Rx + Tx) >> 1, (Ry + Ty) >> 1);
     x1 = make_int2((Rx - Tx) >> 1, (Ry - Ty) >> 1);
     x2 = make_int2((Sx + Uy) >> 1, (Sy - Ux) >> 1);

@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(NT, RDSP_SPEC1024_MINB) k_spec1024(Spec1024Arg
                 const int i = 256 * d4 + 64 * d3 + tid;
                 const int b = i >> 7, n = i & 127;
                 const int32_t smp = ring[(int)((tick + 1 + b) & 7ull) * RDSP_BLK + n];
-                x[d4][d3] = make_int2((int16_t)((smp * (int32_t)__ldg(a.win + i)) >> 15), 0);      // imaginary part 0
+                // the int16 store of the reference changes nothing: 0 <= window <= 32767 (make_hann_q15) keeps the value in int16
+                x[d4][d3] = make_int2((smp * (int32_t)__ldg(a.win + i)) >> 15, 0);                 // imaginary part 0
             }
         // a frame that provably cannot saturate (fft_q15.cuh) takes the butterflies without the min / max pairs
         int amax = 0;

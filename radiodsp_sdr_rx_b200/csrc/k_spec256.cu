@@ -71,10 +71,11 @@ __global__ void __launch_bounds__(WARPS * 32, RDSP_SPEC256_MINB) k_spec256(Spec2
             int2 x[4][4];
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                // (v * w) >> 15 stored back into an int16 by the reference: keep the low 16 bits, sign-extended
+                // (v * w) >> 15 is stored back into an int16 by the reference; with 0 <= w <= 32767 (make_hann_q15) it
+                // lies in [-32767, 32766], so the narrowing changes nothing and is not spelled out
                 const int32_t w0 = lo16(wp[q]), w1 = hi16(wp[q]);
-                x[q >> 2][q & 3] = make_int2((int16_t)((lo16(pw[q]) * w0) >> 15), (int16_t)((hi16(pw[q]) * w0) >> 15));
-                x[2 + (q >> 2)][q & 3] = make_int2((int16_t)((lo16(cw[q]) * w1) >> 15), (int16_t)((hi16(cw[q]) * w1) >> 15));
+                x[q >> 2][q & 3] = make_int2((lo16(pw[q]) * w0) >> 15, (hi16(pw[q]) * w0) >> 15);
+                x[2 + (q >> 2)][q & 3] = make_int2((lo16(cw[q]) * w1) >> 15, (hi16(cw[q]) * w1) >> 15);
             }
 #pragma unroll
             for (int d2 = 0; d2 < 4; d2++) {                        // stage 1: span 64, butterfly i = 16 d2 + l, twiddle step 1
