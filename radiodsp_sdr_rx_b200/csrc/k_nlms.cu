@@ -16,8 +16,13 @@
 //
 //   * p[0..3] are four independent 96-tap dot products against the coefficients at the start of the group
 //     (registers, G lanes per channel, xor-shuffle reductions that pipeline);
-//   * R[i][j] = s_{j-i}(n+j) comes from three lag-autocorrelations: anchored exactly on the register window at
-//     the start of the group (3 x 96 MACs over the G lanes), then slid over the 4 samples (2 FMAs per lag);
+//   * R[i][j] = s_{j-i}(n+j) comes from three lag-autocorrelations.  They depend on the input only, so they are
+//     computed for the whole block BEFORE the main loop, spread over the eight virtual lanes of the channel instead of
+//     replicated in every lane (r02: a third of the loop's scalar instructions): virtual lane k takes samples
+//     16k .. 16k+15, anchors its sums exactly on six 16-sample chunk sums (no running sum lives longer than 16
+//     samples: a sum carried for long would lose all its digits when the signal drops by orders of magnitude inside
+//     the window, exactly where 1/(energy + eps) amplifies every error), slides them over its samples (2 FMAs per lag
+//     and sample) and leaves the six values a group needs in shared memory;
 //   * what remains sequential is a scalar chain of one subtract, one multiply and one FMA per sample;
 //   * the coefficient update c += sum_j g[j] x[n+j] is four independent FMAs per tap.
 //
@@ -49,17 +54,14 @@ namespace {
 constexpr int NWARPS_SCALAR = 2, NWARPS_PACKED = 4;
 constexpr int XS = 260;                      // floats per row: 16-byte aligned, rows 4 banks apart
 constexpr int D = 4;                         // samples per group
-#ifndef RDSP_NLMS_ANCHOR
-#define RDSP_NLMS_ANCHOR 4
-#endif
-constexpr int ANCHOR = RDSP_NLMS_ANCHOR;     // groups between exact re-anchorings of the lag sums (S/4 is a multiple)
+constexpr int RS = 196;                      // floats per row of lag sums: [32 groups][4] + [32 groups][2], rows 4 banks apart
 constexpr float LMS_EPS = 0.000000119209289f;
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
 template <int G, bool PACKED>
-__global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32) k_nlms(NlmsArgs a)
+__global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32, G == 4 ? 7 : 1) k_nlms(NlmsArgs a)   // 4-lane form: 7 CTAs per SM hold the 16 384 channels of cfg3 in one wave
 {
     constexpr int V = 8 / G;                     // virtual lanes (tap segments) per lane: 1 or 2
     constexpr int W = RDSP_LMS_NTAPS / 8;        // taps per segment
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
     constexpr int NWARPS = PACKED ? NWARPS_PACKED : NWARPS_SCALAR;
     __shared__ __align__(16) float s_x[NWARPS * CPW][XS];     // [0,128) previous block / outputs, [128,256) current
     __shared__ __align__(16) float s_x1[PACKED ? NWARPS * CPW : 1][XS];   // the same samples one to the left: s_x1[i] = x[i + 1]
+    __shared__ __align__(16) float s_r[NWARPS * CPW][RS];     // lag sums of the block: group q -> (r1[1], r1[2], r1[3], r2[2]) at 4q, (r2[3], r3[3]) at 128 + 2q
 
     pdl_release_successor();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,6 +81,7 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
     const int ch = active ? (a.list ? a.list[li] : li) : 0;
     float *xb = s_x[warp * CPW + lane / G];
     float *xs = s_x1[PACKED ? warp * CPW + lane / G : 0];     // odd window pairs load from here as aligned 16-byte quads
+    float *rr = s_r[warp * CPW + lane / G];
 
     constexpr int HP = S / 2;                    // window pairs
     float2 cpv[V][W / 2];                        // segment v: (c[2r+1], c[2r])
@@ -145,6 +149,7 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
     pdl_wait_predecessor();                      // own state is loaded; from here on: the predecessor's output
     fetch(0);
 
+    const bool st_y = g == 0 && (a.mode || peak), st_e = g == 0 && !(a.mode || peak);     // lane 0 of a channel emits: estimate or error
     for (int t = 0; t < a.T; t++) {
         const size_t cb = (size_t)t * a.C + ch;
         // ---- stage the current block into xb[128..255]
@@ -170,6 +175,73 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
         }
         __syncwarp();
         shift_copy(128);
+
+        // ---- lag sums r_l(b) = x[b-l]' x[b] (96 products, l = 1..3) of every sample of the block.  Virtual lane k owns
+        // samples b = 16k .. 16k+15: xnw[i] = x[16k-4+i] (entering products), xow[i] = x[16k-100+i] (leaving products).
+        {
+            float xnw[V][20], xow[V][20];
+            auto load_chunk = [&](int v) {
+                const int k = seg(v);
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    const float4 n4 = ld4(xb + 124 + 16 * k + 4 * i), o4 = ld4(xb + 28 + 16 * k + 4 * i);
+                    xnw[v][4 * i] = n4.x; xnw[v][4 * i + 1] = n4.y; xnw[v][4 * i + 2] = n4.z; xnw[v][4 * i + 3] = n4.w;
+                    xow[v][4 * i] = o4.x; xow[v][4 * i + 1] = o4.y; xow[v][4 * i + 2] = o4.z; xow[v][4 * i + 3] = o4.w;
+                }
+            };
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                const int k = seg(v);
+                load_chunk(v);
+                // chunk sums B_l(c) = sum over the 16 samples m of chunk c of x[m-l] x[m]: the entering samples are chunk k,
+                // the leaving ones chunk k - 6.  Slots 0..13 of a lag <-> chunks -6..7.
+                float bn1 = 0.f, bn2 = 0.f, bn3 = 0.f, bo1 = 0.f, bo2 = 0.f, bo3 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    bn1 = fmaf(xnw[v][3 + j], xnw[v][4 + j], bn1); bn2 = fmaf(xnw[v][2 + j], xnw[v][4 + j], bn2); bn3 = fmaf(xnw[v][1 + j], xnw[v][4 + j], bn3);
+                    bo1 = fmaf(xow[v][3 + j], xow[v][4 + j], bo1); bo2 = fmaf(xow[v][2 + j], xow[v][4 + j], bo2); bo3 = fmaf(xow[v][1 + j], xow[v][4 + j], bo3);
+                }
+                rr[k + 6] = bn1; rr[14 + k + 6] = bn2; rr[28 + k + 6] = bn3;
+                if (k < 6) { rr[k] = bo1; rr[14 + k] = bo2; rr[28 + k] = bo3; }      // (k = 6, 7: chunks 0, 1 — lanes 0, 1 write them)
+            }
+            __syncwarp();
+            // r_l(16k - 1) = B_l(k-6) + ... + B_l(k-1), summed in this order
+            float sl[V][3];
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                const int k = seg(v);
+#pragma unroll
+                for (int l = 0; l < 3; l++) {
+                    float acc = rr[14 * l + k];
+#pragma unroll
+                    for (int i = 1; i < 6; i++) acc = __fadd_rn(acc, rr[14 * l + k + i]);
+                    sl[v][l] = acc;
+                }
+            }
+            __syncwarp();
+            // slide: r_l(b) = r_l(b-1) + x[b-l] x[b] - x[b-l-96] x[b-96]; a group of 4 samples n..n+3 needs
+            // r1(n+1), r1(n+2), r1(n+3), r2(n+2) | r2(n+3), r3(n+3)
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                const int k = seg(v);
+                if (V > 1) load_chunk(v);                  // two chunks per lane: loaded again rather than kept in 80 registers
+                float s1 = sl[v][0], s2 = sl[v][1], s3 = sl[v][2];
+#pragma unroll
+                for (int qq = 0; qq < 4; qq++) {
+                    float r1[4], r2[4], r3[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++) {
+                        const int j = 4 * qq + jj;
+                        s1 = fmaf(xnw[v][3 + j], xnw[v][4 + j], s1); s1 = fmaf(-xow[v][3 + j], xow[v][4 + j], s1);
+                        s2 = fmaf(xnw[v][2 + j], xnw[v][4 + j], s2); s2 = fmaf(-xow[v][2 + j], xow[v][4 + j], s2);
+                        s3 = fmaf(xnw[v][1 + j], xnw[v][4 + j], s3); s3 = fmaf(-xow[v][1 + j], xow[v][4 + j], s3);
+                        r1[jj] = s1; r2[jj] = s2; r3[jj] = s3;
+                    }
+                    st4(rr + 16 * k + 4 * qq, make_float4(r1[1], r1[2], r1[3], r2[2]));
+                    *reinterpret_cast<float2 *>(rr + 128 + 8 * k + 2 * qq) = make_float2(r2[3], r3[3]);
+                }
+            }
+        }
         __syncwarp();
 
         // ---- segment-relative window u[m] = x[m - W*seg]; slots m mod S.  Before sample 0: m = -S .. -1 (all slots)
@@ -185,43 +257,14 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
                 O[2 * q] = make_float2(o.x, o.y); O[2 * q + 1] = make_float2(o.z, o.w);
             }
         }
-        float4 xn_p = ld4(xb + 124);                 // x[-4..-1]
-        float4 xo_p = ld4(xb + 28);                  // x[-100..-97]
-        const bool same_block_ref = first && t == 0;
+        const float *dref = (first && t == 0) ? xb + 128 : xb;      // desired signal: the previous block; on the very first call the same block
 
-        float s1 = 0.f, s2 = 0.f, s3 = 0.f;
         for (int n0 = 0; n0 < RDSP_BLK; n0 += S) {
 #pragma unroll
             for (int gq = 0; gq < S / 4; gq++) {
                 const int n = n0 + 4 * gq;
                 if (n < RDSP_BLK) {
                     const int sb = 4 * gq;                                  // slot of u[n] (n0 is a multiple of S)
-                    // ---- lag sums s_l(n-1) = x[n-1-l]' x[n-1], l = 1..3, anchored EXACTLY on the window every ANCHOR
-                    // groups (the window still holds m = n-W-4 .. n-1) and slid over the samples in between.  A running
-                    // sum carried for long would lose all its digits when the signal drops by orders of magnitude
-                    // inside the window, exactly where 1/(energy + eps) amplifies every error.
-                    if (gq % ANCHOR == 0) {
-                        float a1[V], a2[V], a3[V];
-#pragma unroll
-                        for (int v = 0; v < V; v++) {
-                            a1[v] = 0.f; a2[v] = 0.f; a3[v] = 0.f;
-#pragma unroll
-                            for (int i = 0; i < W; i++) {
-                                const float uk = wv(v, sb - 1 - i);
-                                a1[v] = fmaf(wv(v, sb - 2 - i), uk, a1[v]);
-                                a2[v] = fmaf(wv(v, sb - 3 - i), uk, a2[v]);
-                                a3[v] = fmaf(wv(v, sb - 4 - i), uk, a3[v]);
-                            }
-                        }
-                        // two segments in one lane: their sum IS the xor-4 stage of the 8-lane butterfly
-                        s1 = V == 2 ? a1[0] + a1[V - 1] : a1[0]; s2 = V == 2 ? a2[0] + a2[V - 1] : a2[0]; s3 = V == 2 ? a3[0] + a3[V - 1] : a3[0];
-#pragma unroll
-                        for (int o = G / 2 >= 4 ? 4 : 2; o > 0; o >>= 1) {
-                            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                            s3 += __shfl_xor_sync(0xffffffffu, s3, o);
-                        }
-                    }
                     // ---- loads
 #pragma unroll
                     for (int v = 0; v < V; v++) {
@@ -235,13 +278,12 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
                     }
                     const float4 xn4 = ld4(xb + 128 + n);                   // in[n..n+3]
                     const float4 xo4 = ld4(xb + 32 + n);                    // x[n-96 .. n-93]
-                    const float4 d4 = same_block_ref ? xn4 : ld4(xb + n);   // desired
+                    const float4 d4 = ld4(dref + n);                        // desired (always a load: a select costs four moves)
+                    const float4 ra = ld4(rr + n);                          // r1(n+1), r1(n+2), r1(n+3), r2(n+2)
+                    const float2 rb = *reinterpret_cast<const float2 *>(rr + 128 + n / 2);   // r2(n+3), r3(n+3)
                     const float xn[4] = {xn4.x, xn4.y, xn4.z, xn4.w};
                     const float xo[4] = {xo4.x, xo4.y, xo4.z, xo4.w};
                     const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-                    // recent / old samples around the group: index 4 + j <-> sample n + j
-                    const float xr[8] = {xn_p.x, xn_p.y, xn_p.z, xn_p.w, xn4.x, xn4.y, xn4.z, xn4.w};   // x[n-4 .. n+3]
-                    const float xq[8] = {xo_p.x, xo_p.y, xo_p.z, xo_p.w, xo4.x, xo4.y, xo4.z, xo4.w};   // x[n-100 .. n-93]
 
                     // ---- p[j] = c' x[n+j] with the coefficients at the start of the group: even taps and odd taps in
                     // accumulators of their own, added at the end (both forms sum in this order)
@@ -290,8 +332,8 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
                         }
                     }
 
-                    // ---- scalars that do not depend on the error: energy, normaliser, lag sums
-                    float qn[4], r1[4], r2[4], r3[4];
+                    // ---- scalars that do not depend on the error: energy, normaliser
+                    float qn[4];
                     // squares, the + eps and the * mu two samples per instruction in the packed form (same roundings)
                     float xo2[4], xn2[4], en[4];
                     if (PACKED) {
@@ -337,28 +379,20 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
                             for (int j = 0; j < 4; j++) qn[j] = mu * rc[j];
                         }
                     }
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        // s_l(b) = s_l(b-1) + x[b-l] x[b] - x[b-l-96] x[b-96],  b = n + j
-                        s1 = fmaf(xr[4 + j - 1], xn[j], s1); s1 = fmaf(-xq[4 + j - 1], xo[j], s1);
-                        s2 = fmaf(xr[4 + j - 2], xn[j], s2); s2 = fmaf(-xq[4 + j - 2], xo[j], s2);
-                        s3 = fmaf(xr[4 + j - 3], xn[j], s3); s3 = fmaf(-xq[4 + j - 3], xo[j], s3);
-                        r1[j] = s1; r2[j] = s2; r3[j] = s3;
-                    }
 
                     // ---- the sequential part: one subtract, one multiply, one FMA per sample
                     float y[4], e[4], gj[4];
                     y[0] = p[0];
                     e[0] = dd[0] - y[0]; gj[0] = e[0] * qn[0];
-                    y[1] = fmaf(gj[0], r1[1], p[1]);
+                    y[1] = fmaf(gj[0], ra.x, p[1]);
                     e[1] = dd[1] - y[1]; gj[1] = e[1] * qn[1];
-                    y[2] = fmaf(gj[1], r1[2], fmaf(gj[0], r2[2], p[2]));
+                    y[2] = fmaf(gj[1], ra.y, fmaf(gj[0], ra.w, p[2]));
                     e[2] = dd[2] - y[2]; gj[2] = e[2] * qn[2];
-                    y[3] = fmaf(gj[2], r1[3], fmaf(gj[1], r2[3], fmaf(gj[0], r3[3], p[3])));
+                    y[3] = fmaf(gj[2], ra.z, fmaf(gj[1], rb.x, fmaf(gj[0], rb.y, p[3])));
                     e[3] = dd[3] - y[3]; gj[3] = e[3] * qn[3];
 
-                    if (g == 0)
-                        st4(xb + n, (a.mode || peak) ? make_float4(y[0], y[1], y[2], y[3]) : make_float4(e[0], e[1], e[2], e[3]));
+                    if (st_y) st4(xb + n, make_float4(y[0], y[1], y[2], y[3]));        // two predicated stores, no selects
+                    if (st_e) st4(xb + n, make_float4(e[0], e[1], e[2], e[3]));
 
                     // ---- coefficient update c += sum_j g[j] x[n+j]
 #pragma unroll
@@ -375,8 +409,6 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32)
                             }
                         }
                     }
-                    xn_p = xn4;
-                    xo_p = xo4;
                 }
             }
         }

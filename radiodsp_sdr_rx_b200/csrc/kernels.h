@@ -12,7 +12,7 @@
 template <typename K>
 inline void rdsp_uniform_carveout(K kernel)
 {
-    static const int pct = [] { const char *e = getenv("RDSP_CARVEOUT"); return e ? atoi(e) : 50; }();
+    static const int pct = [] { const char *e = getenv("RDSP_CARVEOUT"); return e ? atoi(e) : 100; }();
     if (pct >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 // function attributes belong to a (kernel, device) pair: once per device, and safe when handles on different GPUs
