@@ -118,13 +118,14 @@ __device__ __forceinline__ uint32_t sqrt_u32_approx_fast(uint32_t in, const uint
     return in == 0u ? 0u : n;
 }
 
-// arm_float_to_q15: truncate toward zero, saturate
+// arm_float_to_q15: truncate toward zero, saturate.  cvt.rzi.s16.f32 is exactly that in one instruction (F2I.S16.TRUNC):
+// a float-to-integer cvt clamps to the range of its destination type and turns NaN into 0 (the compare / select /
+// min / max form of r01 was eight instructions per sample).
 __device__ __forceinline__ int32_t f32_to_q15(float v)
 {
-    float s = v * 32768.0f;
-    s = fminf(fmaxf(s, -40000.0f), 40000.0f);          // keeps the cast defined; NaN -> -40000 -> sat
-    if (v != v) s = 0.0f;
-    return sat16((int32_t)s);                           // cvt.rzi
+    short r;
+    asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(r) : "f"(v * 32768.0f));
+    return (int32_t)r;
 }
 
 // streaming (read-once / write-once) 128-bit global accesses
