@@ -106,7 +106,44 @@ HD void fft256_phaseB2(int lane, float2 v[8], const float2 *buf)
     }
 }
 
+// The same transform with the lane's 14 twiddles held in registers (twA[k] = W256^(lane (k+1)), twB[q] = W32^(m1 (q+1))):
+// they are loop invariants of a kernel that transforms block after block, and the table reads were 30 % of the shared-memory
+// wavefronts of a transform.
+HD void fft256_load_twiddles(int lane, const float2 *tw, float2 twA[7], float2 twB[7])
+{
+    const int m1 = lane & 3;
+#pragma unroll
+    for (int k = 1; k < 8; k++) { twA[k - 1] = tw[(lane * k) & 255]; twB[k - 1] = tw[8 * m1 * k]; }
+}
+HD void fft256_phaseA_r(int lane, float2 v[8], float2 *buf, const float2 twA[7])
+{
+    dft8(v);
+#pragma unroll
+    for (int k2 = 1; k2 < 8; k2++) v[k2] = c_mulconj(v[k2], twA[k2 - 1]);
+#pragma unroll
+    for (int k2 = 0; k2 < 8; k2++) buf[k2 * FFT256_LDY + lane] = v[k2];
+}
+HD void fft256_phaseB1_store_r(int lane, float2 v[8], float2 *buf, const float2 twB[7])
+{
+    dft8(v);
+#pragma unroll
+    for (int q2 = 1; q2 < 8; q2++) v[q2] = c_mulconj(v[q2], twB[q2 - 1]);
+#pragma unroll
+    for (int q2 = 0; q2 < 8; q2++) buf[q2 * FFT256_LDY + lane] = v[q2];
+}
+
 #ifdef __CUDACC__
+__device__ __forceinline__ void fft256_warp_r(int lane, float2 v[8], float2 *buf, const float2 twA[7], const float2 twB[7])
+{
+    fft256_phaseA_r(lane, v, buf, twA);
+    __syncwarp();
+    fft256_phaseB1_load(lane, v, buf);
+    __syncwarp();
+    fft256_phaseB1_store_r(lane, v, buf, twB);
+    __syncwarp();
+    fft256_phaseB2(lane, v, buf);
+    __syncwarp();
+}
 // v[j] = x[lane + 32 j] on entry, X[lane + 32 j] on exit.  buf: FFT256_BUF float2 of warp-private smem.
 __device__ __forceinline__ void fft256_warp(int lane, float2 v[8], float2 *buf, const float2 *tw)
 {

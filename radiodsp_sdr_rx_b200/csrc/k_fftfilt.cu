@@ -22,7 +22,10 @@
 
 namespace {
 
-constexpr int WARPS = 8;
+#ifndef RDSP_FFTFILT_WARPS
+#define RDSP_FFTFILT_WARPS 8
+#endif
+constexpr int WARPS = RDSP_FFTFILT_WARPS;
 
 // arm_sin_f32 / arm_cos_f32 (CMSIS-DSP fast math): quarter = 0 for the sine, 0.25 for the cosine.
 // Every operation is a separately rounded f32 operation, in the order of the C source (no FMA contraction).
@@ -42,6 +45,12 @@ __device__ __forceinline__ float arm_trig_f32(float x, bool cosine, const float 
 
 #ifndef RDSP_FFTFILT_MINB
 #define RDSP_FFTFILT_MINB 3
+#endif
+#ifndef RDSP_FFT_TW_REGS
+#define RDSP_FFT_TW_REGS 0
+#endif
+#ifndef RDSP_FFTFILT_WARPS
+#define RDSP_FFTFILT_WARPS 8
 #endif
 __global__ void __launch_bounds__(WARPS * 32, RDSP_FFTFILT_MINB) k_fftfilt(FftFiltArgs a)
 {
@@ -81,6 +90,13 @@ __global__ void __launch_bounds__(WARPS * 32, RDSP_FFTFILT_MINB) k_fftfilt(FftFi
         for (int j = 0; j < 4; j++) pw[j] = lrow[lane + 32 * j];
     }
     float nfloor = a.nfloor[ch];
+#if RDSP_FFT_TW_REGS
+    float2 twA[7], twB[7];
+    fft256_load_twiddles(lane, s_tw, twA, twB);
+#define FFT256(v) fft256_warp_r(lane, v, buf, twA, twB)
+#else
+#define FFT256(v) fft256_warp(lane, v, buf, s_tw)
+#endif
 
     pdl_wait_predecessor();                            // tables, mask, previous block are loaded; the rows are the predecessor's output
     for (int t = 0; t < a.T; t++) {
@@ -104,7 +120,7 @@ __global__ void __launch_bounds__(WARPS * 32, RDSP_FFTFILT_MINB) k_fftfilt(FftFi
             pw[j] = cw[j];
         }
 
-        fft256_warp(lane, v, buf, s_tw);                   // v[j] = X[lane + 32 j]
+        FFT256(v);                   // v[j] = X[lane + 32 j]
 
         // the inverse transform is conj -> forward -> conj -> 1/N: the first conjugation rides on the product
         if (!spectral) {
@@ -133,7 +149,7 @@ __global__ void __launch_bounds__(WARPS * 32, RDSP_FFTFILT_MINB) k_fftfilt(FftFi
             }
         }
 
-        fft256_warp(lane, v, buf, s_tw);
+        FFT256(v);
 
         // keep x[128 + lane + 32 h]; re-distribute so that each lane owns 4 consecutive samples
 #pragma unroll

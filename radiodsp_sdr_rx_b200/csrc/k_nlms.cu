@@ -54,6 +54,9 @@ namespace {
 constexpr int NWARPS_SCALAR = 2, NWARPS_PACKED = 4;
 constexpr int XS = 260;                      // floats per row: 16-byte aligned, rows 4 banks apart
 constexpr int D = 4;                         // samples per group
+#ifndef RDSP_NLMS_MINB8
+#define RDSP_NLMS_MINB8 1
+#endif
 constexpr int RS = 196;                      // floats per row of lag sums: [32 groups][4] + [32 groups][2], rows 4 banks apart
 constexpr float LMS_EPS = 0.000000119209289f;
 
@@ -61,7 +64,7 @@ __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
 template <int G, bool PACKED>
-__global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32, G == 4 ? 7 : 1) k_nlms(NlmsArgs a)   // 4-lane form: 7 CTAs per SM hold the 16 384 channels of cfg3 in one wave
+__global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32, G == 4 ? 7 : RDSP_NLMS_MINB8) k_nlms(NlmsArgs a)   // 4-lane form: 7 CTAs per SM hold the 16 384 channels of cfg3 in one wave
 {
     constexpr int V = 8 / G;                     // virtual lanes (tap segments) per lane: 1 or 2
     constexpr int W = RDSP_LMS_NTAPS / 8;        // taps per segment
