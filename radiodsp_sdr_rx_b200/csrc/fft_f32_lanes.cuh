@@ -92,14 +92,17 @@ HD void fft256_phaseB1_store(int lane, float2 v[8], float2 *buf, const float2 *t
 #pragma unroll
     for (int q2 = 1; q2 < 8; q2++) v[q2] = c_mulconj(v[q2], tw[8 * m1 * q2]);
 #pragma unroll
-    for (int q2 = 0; q2 < 8; q2++) buf[q2 * FFT256_LDY + lane] = v[q2];      // lane = k2*4 + m1
+    for (int q2 = 0; q2 < 8; q2++) buf[q2 * FFT256_LDY + lane + ((lane >> 4) << 1)] = v[q2];   // upper half of a row 16 bytes further: see phase B2      // lane = k2*4 + m1
 }
 HD void fft256_phaseB2(int lane, float2 v[8], const float2 *buf)
 {
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int p = lane + 32 * h, k2 = p & 7, q2 = p >> 3;
-        const float2 *z = buf + q2 * FFT256_LDY + k2 * 4;
+        // 32-byte reads of eight lanes, 32 bytes apart: k2 and k2 + 4 would meet on the same banks (the ncu capture of r02b
+        // showed a third of the kernel's shared-memory wavefronts were conflicts), so rows are stored with their upper half
+        // skewed by 16 bytes
+        const float2 *z = buf + q2 * FFT256_LDY + k2 * 4 + ((k2 >> 2) << 1);
         float2 z0 = z[0], z1 = z[1], z2 = z[2], z3 = z[3];
         dft4(z0, z1, z2, z3);
         v[0 + h] = z0; v[2 + h] = z1; v[4 + h] = z2; v[6 + h] = z3;
@@ -129,7 +132,7 @@ HD void fft256_phaseB1_store_r(int lane, float2 v[8], float2 *buf, const float2 
 #pragma unroll
     for (int q2 = 1; q2 < 8; q2++) v[q2] = c_mulconj(v[q2], twB[q2 - 1]);
 #pragma unroll
-    for (int q2 = 0; q2 < 8; q2++) buf[q2 * FFT256_LDY + lane] = v[q2];
+    for (int q2 = 0; q2 < 8; q2++) buf[q2 * FFT256_LDY + lane + ((lane >> 4) << 1)] = v[q2];   // upper half of a row 16 bytes further: see phase B2
 }
 
 #ifdef __CUDACC__

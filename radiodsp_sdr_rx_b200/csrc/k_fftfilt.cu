@@ -23,7 +23,7 @@
 namespace {
 
 #ifndef RDSP_FFTFILT_WARPS
-#define RDSP_FFTFILT_WARPS 8
+#define RDSP_FFTFILT_WARPS 4
 #endif
 constexpr int WARPS = RDSP_FFTFILT_WARPS;
 
@@ -44,13 +44,13 @@ __device__ __forceinline__ float arm_trig_f32(float x, bool cosine, const float 
 }
 
 #ifndef RDSP_FFTFILT_MINB
-#define RDSP_FFTFILT_MINB 3
+#define RDSP_FFTFILT_MINB 5     // 96 registers (r02b A/B on one box, cfg5 step: 8 warps x 3 CTAs 444.5 us, 8 x 2 441.6, 6 x 3 437.8, 4 x 5 420.6)
 #endif
 #ifndef RDSP_FFT_TW_REGS
-#define RDSP_FFT_TW_REGS 0
+#define RDSP_FFT_TW_REGS 1      // the lane's 14 twiddles live in registers across the blocks of a call (86 -> 64 us per 8-block launch)
 #endif
 #ifndef RDSP_FFTFILT_WARPS
-#define RDSP_FFTFILT_WARPS 8
+#define RDSP_FFTFILT_WARPS 4
 #endif
 __global__ void __launch_bounds__(WARPS * 32, RDSP_FFTFILT_MINB) k_fftfilt(FftFiltArgs a)
 {
@@ -151,34 +151,29 @@ __global__ void __launch_bounds__(WARPS * 32, RDSP_FFTFILT_MINB) k_fftfilt(FftFi
 
         FFT256(v);
 
-        // keep x[128 + lane + 32 h]; re-distribute so that each lane owns 4 consecutive samples
-#pragma unroll
-        for (int h = 0; h < 4; h++)
-            buf[lane + 32 * h] = p_mul(v[4 + h], make_float2(1.0f / 256.0f, -1.0f / 256.0f));
-        __syncwarp();
+        // keep x[128 + lane + 32 h].  The lane stores its four samples where they are: every store instruction of the warp
+        // covers one contiguous 64- or 128-byte run, so the round trip through shared memory that gave each lane four
+        // consecutive samples (r01) bought nothing and cost 16 of the block's 144 shared-memory wavefronts.
         float2 o[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) o[i] = buf[4 * lane + i];
-        __syncwarp();
+        for (int h = 0; h < 4; h++) o[h] = p_mul(v[4 + h], make_float2(1.0f / 256.0f, -1.0f / 256.0f));
 
         if (to_dnr) {
-            *reinterpret_cast<float4 *>(a.out_f32_L + cb * RDSP_BLK + 4 * lane) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
+#pragma unroll
+            for (int h = 0; h < 4; h++) a.out_f32_L[cb * RDSP_BLK + lane + 32 * h] = o[h].x;
         } else {
             if (a.out_mono) {
-                st_stream8(a.out_mono + cb * RDSP_BLK + lane * 4,
-                           make_int2((int)mk16(f32_to_q15(o[0].x), f32_to_q15(o[1].x)), (int)mk16(f32_to_q15(o[2].x), f32_to_q15(o[3].x))));
+#pragma unroll
+                for (int h = 0; h < 4; h++) a.out_mono[cb * RDSP_BLK + lane + 32 * h] = (int16_t)f32_to_q15(o[h].x);
             } else {
-                int4 q;
-                q.x = (int)mk16(f32_to_q15(o[0].x), f32_to_q15(o[0].y));
-                q.y = (int)mk16(f32_to_q15(o[1].x), f32_to_q15(o[1].y));
-                q.z = (int)mk16(f32_to_q15(o[2].x), f32_to_q15(o[2].y));
-                q.w = (int)mk16(f32_to_q15(o[3].x), f32_to_q15(o[3].y));
-                st_stream16(a.out_stereo + cb * 2 * RDSP_BLK + lane * 8, q);
+                uint32_t *dst = reinterpret_cast<uint32_t *>(a.out_stereo + cb * 2 * RDSP_BLK);
+#pragma unroll
+                for (int h = 0; h < 4; h++) dst[lane + 32 * h] = mk16(f32_to_q15(o[h].x), f32_to_q15(o[h].y));
             }
             if (a.dbg) {
-                float4 *dp = reinterpret_cast<float4 *>(a.dbg + cb * 2 * RDSP_BLK + lane * 8);
-                dp[0] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
-                dp[1] = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+                float2 *dp = reinterpret_cast<float2 *>(a.dbg + cb * 2 * RDSP_BLK);
+#pragma unroll
+                for (int h = 0; h < 4; h++) dp[lane + 32 * h] = o[h];
             }
         }
     }
