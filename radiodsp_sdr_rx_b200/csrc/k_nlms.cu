@@ -40,6 +40,10 @@
 // so that every (x[k-1], x[k]) a pair of taps meets is an aligned register pair.  Each lane of a pair is exactly the
 // scalar FMA sequence of the unpacked form (even taps in one lane, odd taps in the other), so results do not change.
 //
+// (r02b, measured and not kept: the odd pairs assembled from the even ones with register moves instead of the shifted
+// shared-memory copy — 4 wavefronts per group less, but the unrolled loop loses its register rotation: 134 moves per 16
+// samples, 496 -> 601 instructions.)
+//
 // The per-channel state in HBM is coefficients (384 B) + previous block (512 B) + energy: the CMSIS state
 // buffer (last 95 inputs), x0 and the lag sums are functions of the previous block, so they are not stored.
 #include "rdsp_common.cuh"
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32,
     constexpr int NWARPS = PACKED ? NWARPS_PACKED : NWARPS_SCALAR;
     __shared__ __align__(16) float s_x[NWARPS * CPW][XS];     // [0,128) previous block / outputs, [128,256) current
     __shared__ __align__(16) float s_x1[PACKED ? NWARPS * CPW : 1][XS];   // the same samples one to the left: s_x1[i] = x[i + 1]
-    __shared__ __align__(16) float s_r[NWARPS * CPW][RS];     // lag sums of the block: group q -> (r1[1], r1[2], r1[3], r2[2]) at 4q, (r2[3], r3[3]) at 128 + 2q
+    __shared__ __align__(16) float s_r[NWARPS * CPW][RS];     // lag sums of the block: group q = 4k + qq -> (r1[1], r1[2], r1[3], r2[2]) at 4 (8 qq + k), (r2[3], r3[3]) at 128 + 2 (8 qq + k)
 
     pdl_release_successor();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -240,8 +244,10 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32,
                         s3 = fmaf(xnw[v][1 + j], xnw[v][4 + j], s3); s3 = fmaf(-xow[v][1 + j], xow[v][4 + j], s3);
                         r1[jj] = s1; r2[jj] = s2; r3[jj] = s3;
                     }
-                    st4(rr + 16 * k + 4 * qq, make_float4(r1[1], r1[2], r1[3], r2[2]));
-                    *reinterpret_cast<float2 *>(rr + 128 + 8 * k + 2 * qq) = make_float2(r2[3], r3[3]);
+                    // group 4k + qq sits at slot 8 qq + k: the eight lanes of a channel store 16 bytes apart (conflict free; chunk
+                    // after chunk, 64 bytes apart, was a 4-way bank conflict)
+                    st4(rr + 4 * (8 * qq + k), make_float4(r1[1], r1[2], r1[3], r2[2]));
+                    *reinterpret_cast<float2 *>(rr + 128 + 2 * (8 * qq + k)) = make_float2(r2[3], r3[3]);
                 }
             }
         }
@@ -282,8 +288,9 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32,
                     const float4 xn4 = ld4(xb + 128 + n);                   // in[n..n+3]
                     const float4 xo4 = ld4(xb + 32 + n);                    // x[n-96 .. n-93]
                     const float4 d4 = ld4(dref + n);                        // desired (always a load: a select costs four moves)
-                    const float4 ra = ld4(rr + n);                          // r1(n+1), r1(n+2), r1(n+3), r2(n+2)
-                    const float2 rb = *reinterpret_cast<const float2 *>(rr + 128 + n / 2);   // r2(n+3), r3(n+3)
+                    const int rslot = 8 * gq + n0 / S;                      // group n / 4 = 4 (n0 / 16) + gq -> slot 8 gq + n0 / 16
+                    const float4 ra = ld4(rr + 4 * rslot);                  // r1(n+1), r1(n+2), r1(n+3), r2(n+2)
+                    const float2 rb = *reinterpret_cast<const float2 *>(rr + 128 + 2 * rslot);   // r2(n+3), r3(n+3)
                     const float xn[4] = {xn4.x, xn4.y, xn4.z, xn4.w};
                     const float xo[4] = {xo4.x, xo4.y, xo4.z, xo4.w};
                     const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
