@@ -81,7 +81,7 @@ __device__ __forceinline__ void fft1024_passes(int2 (&x)[4][4], int2 *s_fft, con
 }
 
 #ifndef RDSP_SPEC1024_MINB
-#define RDSP_SPEC1024_MINB 12    // 80 registers, no spills (10 = what 96 registers allowed; 12 / 14: 495.6 / 499.6 us per step with k_spec256 at 4)
+#define RDSP_SPEC1024_MINB 16    // 64 registers, no spills (r02b A/B on one box, cfg5 step: 10 / 12 / 14 / 16 CTAs per SM = 417.7 / 416.7 / 414.3 / 413.6 us; alone 96.9 / 94.4 / 92.1 / 91.6 us)
 #endif
 __global__ void __launch_bounds__(NT, RDSP_SPEC1024_MINB) k_spec1024(Spec1024Args a)
 {

@@ -107,8 +107,7 @@ __global__ void __launch_bounds__(WARPS * 32, RDSP_SPEC256_MINB) k_spec256(Spec2
             __syncwarp();                                            // the buffer may be rewritten by the next block
 #pragma unroll
             for (int d0 = 0; d0 < 4; d0++) {                        // stage 3: span 4, j = d0, twiddle step 16
-                const int ic = 16 * d0;
-                q15fft::middle_r(y[0][d0], y[1][d0], y[2][d0], y[3][d0], s_tw[ic], s_tw[2 * ic], s_tw[3 * ic]);
+                q15fft::middle_r(y[0][d0], y[1][d0], y[2][d0], y[3][d0], a.tw3[d0][0], a.tw3[d0][1], a.tw3[d0][2]);
             }
 #pragma unroll
             for (int d1 = 0; d1 < 4; d1++) q15fft::last_r(y[d1][0], y[d1][1], y[d1][2], y[d1][3]);

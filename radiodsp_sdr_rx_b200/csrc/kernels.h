@@ -175,6 +175,8 @@ struct Spec256Args {
     int div_shift;                  // (magsq * div_magic) >> div_shift == magsq / naverage for magsq <= 2^31
     const int2 *tw;             // [3072] twiddleCoef_4096_q15 as (cos, sin) int pairs
     const int16_t *win;         // [256] Hann
+    int2 tw3[4][3];             // tw[256 d0 k], k = 1..3: the twiddles of stage 3 are the same for every lane, so they travel as kernel
+                                // parameters (constant-bank operands of the multiplies) instead of 12 shared-memory reads per frame
 };
 void launch_spec256(const Spec256Args &a, cudaStream_t st);
 

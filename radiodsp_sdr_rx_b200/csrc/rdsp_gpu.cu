@@ -91,6 +91,7 @@ struct rdsp_gpu {
     int masks_uploaded = 0, mask_cap = 0;
     float2 *d_masks = nullptr;
     int2 *d_tw = nullptr;
+    int2 tw3_256[4][3] = {};
     int16_t *d_win256 = nullptr, *d_win1024 = nullptr;
     float2 *d_tw256 = nullptr;
     float *d_sin512 = nullptr;
@@ -611,6 +612,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
             a.div_shift = 32 + lgn;
             a.div_magic = ((1ull << a.div_shift) + h->cfg.spec256_naverage - 1) / h->cfg.spec256_naverage;
             a.tw = h->d_tw; a.win = h->d_win256;
+            for (int d0 = 0; d0 < 4; d0++) for (int k = 0; k < 3; k++) a.tw3[d0][k] = h->tw3_256[d0][k];
             { Prof pr(h, KK_SPEC256, s_spec); launch_spec256(a, s_spec); }
         } else if (piped) {
             CK(cudaStreamWaitEvent(s_spec, h->ev_fork, 0));
@@ -945,6 +947,8 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
         std::vector<int2> tw2(3072);
         for (int k = 0; k < 3072; k++) tw2[k] = make_int2((int16_t)(tw[k] & 0xFFFFu), (int16_t)(tw[k] >> 16));
         CKC(cudaMemcpy(h->d_tw, tw2.data(), tw2.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        for (int d0 = 0; d0 < 4; d0++)
+            for (int k = 1; k <= 3; k++) h->tw3_256[d0][k - 1] = tw2[256 * d0 * k];       // stage 3 of the 256-point transform (k_spec256)
     }
     if (sm & RDSP_STAGE_SPEC256) {
         CKC(dalloc(&h->d_bq_state, C * 8));
