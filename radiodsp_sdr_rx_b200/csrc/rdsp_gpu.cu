@@ -59,8 +59,11 @@ struct rdsp_gpu {
     // D2H of call n-1 overlap the kernels of call n (async handles)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     // host I/O: a ring of n_stage device staging buffers (H2D of call n+1, kernels of call n, D2H of call n-1 overlap;
-    // RDSP_HOST_STAGES = 2..4: measured 11.5 - 11.7 GS/s end to end for 2, 3 and 4 alike (cfg5; both-way PCIe copies of
-    // the box alone reach 49.6 + 50.6 GB/s = 12.4 GS/s), so two it is)
+    // RDSP_HOST_STAGES = 2..4.  Measured end to end, cfg5: with 8 blocks per call 11.5 - 11.7 GS/s for 2, 3 and 4 alike (a
+    // call's copies and kernels are 0.7 / 0.4 ms: two buffers overlap them), so two it is there; with ONE block per call the
+    // three phases of a call take ~ 90 / 100 / 90 us and two buffers leave them waiting for each other: 2 / 3 / 4 buffers =
+    // 7.6 - 8.4 / 9.1 - 9.7 / 9.8 GS/s (0.84 / 0.92 - 0.97 / 0.97 of the copy ceiling measured in the same run), so handles
+    // for short calls (max_blocks_per_call <= 4) get four)
     static constexpr int kMaxStage = 4;
     int n_stage = 2;
     cudaEvent_t ev_h2d[kMaxStage] = {}, ev_comp[kMaxStage] = {}, ev_d2h[kMaxStage] = {};
@@ -981,6 +984,7 @@ int rdsp_gpu_create(const rdsp_gpu_config_t *cfg, rdsp_gpu_t **out)
     if (cfg->io_location == RDSP_IO_HOST) {
         CKC(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
         CKC(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+        h->n_stage = h->maxT <= 4 ? rdsp_gpu::kMaxStage : 2;
         if (const char *e = getenv("RDSP_HOST_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= rdsp_gpu::kMaxStage) h->n_stage = v; }
         for (int i = 0; i < h->n_stage; i++) {
             CKC(dalloc(&h->d_in_stage2[i], T * C * 2 * RDSP_BLK));
