@@ -52,6 +52,8 @@ __device__ __forceinline__ float arm_trig_f32(float x, bool cosine, const float 
 #ifndef RDSP_FFTFILT_WARPS
 #define RDSP_FFTFILT_WARPS 4
 #endif
+// RING: one-block calls, where this kernel appends the audio rows it emits to the ring of the audio spectrum (FftFiltArgs::ring)
+template <bool RING>
 __global__ void __launch_bounds__(WARPS * 32, RDSP_FFTFILT_MINB) k_fftfilt(FftFiltArgs a)
 {
     __shared__ float2 s_tw[256];
@@ -170,6 +172,13 @@ __global__ void __launch_bounds__(WARPS * 32, RDSP_FFTFILT_MINB) k_fftfilt(FftFi
 #pragma unroll
                 for (int h = 0; h < 4; h++) dst[lane + 32 * h] = mk16(f32_to_q15(o[h].x), f32_to_q15(o[h].y));
             }
+            if (RING) {
+                // one-block calls: the audio-spectrum kernel would launch a CTA per channel only to copy this row into its ring
+                // on three ticks out of four; the row is appended here instead (k_spec1024.cu, `appended`)
+                int16_t *rrow = a.ring + ((size_t)ch * 8 + (size_t)((a.tick_in->tick + (unsigned long long)t) & 7ull)) * RDSP_BLK;
+#pragma unroll
+                for (int h = 0; h < 4; h++) rrow[lane + 32 * h] = (int16_t)f32_to_q15(o[h].x);
+            }
             if (a.dbg) {
                 float2 *dp = reinterpret_cast<float2 *>(a.dbg + cb * 2 * RDSP_BLK);
 #pragma unroll
@@ -190,6 +199,8 @@ __global__ void __launch_bounds__(WARPS * 32, RDSP_FFTFILT_MINB) k_fftfilt(FftFi
 
 void launch_fftfilt(const FftFiltArgs &a, cudaStream_t st)
 {
-    RDSP_CARVEOUT_ONCE(k_fftfilt);
-    if (a.n > 0) rdsp_launch(k_fftfilt, (a.n + WARPS - 1) / WARPS, WARPS * 32, 0, st, a.pdl != 0, a);
+    RDSP_CARVEOUT_ONCE(k_fftfilt<false>); RDSP_CARVEOUT_ONCE(k_fftfilt<true>);
+    if (a.n <= 0) return;
+    if (a.ring) rdsp_launch(k_fftfilt<true>, (a.n + WARPS - 1) / WARPS, WARPS * 32, 0, st, a.pdl != 0, a);
+    else rdsp_launch(k_fftfilt<false>, (a.n + WARPS - 1) / WARPS, WARPS * 32, 0, st, a.pdl != 0, a);
 }

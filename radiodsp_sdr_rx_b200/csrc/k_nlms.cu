@@ -67,7 +67,8 @@ constexpr float LMS_EPS = 0.000000119209289f;
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
-template <int G, bool PACKED>
+// RING: one-block calls, where the DNR appends the audio rows it emits to the ring of the audio spectrum (NlmsArgs::ring)
+template <int G, bool PACKED, bool RING>
 __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32, G == 4 ? 7 : RDSP_NLMS_MINB8) k_nlms(NlmsArgs a)   // 4-lane form: 7 CTAs per SM hold the 16 384 channels of cfg3 in one wave
 {
     constexpr int V = 8 / G;                     // virtual lanes (tap segments) per lane: 1 or 2
@@ -432,6 +433,8 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32,
             } else {
                 int4 *dst = reinterpret_cast<int4 *>(a.out_stereo + cb * 2 * RDSP_BLK);
                 int2 *dst_mono = reinterpret_cast<int2 *>(a.out_mono + cb * RDSP_BLK);
+                // one-block calls: the L row goes into the audio-spectrum ring from here (k_spec1024.cu, `appended`)
+                int2 *dst_ring = RING ? reinterpret_cast<int2 *>(a.ring + ((size_t)ch * 8 + (size_t)((a.tick_in->tick + (unsigned long long)t) & 7ull)) * RDSP_BLK) : nullptr;
                 float4 *dbg = a.dbg ? reinterpret_cast<float4 *>(a.dbg + cb * 2 * RDSP_BLK) : nullptr;
                 for (int i = g; i < 32; i += G) {
                     const float4 yv = ld4(xb + 4 * i);
@@ -440,6 +443,7 @@ __global__ void __launch_bounds__((PACKED ? NWARPS_PACKED : NWARPS_SCALAR) * 32,
                     const int32_t q0 = f32_to_q15(f0), q1 = f32_to_q15(f1), q2 = f32_to_q15(f2), q3 = f32_to_q15(f3);
                     if (a.out_mono) dst_mono[i] = make_int2((int)mk16(q0, q1), (int)mk16(q2, q3));     // RDSP_AUDIO_MONO: L only
                     else dst[i] = make_int4((int)mk16(q0, q0), (int)mk16(q1, q1), (int)mk16(q2, q2), (int)mk16(q3, q3));
+                    if (RING) dst_ring[i] = make_int2((int)mk16(q0, q1), (int)mk16(q2, q3));
                     if (dbg) {
                         dbg[2 * i] = make_float4(f0, f0, f1, f1);
                         dbg[2 * i + 1] = make_float4(f2, f2, f3, f3);
@@ -520,9 +524,17 @@ void launch_nlms(const NlmsArgs &a, cudaStream_t st)
     const int nw = (G == 8 && packed) ? NWARPS_PACKED : NWARPS_SCALAR;
     const int cpb = nw * (32 / G);
     const int grid = (a.n_list + cpb - 1) / cpb;
-    RDSP_CARVEOUT_ONCE((k_nlms<4, false>)); RDSP_CARVEOUT_ONCE((k_nlms<8, false>)); RDSP_CARVEOUT_ONCE((k_nlms<8, true>));
+    RDSP_CARVEOUT_ONCE((k_nlms<4, false, false>)); RDSP_CARVEOUT_ONCE((k_nlms<8, false, false>)); RDSP_CARVEOUT_ONCE((k_nlms<8, true, false>));
+    RDSP_CARVEOUT_ONCE((k_nlms<4, false, true>)); RDSP_CARVEOUT_ONCE((k_nlms<8, false, true>)); RDSP_CARVEOUT_ONCE((k_nlms<8, true, true>));
+    const bool ring = a.mode == 1 && a.ring != nullptr;                     // one-block calls: the DNR appends its rows to the audio-spectrum ring
     // (G = 4 packed measured slower than G = 4 scalar everywhere: cfg5 0.565 vs 0.530 ms for G = 8 packed, cfg4a 0.381 vs 0.333)
-    if (G == 4) rdsp_launch(k_nlms<4, false>, grid, nw * 32, 0, st, a.pdl != 0, a);
-    else if (packed) rdsp_launch(k_nlms<8, true>, grid, nw * 32, 0, st, a.pdl != 0, a);
-    else rdsp_launch(k_nlms<8, false>, grid, nw * 32, 0, st, a.pdl != 0, a);
+    if (ring) {
+        if (G == 4) rdsp_launch(k_nlms<4, false, true>, grid, nw * 32, 0, st, a.pdl != 0, a);
+        else if (packed) rdsp_launch(k_nlms<8, true, true>, grid, nw * 32, 0, st, a.pdl != 0, a);
+        else rdsp_launch(k_nlms<8, false, true>, grid, nw * 32, 0, st, a.pdl != 0, a);
+    } else {
+        if (G == 4) rdsp_launch(k_nlms<4, false, false>, grid, nw * 32, 0, st, a.pdl != 0, a);
+        else if (packed) rdsp_launch(k_nlms<8, true, false>, grid, nw * 32, 0, st, a.pdl != 0, a);
+        else rdsp_launch(k_nlms<8, false, false>, grid, nw * 32, 0, st, a.pdl != 0, a);
+    }
 }

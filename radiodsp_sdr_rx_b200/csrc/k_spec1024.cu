@@ -12,7 +12,10 @@
 // the magnitudes.  Two shared-memory round trips and barriers instead of five (the per-butterfly arithmetic is the one of
 // fft_q15.cuh, so the result is bit-identical); element i sits at i + 4 (i >> 6), which keeps all three access patterns
 // conflict free.  Twiddles and the window come through L1.  The last 8 blocks of L live in an HBM ring [C][8][128]
-// indexed by tick mod 8; ticks that do not complete a frame only append their block.
+// indexed by tick mod 8; ticks that do not complete a frame only append their block.  In one-block calls (the sketch's calling
+// pattern) the kernels that emit the audio append the row themselves (k_fftfilt / k_nlms, `ring`) and this kernel is launched
+// as k_spec1024<true>, which returns at once on the three ticks out of four that complete no frame (r02d: 102.3 -> 98.3 us per
+// one-block call).
 #include "rdsp_common.cuh"
 #include "fft_q15.cuh"
 #include "kernels.h"
@@ -83,6 +86,9 @@ __device__ __forceinline__ void fft1024_passes(int2 (&x)[4][4], int2 *s_fft, con
 #ifndef RDSP_SPEC1024_MINB
 #define RDSP_SPEC1024_MINB 16    // 64 registers, no spills (r02b A/B on one box, cfg5 step: 10 / 12 / 14 / 16 CTAs per SM = 417.7 / 416.7 / 414.3 / 413.6 us; alone 96.9 / 94.4 / 92.1 / 91.6 us)
 #endif
+// APPENDED: one-block calls, where the kernels that emitted the audio appended the row to the ring themselves (`ring` of FftFiltArgs /
+// NlmsArgs): nothing to do on the three ticks out of four that complete no frame
+template <bool APPENDED>
 __global__ void __launch_bounds__(NT, RDSP_SPEC1024_MINB) k_spec1024(Spec1024Args a)
 {
     __shared__ __align__(16) int2 s_fft[1024 + 64];               // unpacked (re, im), element i at PP(i)
@@ -97,11 +103,12 @@ __global__ void __launch_bounds__(NT, RDSP_SPEC1024_MINB) k_spec1024(Spec1024Arg
 
     const unsigned long long tick0 = a.tick_in->tick;
     if (blockIdx.x == 0 && tid == 0) a.tick_out->tick = tick0 + (unsigned long long)a.T;
+    if (APPENDED && !(tick0 >= 7ull && ((tick0 - 7ull) & 3ull) == 0ull)) return;
     pdl_wait_predecessor();                                       // the audio rows are the predecessor's output
     for (int t = 0; t < a.T; t++) {
         const unsigned long long tick = tick0 + t;
         const int slot = (int)(tick & 7ull);
-        if (tid < 32) {                                             // append L of this block: 4 frames per lane
+        if (tid < 32 && !APPENDED) {                                // append L of this block: 4 frames per lane
             if (a.audio_mono) {
                 gring[slot * 32 + tid] = *reinterpret_cast<const uint2 *>(a.audio + ((size_t)t * a.C + ch) * RDSP_BLK + tid * 4);
             } else {
@@ -158,6 +165,8 @@ __global__ void __launch_bounds__(NT, RDSP_SPEC1024_MINB) k_spec1024(Spec1024Arg
 
 void launch_spec1024(const Spec1024Args &a, cudaStream_t st)
 {
-    RDSP_CARVEOUT_ONCE(k_spec1024);
-    if (a.n > 0) rdsp_launch(k_spec1024, a.n, NT, 0, st, a.pdl != 0, a);
+    RDSP_CARVEOUT_ONCE(k_spec1024<false>); RDSP_CARVEOUT_ONCE(k_spec1024<true>);
+    if (a.n <= 0) return;
+    if (a.appended) rdsp_launch(k_spec1024<true>, a.n, NT, 0, st, a.pdl != 0, a);
+    else rdsp_launch(k_spec1024<false>, a.n, NT, 0, st, a.pdl != 0, a);
 }

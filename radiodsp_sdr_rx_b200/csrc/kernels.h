@@ -102,6 +102,8 @@ struct NlmsArgs {
     uint8_t *first;             // [C] 1 until the instance ran once (RDSP_noise_reduction.h:69 statics)
     const RdspChanParams *par;
     int mode;                   // 0 = notch (output error), 1 = DNR (output estimate)
+    int16_t *ring;              // one-block calls (mode 1): [C][8][128] ring of K10; the kernel appends its own L row (slot = tick mod 8) ...
+    const RdspTick *tick_in;    // ... tick index of this call's block; both nullptr otherwise
     int contended;              // 1: other kernels run beside this one (spectrum branches): the FFMA2 form pays (fewer issue slots)
     int direct;                 // 1: the sample-by-sample cross-check kernel (k_nlms_direct.cu; RDSP_NLMS_IMPL=direct at create)
     int pdl;                    // launched as a programmatic dependent of the kernel before it on the stream
@@ -146,6 +148,8 @@ struct FftFiltArgs {
     int ch0, n;
     int nr_stage;               // RDSP_STAGE_NR present
     int pdl;                    // launched as a programmatic dependent of the kernel before it on the stream
+    int16_t *ring;              // one-block calls: [C][8][128] ring of K10; channels whose audio this kernel emits append their L row ...
+    const RdspTick *tick_in;    // ... at slot = tick mod 8; both nullptr otherwise
 };
 void launch_fftfilt(const FftFiltArgs &a, cudaStream_t st);
 
@@ -194,6 +198,7 @@ struct Spec1024Args {
     const int2 *tw;             // [3072]
     const int16_t *win;         // [1024] Hann
     int pdl;                    // launched as a programmatic dependent of the kernel before it on the stream
+    int appended;               // one-block calls: the kernels that emitted the audio appended the row already (FftFiltArgs / NlmsArgs ring)
 };
 void launch_spec1024(const Spec1024Args &a, cudaStream_t st);
 

@@ -494,6 +494,11 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
     // short calls: every kernel of a chain is a programmatic dependent of the one before it (kernels.h); `first` marks the kernel
     // that follows an event wait (no kernel in front of it on its stream)
     const int pdl = (piped && T <= h->pdl_max_T) ? 1 : 0;
+    // one-block calls (the sketch's calling pattern): the kernel that emits a channel's audio — the DNR, else the FFT filter — also
+    // appends the row to the ring of the audio spectrum, whose own kernel then has nothing to do on the three ticks out of four that
+    // complete no frame (it exits on its first instruction instead of launching a CTA per channel to copy 256 bytes).  Only with one
+    // block per call: a frame reads the eight newest rows, and rows appended ahead of it would overwrite the oldest of them.
+    const bool fused_append = T == 1 && ff && has(h, RDSP_STAGE_SPEC1024) && !h->nlms_direct;
     auto run_chain = [&](cudaStream_t cs, int cls, int c0, int c1, cudaEvent_t *marks, int *n_marks) -> int {
         auto mark = [&](int k) { if (marks && piped && h->spec_after >= 2) { cudaEventRecord(marks[k], cs); if (*n_marks < k + 1) *n_marks = k + 1; } };
         bool first = true;                                   // the chain's first kernel has no kernel before it on `cs`
@@ -540,6 +545,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
             f.in_mono = fe ? mono : nullptr; f.in_stereo = fe ? nullptr : iq; f.out_stereo = mono_out ? nullptr : audio; f.out_mono = mono_out ? audio : nullptr; f.out_f32_L = h->d_scr;
             f.dbg = dbg; f.last = h->d_conv_last; f.nfloor = h->d_nfloor; f.masks = h->d_masks; f.tw256 = h->d_tw256; f.sin512 = h->d_sin512;
             f.par = h->d_par; f.C = C; f.T = T; f.list = cls_list; f.ch0 = c0; f.n = cls_n; f.nr_stage = nr ? 1 : 0; f.pdl = dep();
+            if (fused_append) { f.ring = h->d_ring; f.tick_in = tick_in; }
             { Prof pr(h, KK_FFTFILT, cs); launch_fftfilt(f, cs); }
             if (cls != 1 && notch) mark(2);
             if (nr) {
@@ -553,6 +559,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
                     n.in_f32 = h->d_scr; n.out_stereo = mono_out ? nullptr : audio; n.out_mono = mono_out ? audio : nullptr; n.dbg = dbg;
                     n.coeff = h->d_dn_coeff; n.prev = h->d_dn_prev; n.energy = h->d_dn_energy; n.first = h->d_dn_first;
                     n.par = h->d_par; n.mode = 1; n.contended = nlms_contended; n.direct = h->nlms_direct; n.pdl = dep();
+                    if (fused_append) { n.ring = h->d_ring; n.tick_in = tick_in; }
                     { Prof pr(h, KK_DNR, cs); launch_nlms(n, cs); }
                     if (cls != 1 && notch) mark(3);
                 }
@@ -563,6 +570,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
             s1.audio = audio; s1.audio_mono = mono_out ? 1 : 0; s1.ring = h->d_ring; s1.output = h->d_spec1024_out; s1.C = C; s1.T = T;
             s1.list = cls_list; s1.ch0 = c0; s1.n = cls_n;
             s1.tick_in = tick_in; s1.tick_out = tick_out; s1.tw = h->d_tw; s1.win = h->d_win1024; s1.pdl = dep();
+            s1.appended = fused_append ? 1 : 0;
             { Prof pr(h, KK_SPEC1024, cs); launch_spec1024(s1, cs); }
         }
         return RDSP_OK;

@@ -464,6 +464,38 @@ def test_blocks_per_call_invariance(rd, po):
         assert np.array_equal(o, outs[0][0]) and np.array_equal(s, outs[0][1]) and np.array_equal(a, outs[0][2])
 
 
+@pytest.mark.parametrize("layout", ["stereo", "mono"])
+def test_one_block_calls_append_the_audio_row_themselves(rd, po, layout):
+    """With one block per call (the sketch's own calling pattern) the kernel that emits a channel's audio — the DNR, else the
+    FFT filter — appends the row to the ring of the audio spectrum itself, and k_spec1024 only runs on the ticks that
+    complete a frame (rdsp_gpu.cu, fused_append).  Audio, both spectra and the `ready` flags are what 8-block calls give,
+    in both audio layouts, through a parameter change in the middle (DNR off / on moves channels between the two emitters)."""
+    nc, nb = 45, 32
+    iq = bench.make_inputs("cfg5", 0, nc, nb)
+    res = []
+    for T in (8, 1):
+        cfg = rd.default_config(n_channels=nc, stage_mask=rd.STAGE_ALL, max_blocks_per_call=8, io_location=rd.IO_HOST,
+                                audio_layout=rd.AUDIO_MONO if layout == "mono" else rd.AUDIO_STEREO)
+        bank = rd.ReceiverBank(cfg)
+        for c in range(nc):
+            bank.set_mode(c, 1, rd.default_params(**bench.channel_params("cfg5", c)))
+        outs, specs = [], []
+        for b in range(0, nb, T):
+            if b == 16:
+                for c in range(0, nc, 3):
+                    p = dict(bench.channel_params("cfg5", c))
+                    p.update(nr_kind=0 if p["nr_level"] else 1, nr_level=0 if p["nr_level"] else 30)
+                    bank.set_mode(c, 1, rd.default_params(**p))
+            outs.append(bank.process_host(iq[b:b + T]))
+            if (b + T) % 8 == 0:
+                specs.append(bank.read_audio_spectrum())
+        res.append((np.concatenate(outs), specs, bank.read_spectrum()[0]))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][2], res[1][2])
+    for (s8, r8), (s1, r1) in zip(res[0][1], res[1][1]):
+        assert np.array_equal(s8, s1) and np.array_equal(r8, r1)
+    assert res[1][1][-1][0].any()
+
+
 def test_channel_range_sharding_matches_single_handle(rd, po):
     """N handles over contiguous channel ranges reproduce one handle byte for byte"""
     nc, nb = 37, 16
