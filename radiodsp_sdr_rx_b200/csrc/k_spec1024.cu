@@ -14,8 +14,8 @@
 // conflict free.  Twiddles and the window come through L1.  The last 8 blocks of L live in an HBM ring [C][8][128]
 // indexed by tick mod 8; ticks that do not complete a frame only append their block.  In one-block calls (the sketch's calling
 // pattern) the kernels that emit the audio append the row themselves (k_fftfilt / k_nlms, `ring`) and this kernel is launched
-// as k_spec1024<true>, which returns at once on the three ticks out of four that complete no frame (r02d: 102.3 -> 98.3 us per
-// one-block call).
+// as k_spec1024<true>; on the three ticks out of four that complete no frame the host (which mirrors the cadence) launches ONE
+// CTA of it, which advances the tick counter and returns (r02f: a non-frame tick 100 -> 90 us, the mean over four ticks 103 -> 100.7 us).
 #include "rdsp_common.cuh"
 #include "fft_q15.cuh"
 #include "kernels.h"
@@ -103,8 +103,10 @@ __global__ void __launch_bounds__(NT, RDSP_SPEC1024_MINB) k_spec1024(Spec1024Arg
 
     const unsigned long long tick0 = a.tick_in->tick;
     if (blockIdx.x == 0 && tid == 0) a.tick_out->tick = tick0 + (unsigned long long)a.T;
-    if (APPENDED && !(tick0 >= 7ull && ((tick0 - 7ull) & 3ull) == 0ull)) return;
     pdl_wait_predecessor();                                       // the audio rows are the predecessor's output
+    // (before the early return, not after: whatever follows this kernel on the stream — the join, the copy out — is ordered behind
+    // THIS grid only, and a programmatic dependent that returned without waiting could complete before the kernel in front of it)
+    if (APPENDED && !(tick0 >= 7ull && ((tick0 - 7ull) & 3ull) == 0ull)) return;
     for (int t = 0; t < a.T; t++) {
         const unsigned long long tick = tick0 + t;
         const int slot = (int)(tick & 7ull);

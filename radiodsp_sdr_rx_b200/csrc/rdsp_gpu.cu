@@ -36,6 +36,7 @@ struct ProfRec { int kind; cudaEvent_t e0, e1; };
 // one captured call shape (run_call)
 struct GraphEntry {
     int T; const void *iq; void *audio; int fe_cur, par; cudaStream_t st;
+    int frame;                                 // one-block calls: does this tick complete an audio-spectrum frame (else 0)
     cudaGraphExec_t exec;                      // nullptr: seen once, not captured yet
     uint64_t launches;                         // kernels in the graph
     unsigned long long last_use;
@@ -431,7 +432,11 @@ void free_all(rdsp_gpu *h)
 // (The first version cut the call along TIME instead; its timeline, tools/diag_timeline.py, showed every stage
 // paying its launch + state latency per chunk and the DNR stage of 4 chunks taking twice its one-launch time.)
 // While per-kernel profiling is on, everything runs as one group on one stream so that each kernel's time is its own.
-int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStream_t st, bool piped, int fe_cur, int par)
+// does the next call, if it covers ONE block, complete a frame of the audio spectrum?  (host mirror of the tick counter: the
+// cadence of AudioAnalyzeFFT1024 — a frame every 4 ticks from tick 7 on — is uniform over the channels)
+int one_block_frame(const rdsp_gpu *h, int T) { return (T == 1 && h->tick >= 7 && ((h->tick - 7) & 3) == 0) ? 1 : 0; }
+
+int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStream_t st, bool piped, int fe_cur, int par, int frame)
 {
     const bool fe = has(h, RDSP_STAGE_FRONTEND), notch = has(h, RDSP_STAGE_NOTCH), agc = has(h, RDSP_STAGE_AGC);
     const bool ff = has(h, RDSP_STAGE_FFTFILT), nr = has(h, RDSP_STAGE_NR);
@@ -496,7 +501,7 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
     const int pdl = (piped && T <= h->pdl_max_T) ? 1 : 0;
     // one-block calls (the sketch's calling pattern): the kernel that emits a channel's audio — the DNR, else the FFT filter — also
     // appends the row to the ring of the audio spectrum, whose own kernel then has nothing to do on the three ticks out of four that
-    // complete no frame (it exits on its first instruction instead of launching a CTA per channel to copy 256 bytes).  Only with one
+    // complete no frame (it is launched as ONE CTA that advances the tick counter, instead of a CTA per channel to copy 256 bytes).  Only with one
     // block per call: a frame reads the eight newest rows, and rows appended ahead of it would overwrite the oldest of them.
     const bool fused_append = T == 1 && ff && has(h, RDSP_STAGE_SPEC1024) && !h->nlms_direct;
     auto run_chain = [&](cudaStream_t cs, int cls, int c0, int c1, cudaEvent_t *marks, int *n_marks) -> int {
@@ -571,6 +576,9 @@ int enqueue_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStre
             s1.list = cls_list; s1.ch0 = c0; s1.n = cls_n;
             s1.tick_in = tick_in; s1.tick_out = tick_out; s1.tw = h->d_tw; s1.win = h->d_win1024; s1.pdl = dep();
             s1.appended = fused_append ? 1 : 0;
+            // ... and on the three ticks out of four that complete no frame all that is left of this kernel is the tick counter: ONE
+            // CTA (the host mirrors the cadence, and a call shape is captured per `frame`)
+            if (fused_append && !frame) s1.n = 1;
             { Prof pr(h, KK_SPEC1024, cs); launch_spec1024(s1, cs); }
         }
         return RDSP_OK;
@@ -680,12 +688,12 @@ void drop_graphs(rdsp_gpu *h)
 int run_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStream_t st)
 {
     const bool piped = !h->profiling;
-    const int fe_cur = h->fe_hist_cur, par = h->tick_par;
-    if (!h->use_graphs || h->profiling || h->timeline) return enqueue_call(h, T, iq, audio, st, piped, fe_cur, par);
+    const int fe_cur = h->fe_hist_cur, par = h->tick_par, frame = one_block_frame(h, T);
+    if (!h->use_graphs || h->profiling || h->timeline) return enqueue_call(h, T, iq, audio, st, piped, fe_cur, par, frame);
 
     GraphEntry *e = nullptr;
     for (auto &g : h->graphs)
-        if (g.T == T && g.iq == iq && g.audio == audio && g.fe_cur == fe_cur && g.par == par && g.st == st) { e = &g; break; }
+        if (g.T == T && g.iq == iq && g.audio == audio && g.fe_cur == fe_cur && g.par == par && g.st == st && g.frame == frame) { e = &g; break; }
     h->graph_clock++;
     if (e && e->exec) {
         e->last_use = h->graph_clock;
@@ -703,16 +711,16 @@ int run_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStream_t
             h->graphs.erase(h->graphs.begin() + (long)victim);
         }
         GraphEntry n{};
-        n.T = T; n.iq = iq; n.audio = audio; n.fe_cur = fe_cur; n.par = par; n.st = st; n.last_use = h->graph_clock;
+        n.T = T; n.iq = iq; n.audio = audio; n.fe_cur = fe_cur; n.par = par; n.st = st; n.frame = frame; n.last_use = h->graph_clock;
         h->graphs.push_back(n);
-        return enqueue_call(h, T, iq, audio, st, piped, fe_cur, par);
+        return enqueue_call(h, T, iq, audio, st, piped, fe_cur, par, frame);
     }
     // second sight: capture, instantiate, launch
     e->last_use = h->graph_clock;
     const uint64_t l0 = h->launches;
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    const int rc = enqueue_call(h, T, iq, audio, st, piped, fe_cur, par);
+    const int rc = enqueue_call(h, T, iq, audio, st, piped, fe_cur, par, frame);
     const cudaError_t ce = cudaStreamEndCapture(st, &graph);
     const uint64_t n_launch = h->launches - l0;
     h->launches = l0;
@@ -722,7 +730,7 @@ int run_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStream_t
         if (rc != RDSP_OK) return rc;
         h->use_graphs = false;                                   // capture not possible here (e.g. a caller stream that is itself capturing)
         drop_graphs(h);
-        return enqueue_call(h, T, iq, audio, st, piped, fe_cur, par);
+        return enqueue_call(h, T, iq, audio, st, piped, fe_cur, par, frame);
     }
     if (getenv("RDSP_GRAPH_DEBUG")) {
         // development aid: what the capture recorded (node count, kernel priorities)
@@ -748,7 +756,7 @@ int run_call(rdsp_gpu *h, int T, const int16_t *iq, int16_t *audio, cudaStream_t
         cudaGetLastError();
         h->use_graphs = false;
         drop_graphs(h);
-        return enqueue_call(h, T, iq, audio, st, piped, fe_cur, par);
+        return enqueue_call(h, T, iq, audio, st, piped, fe_cur, par, frame);
     }
     e->exec = exec;
     e->launches = n_launch;
