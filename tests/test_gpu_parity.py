@@ -496,6 +496,27 @@ def test_one_block_calls_append_the_audio_row_themselves(rd, po, layout):
     assert res[1][1][-1][0].any()
 
 
+def test_one_block_calls_mixed_with_longer_ones(rd, po):
+    """one-block calls (rows appended by the emitting kernels, k_spec1024 gated by the host's mirror of the frame cadence) and
+    longer calls (k_spec1024 appends) in any order keep ONE ring and ONE tick counter: audio and spectra equal those of 8-block calls"""
+    nc, nb = 30, 40
+    iq = bench.make_inputs("cfg5", 0, nc, nb)
+    res = []
+    for pattern in ((8,) * 5, (1, 1, 3, 1, 8, 1, 1, 1, 1, 2, 1, 5, 1, 1, 8, 1, 1, 1, 1)):
+        assert sum(pattern) == nb
+        bank = make_bank(rd, nc, rd.STAGE_ALL, max_blocks=8)
+        for c in range(nc):
+            bank.set_mode(c, 1, rd.default_params(**bench.channel_params("cfg5", c)))
+        outs, b = [], 0
+        for T in pattern:
+            outs.append(bank.process_host(iq[b:b + T]))
+            b += T
+        res.append((np.concatenate(outs), bank.read_spectrum()[0], bank.read_audio_spectrum()[0]))
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    assert res[1][2].any()
+
+
 def test_channel_range_sharding_matches_single_handle(rd, po):
     """N handles over contiguous channel ranges reproduce one handle byte for byte"""
     nc, nb = 37, 16
