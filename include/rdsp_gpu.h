@@ -203,7 +203,10 @@ int  rdsp_gpu_process_blocks(rdsp_gpu_t *h, uint32_t n_blocks, const int16_t *iq
 int  rdsp_gpu_synchronize(rdsp_gpu_t *h);
 
 /* RDSP_IO_HOST + async: copies run on the handle's own copy streams so that they overlap the kernels of the
- * neighbouring calls.  rdsp_gpu_stream_join makes the handle's stream wait (on the device, without blocking
+ * neighbouring calls (a ring of device staging buffers: two, or four for handles of short calls, max_blocks_per_call <= 4,
+ * where copy-in, kernels and copy-out of a call take about as long as each other).  A call returns after enqueue: its
+ * iq_in is read and its audio_out written later, in issue order — keep both untouched until rdsp_gpu_synchronize, or
+ * until an event recorded after rdsp_gpu_stream_join has completed.  rdsp_gpu_stream_join makes the handle's stream wait (on the device, without blocking
  * the host) for all outstanding device-to-host copies, so that an event recorded on the stream afterwards
  * covers them.  A no-op for RDSP_IO_DEVICE handles. */
 int  rdsp_gpu_stream_join(rdsp_gpu_t *h);
